@@ -1,0 +1,170 @@
+/*
+ * littlegan_b200 - C-ABI of the B200-native LittleGAN hot path.
+ *
+ * The reference (IXarea/LittleGAN) has no native ABI: every arithmetic op on its hot path is
+ * a TensorFlow-1.15 library kernel reached through Keras layers.  Each entry point below
+ * therefore cites the reference call site whose TF op it replaces.  Conventions:
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every call is asynchronous on `stream`, allocates nothing and transfers no ownership;
+ *   - return 0 on success, <0 on error (message via lg_last_error(), thread-local);
+ *   - activations are NHWC; `dtype` selects the activation storage type (LG_F32 / LG_BF16);
+ *     weights, biases, gradients of weights, statistics and losses are always fp32/fp64.
+ *
+ * Convolution family.  One 5x5 geometry, stride s in {1,2}, TF 'SAME' padding (pad = 1 for
+ * s=2, 2 for s=1), links a "big" map [N,Hb,Wb,A] and a "small" map [N,Hb/s,Wb/s,B] through a
+ * kernel W[5,5,A,B] (fp32):
+ *     fprop : small[n,i,j,b] = sum_{ky,kx,a} big[n, s*i+ky-pad, s*j+kx-pad, a] * W[ky,kx,a,b]
+ *     dgrad : big[n,Y,X,a]   = sum_{s*i+ky-pad==Y, s*j+kx-pad==X, b} small[n,i,j,b] * W[ky,kx,a,b]
+ *     wgrad : dW[ky,kx,a,b] += sum_{n,i,j} big[n, s*i+ky-pad, s*j+kx-pad, a] * small[n,i,j,b]
+ * tf.layers.Conv2D (kernel HWIO = [5,5,in=A,out=B], model.py:15) is fprop; its input gradient is
+ * dgrad.  tf.layers.Conv2DTranspose (kernel [5,5,out=A,in=B], model.py:39,86) is dgrad; its input
+ * gradient is fprop.  Both share wgrad with (big, small) = (x, dy) resp. (dy, x).
+ */
+#ifndef LITTLEGAN_B200_H_
+#define LITTLEGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_F32 0
+#define LG_BF16 1
+
+#define LG_ACT_NONE 0
+#define LG_ACT_TANH 1
+#define LG_ACT_SIGMOID 2
+
+#define LG_OK 0
+#define LG_ERR_INVALID (-1)
+#define LG_ERR_CUDA (-2)
+#define LG_ERR_UNSUPPORTED (-3)
+
+/* ABI version of this header (bumped on any signature change). */
+int lg_abi_version(void);
+/* Last error message of the calling thread ("" if none). */
+const char* lg_last_error(void);
+/* 1 if the tcgen05/TMA kernels can run on the current device (sm_100), else 0. */
+int lg_tensor_core_path_available(void);
+/* 1 if the tcgen05 path covers this geometry (op: 0 fprop, 1 dgrad, 2 wgrad), else 0. */
+#define LG_OP_FPROP 0
+#define LG_OP_DGRAD 1
+#define LG_OP_WGRAD 2
+int lg_conv2d_tc_supported(int op, int N, int Hb, int Wb, int A, int B, int stride);
+
+/* ---- convolution family (replaces TF Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter,
+ *      model.py:15,39,86 and their autodiff from eager_trainer.py:145,149,163) -------------- */
+
+/* fprop.  bias: [B] or NULL.  stats: double[N][2] (sum, sum of squares of the written values,
+ * per sample, ACCUMULATED - caller zeroes) or NULL.  use_tc: 1 = tcgen05 path (requires LG_BF16,
+ * wpack from lg_pack_conv_weights), 0 = fp32-accumulate SIMT path reading W fp32. */
+int lg_conv2d_fprop(const void* big, const float* W, const void* wpack, const float* bias,
+                    void* small_out, double* stats, int N, int Hb, int Wb, int A, int B,
+                    int stride, int dtype, int use_tc, void* stream);
+
+/* dgrad (== Conv2DTranspose forward).  bias: [A] or NULL; act: LG_ACT_NONE / LG_ACT_TANH applied
+ * after the bias; stats as above, taken on the pre-activation values. */
+int lg_conv2d_dgrad(const void* small, const float* W, const void* wpack, const float* bias,
+                    void* big_out, double* stats, int N, int Hb, int Wb, int A, int B,
+                    int stride, int act, int dtype, int use_tc, void* stream);
+
+/* wgrad.  dW [5,5,A,B] fp32 is ACCUMULATED into (caller zeroes). */
+int lg_conv2d_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb,
+                    int A, int B, int stride, int dtype, int use_tc, void* stream);
+
+/* Conv2DTranspose spelled out (thin aliases; same arithmetic as above). */
+int lg_conv2d_transpose_fprop(const void* x_small, const float* W, const void* wpack,
+                              const float* bias, void* y_big, double* stats, int N, int Hb, int Wb,
+                              int A_out, int B_in, int stride, int act, int dtype, int use_tc,
+                              void* stream);
+int lg_conv2d_transpose_dgrad(const void* dy_big, const float* W, const void* wpack,
+                              void* dx_small, int N, int Hb, int Wb, int A_out, int B_in,
+                              int stride, int dtype, int use_tc, void* stream);
+
+/* bf16 operand copies of one kernel W[25][A][B] for the tcgen05 path:
+ *   wpack = [ Wt : 25 x Apad x Bpad (b contiguous) | Wf : 25 x Bpad x Apad (a contiguous) ],
+ * Apad = round_up(A,16), Bpad = round_up(B,16), zero padded.  Returns bytes needed when
+ * wpack == NULL. */
+int64_t lg_pack_conv_weights(const float* W, void* wpack, int A, int B, void* stream);
+
+/* db[c] += sum_rows g[row, c]  (bias gradient; rows = N*H*W).  fp32 accumulate. */
+int lg_bias_grad(const void* g, float* db, int64_t rows, int C, int dtype, void* stream);
+
+/* ---- InstanceNormalization(axis=None) + LeakyReLU (instance.py:105-128, model.py:21-24,46-50,
+ *      100-102,130-131) ----------------------------------------------------------------------- */
+
+/* Per-sample sum / sum of squares of pre(z) over M elements, pre = leaky(alpha_pre)
+ * (alpha_pre = 1 -> identity); stats double[N][2] ACCUMULATED. */
+int lg_rowstats(const void* z, double* stats, int N, int64_t M, float alpha_pre, int dtype,
+                void* stream);
+
+/* out = leaky_post( gamma * (pre(z) - mu) / (sigma + eps) + beta ) [+ skip]
+ * mu, sigma from stats (population variance), gamma/beta: device scalars. */
+int lg_instnorm_act_fwd(const void* z, const double* stats, const float* gamma, const float* beta,
+                        const void* skip, void* out, int N, int64_t M, float eps, float alpha_pre,
+                        float alpha_post, int dtype, void* stream);
+
+/* Backward, pass 1: red double[N][2] += (sum dy, sum dy*xhat), dy = g * leaky_post'(y). */
+int lg_instnorm_act_bwd_reduce(const void* g, const void* z, const double* stats,
+                               const float* gamma, const float* beta, double* red, int N,
+                               int64_t M, float eps, float alpha_pre, float alpha_post, int dtype,
+                               void* stream);
+/* Backward, pass 2: dz = pre'(z) * (gamma/s) * (dy - mean(dy) - xhat*(s/sigma)*mean(dy*xhat));
+ * dgamma += sum_n red[n][1], dbeta += sum_n red[n][0] (added once, by block 0), either may be
+ * NULL. */
+int lg_instnorm_act_bwd_apply(const void* g, const void* z, const double* stats, const double* red,
+                              const float* gamma, const float* beta, void* dz, float* dgamma,
+                              float* dbeta, int N, int64_t M, float eps, float alpha_pre,
+                              float alpha_post, int dtype, void* stream);
+
+/* ---- Dense (tf.layers.Dense, model.py:62,63,83,120): C[M,N] (+)= op(A)[M,K] * op(B)[K,N] ----
+ * A is activation-typed (a_dtype), B fp32, C c_dtype.  transA: A stored [K,M]; transB: B stored
+ * [N,K].  accumulate: C += (fp32 C only; also used for split-K, caller zeroes). */
+int lg_gemm(const void* A, const float* Bm, void* C, int M, int N, int K, int transA, int transB,
+            int accumulate, int a_dtype, int c_dtype, void* stream);
+/* x[r,c] = act(x[r,c] + bias[c]) in place, fp32. */
+int lg_bias_act(float* x, const float* bias, int rows, int cols, int act, void* stream);
+
+/* ---- losses (eager_trainer.py:85-102, Keras binary_crossentropy, utils.py:47-48) ----------- */
+
+/* p [rows,cols] probabilities (post-sigmoid).  target: device [rows,cols] or NULL -> constant
+ * target_const.  loss_accum[0] += weight * mean(bce).  dlogit (may be NULL) =
+ * weight/(rows*cols) * dBCE/dp * p*(1-p)   (gradient w.r.t. the pre-sigmoid logits). */
+int lg_bce_sigmoid(const float* p, const float* target, float target_const, int rows, int cols,
+                   float weight, float* loss_accum, float* dlogit, void* stream);
+
+/* y = tanh output image, t = target image (both activation-typed, n elements).
+ * loss_accum[0] += weight * mean|t - y|  (if loss_accum != NULL);
+ * dpre (may be NULL) = (g_in + weight/n * sign(y - t)) * (1 - y^2), g_in may be NULL. */
+int lg_l1_tanh_bwd(const void* y, const void* t, const void* g_in, void* dpre, int64_t n,
+                   float weight, float* loss_accum, int dtype, void* stream);
+
+/* ---- optimiser (tf.compat.v1.train.AdamOptimizer, eager_trainer.py:28-30,164-168) ---------- */
+
+/* state: double[4] = {t, beta1^t, beta2^t, lr_t}; advances t by one and recomputes
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t).  Called once per apply_gradients. */
+int lg_adam_advance(double* state, double lr, double beta1, double beta2, void* stream);
+/* TF Adam on a flat range: optional value clip of g to [-clip, clip] (clip <= 0: none),
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps). */
+int lg_adam_apply(float* p, const float* g, float* m, float* v, int64_t n, const double* state,
+                  float beta1, float beta2, float eps, float clip, void* stream);
+
+/* ---- casts ------------------------------------------------------------------------------- */
+int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+
+/* ---- FID statistics (fid.py:169-188: np.mean / np.cov in fp64) ----------------------------- */
+
+/* X [n,d] fp32 features.  S1 double[d] += sum_r (x_r - shift); S2 double[d,d] (upper AND lower
+ * triangles) += sum_r (x_r - shift)(x_r - shift)^T.  shift double[d] (may be NULL = 0). */
+int lg_fid_accumulate(const float* X, const double* shift, double* S1, double* S2, int64_t n,
+                      int d, void* stream);
+/* mu = shift + S1/n ; sigma = (S2 - S1 S1^T / n) / (n-1)  (unbiased, np.cov default). */
+int lg_fid_finalize(const double* S1, const double* S2, const double* shift, double* mu,
+                    double* sigma, int64_t n, int d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LITTLEGAN_B200_H_ */

@@ -1,0 +1,118 @@
+// extern "C" surface: argument validation, error reporting and SIMT / tcgen05 dispatch for the
+// convolution family and the dense GEMM.  See include/littlegan_b200.h for the contracts.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+static thread_local char g_err[512] = "";
+
+void lg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int lg_abi_version(void) { return 1; }
+extern "C" const char* lg_last_error(void) { return g_err; }
+
+extern "C" int lg_tensor_core_path_available(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int lg_conv2d_tc_supported(int op, int N, int Hb, int Wb, int A, int B, int stride) {
+  return lg_tc_supported(op, Hb, Wb, A, B, stride, N);
+}
+
+static int check_geom(const char* fn, int N, int Hb, int Wb, int A, int B, int s, int dtype) {
+  if (N <= 0 || Hb <= 0 || Wb <= 0 || A <= 0 || B <= 0 || (s != 1 && s != 2) || (Hb % s) || (Wb % s) ||
+      (dtype != LG_F32 && dtype != LG_BF16)) {
+    lg_set_error("%s: invalid geometry N=%d Hb=%d Wb=%d A=%d B=%d stride=%d dtype=%d", fn, N, Hb, Wb, A, B, s,
+                 dtype);
+    return LG_ERR_INVALID;
+  }
+  return LG_OK;
+}
+
+extern "C" int lg_conv2d_fprop(const void* big, const float* W, const void* wpack, const float* bias,
+                               void* small_out, double* stats, int N, int Hb, int Wb, int A, int B, int stride,
+                               int dtype, int use_tc, void* stream) {
+  if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, dtype)) return e;
+  LG_REQUIRE(big && small_out, "NULL tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc) {
+    LG_REQUIRE(dtype == LG_BF16 && wpack, "tcgen05 path needs LG_BF16 activations and packed weights");
+    int e = lg_tc_fprop(big, wpack, bias, small_out, stats, N, Hb, Wb, A, B, stride, st);
+    if (e) return e;
+  } else {
+    LG_REQUIRE(W, "NULL weights");
+    lg_simt_fprop(big, W, bias, small_out, stats, N, Hb, Wb, A, B, stride, dtype, st);
+  }
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wpack, const float* bias,
+                               void* big_out, double* stats, int N, int Hb, int Wb, int A, int B, int stride,
+                               int act, int dtype, int use_tc, void* stream) {
+  if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, dtype)) return e;
+  LG_REQUIRE(small && big_out, "NULL tensor");
+  LG_REQUIRE(act == LG_ACT_NONE || act == LG_ACT_TANH, "unsupported activation");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc) {
+    LG_REQUIRE(dtype == LG_BF16 && wpack, "tcgen05 path needs LG_BF16 activations and packed weights");
+    int e = lg_tc_dgrad(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
+    if (e) return e;
+  } else {
+    LG_REQUIRE(W, "NULL weights");
+    lg_simt_dgrad(small, W, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, dtype, st);
+  }
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_conv2d_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A,
+                               int B, int stride, int dtype, int use_tc, void* stream) {
+  if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, dtype)) return e;
+  LG_REQUIRE(big && small && dW, "NULL tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc) {
+    LG_REQUIRE(dtype == LG_BF16, "tcgen05 path needs LG_BF16 activations");
+    int e = lg_tc_wgrad(big, small, dW, N, Hb, Wb, A, B, stride, st);
+    if (e) return e;
+  } else {
+    lg_simt_wgrad(big, small, dW, N, Hb, Wb, A, B, stride, dtype, st);
+  }
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_conv2d_transpose_fprop(const void* x_small, const float* W, const void* wpack,
+                                         const float* bias, void* y_big, double* stats, int N, int Hb, int Wb,
+                                         int A_out, int B_in, int stride, int act, int dtype, int use_tc,
+                                         void* stream) {
+  return lg_conv2d_dgrad(x_small, W, wpack, bias, y_big, stats, N, Hb, Wb, A_out, B_in, stride, act, dtype, use_tc,
+                         stream);
+}
+
+extern "C" int lg_conv2d_transpose_dgrad(const void* dy_big, const float* W, const void* wpack, void* dx_small,
+                                         int N, int Hb, int Wb, int A_out, int B_in, int stride, int dtype,
+                                         int use_tc, void* stream) {
+  return lg_conv2d_fprop(dy_big, W, wpack, nullptr, dx_small, nullptr, N, Hb, Wb, A_out, B_in, stride, dtype, use_tc,
+                         stream);
+}
+
+extern "C" int lg_gemm(const void* A, const float* Bm, void* C, int M, int N, int K, int transA, int transB,
+                       int accumulate, int a_dtype, int c_dtype, void* stream) {
+  LG_REQUIRE(A && Bm && C && M > 0 && N > 0 && K > 0, "bad arguments");
+  LG_REQUIRE(!accumulate || c_dtype == LG_F32, "accumulate needs an fp32 C");
+  lg_simt_dense(A, Bm, C, M, N, K, transA, transB, accumulate, a_dtype, c_dtype, (cudaStream_t)stream);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}

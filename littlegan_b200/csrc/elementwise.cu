@@ -1,0 +1,510 @@
+// Bandwidth-bound kernels of the LittleGAN hot path: InstanceNormalization(axis=None) statistics /
+// apply / backward, bias gradient, losses, TF-style Adam, casts and weight packing.
+// All are coalesced, 16-byte vectorised, warp-shuffle reduced; HBM is the roofline.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int N = 4; };
+template <> struct Vec<bf16>  { static constexpr int N = 8; };
+
+// 16-byte vector load/store of V elements as float[V]  (V == Vec<T>::N), or scalar when V == 1.
+template <typename T, int V>
+__device__ __forceinline__ void ldv(const T* p, float* o) {
+  if constexpr (V == 1) { o[0] = to_f(p[0]); }
+  else if constexpr (sizeof(T) == 4) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  } else {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void stv(T* p, const float* o) {
+  if constexpr (V == 1) { p[0] = from_f<T>(o[0]); }
+  else if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+}
+
+struct NormParams { float mu, inv, s_over_sigma; };
+__device__ __forceinline__ NormParams norm_params(const double* stats, int n, int64_t M, float eps) {
+  double mu = stats[2 * n] / (double)M;
+  double var = stats[2 * n + 1] / (double)M - mu * mu;
+  double sigma = var > 0.0 ? sqrt(var) : 0.0;
+  double s = sigma + (double)eps;
+  NormParams p;
+  p.mu = (float)mu; p.inv = (float)(1.0 / s); p.s_over_sigma = sigma > 0.0 ? (float)(s / sigma) : 0.f;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-sample sum / sum of squares
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(NT) rowstats_kernel(const T* __restrict__ z, double* stats, int64_t M,
+                                                      int64_t per_cta, float alpha_pre) {
+  __shared__ double sh[64];
+  const int n = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * per_cta, end = min(M, beg + per_cta);
+  const T* zp = z + (int64_t)n * M;
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
+    float v[V];
+    ldv<T, V>(zp + i, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { float u = leaky_f(v[k], alpha_pre); s1 += u; s2 += u * u; }
+  }
+  double a = s1, b = s2;
+  block_sum2(a, b, sh);
+  if (threadIdx.x == 0) { atomicAdd(&stats[2 * n], a); atomicAdd(&stats[2 * n + 1], b); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out = leaky_post(gamma * (pre(z) - mu) * inv + beta) [+ skip]
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(NT) instnorm_fwd_kernel(const T* __restrict__ z, const double* __restrict__ stats,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const T* __restrict__ skip, T* __restrict__ out, int64_t M,
+                                                          int64_t per_cta, float eps, float alpha_pre, float alpha_post) {
+  const int n = blockIdx.y;
+  const NormParams np = norm_params(stats, n, M, eps);
+  const float g = gamma[0] * np.inv, b = beta[0] - gamma[0] * np.inv * np.mu;   // y = g*u + b
+  const int64_t beg = (int64_t)blockIdx.x * per_cta, end = min(M, beg + per_cta);
+  const int64_t base = (int64_t)n * M;
+  for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
+    float v[V], o[V];
+    ldv<T, V>(z + base + i, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = leaky_f(fmaf(g, leaky_f(v[k], alpha_pre), b), alpha_post);
+    if (skip != nullptr) {
+      float sk[V];
+      ldv<T, V>(skip + base + i, sk);
+#pragma unroll
+      for (int k = 0; k < V; ++k) o[k] += sk[k];
+    }
+    stv<T, V>(out + base + i, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 1: red[n] += (sum dy, sum dy*xhat)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const T* __restrict__ gp, const T* __restrict__ z,
+                                                                 const double* __restrict__ stats,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 double* red, int64_t M, int64_t per_cta, float eps,
+                                                                 float alpha_pre, float alpha_post) {
+  __shared__ double sh[64];
+  const int n = blockIdx.y;
+  const NormParams np = norm_params(stats, n, M, eps);
+  const float ga = gamma[0], be = beta[0];
+  const int64_t beg = (int64_t)blockIdx.x * per_cta, end = min(M, beg + per_cta);
+  const int64_t base = (int64_t)n * M;
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
+    float v[V], g[V];
+    ldv<T, V>(z + base + i, v);
+    ldv<T, V>(gp + base + i, g);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float xh = (leaky_f(v[k], alpha_pre) - np.mu) * np.inv;
+      float y = fmaf(ga, xh, be);
+      float dy = g[k] * leaky_d(y, alpha_post);
+      s1 += dy; s2 += dy * xh;
+    }
+  }
+  double a = s1, b = s2;
+  block_sum2(a, b, sh);
+  if (threadIdx.x == 0) { atomicAdd(&red[2 * n], a); atomicAdd(&red[2 * n + 1], b); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 2
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restrict__ gp, const T* __restrict__ z,
+                                                                const double* __restrict__ stats, const double* __restrict__ red,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                T* __restrict__ dz, float* dgamma, float* dbeta, int N, int64_t M,
+                                                                int64_t per_cta, float eps, float alpha_pre, float alpha_post) {
+  const int n = blockIdx.y;
+  if (blockIdx.x == 0 && n == 0 && threadIdx.x < 32) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < N; i += 32) { a += red[2 * i]; b += red[2 * i + 1]; }
+    a = warp_sum(a); b = warp_sum(b);
+    if (threadIdx.x == 0) {
+      if (dbeta) atomicAdd(dbeta, (float)a);
+      if (dgamma) atomicAdd(dgamma, (float)b);
+    }
+  }
+  const NormParams np = norm_params(stats, n, M, eps);
+  const float ga = gamma[0], be = beta[0];
+  const float mdy = (float)(red[2 * n] / (double)M);
+  const float mdyx = (float)(red[2 * n + 1] / (double)M) * np.s_over_sigma;
+  const float scale = ga * np.inv;
+  const int64_t beg = (int64_t)blockIdx.x * per_cta, end = min(M, beg + per_cta);
+  const int64_t base = (int64_t)n * M;
+  for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
+    float v[V], g[V], o[V];
+    ldv<T, V>(z + base + i, v);
+    ldv<T, V>(gp + base + i, g);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float xh = (leaky_f(v[k], alpha_pre) - np.mu) * np.inv;
+      float y = fmaf(ga, xh, be);
+      float dy = g[k] * leaky_d(y, alpha_post);
+      o[k] = scale * (dy - mdy - xh * mdyx) * leaky_d(v[k], alpha_pre);
+    }
+    stv<T, V>(dz + base + i, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias gradient: db[c] += sum_rows g[row][c]
+// ------------------------------------------------------------------------------------------------
+// PERIODIC: (NT*V) % C == 0 and C % V == 0, so a thread sees the same V columns every iteration.
+template <typename T, int V, bool PERIODIC>
+__global__ void __launch_bounds__(NT) bias_grad_kernel(const T* __restrict__ g, float* db, int64_t total, int C,
+                                                       int64_t per_cta) {
+  extern __shared__ float shc[];
+  for (int c = threadIdx.x; c < C; c += NT) shc[c] = 0.f;
+  __syncthreads();
+  const int64_t beg = (int64_t)blockIdx.x * per_cta, end = min(total, beg + per_cta);
+  if constexpr (PERIODIC) {
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    const int64_t first = beg + (int64_t)threadIdx.x * V;
+    for (int64_t i = first; i < end; i += (int64_t)NT * V) {
+      float v[V];
+      ldv<T, V>(g + i, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += v[k];
+    }
+    const int c0 = (int)(first % C);
+#pragma unroll
+    for (int k = 0; k < V; ++k) atomicAdd(&shc[c0 + k], acc[k]);
+  } else {
+    for (int64_t i = beg + threadIdx.x; i < end; i += NT) atomicAdd(&shc[(int)(i % C)], to_f(g[i]));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += NT) atomicAdd(&db[c], shc[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void bias_act_kernel(float* x, const float* bias, int rows, int cols, int act) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  float v = x[i] + (bias ? bias[i % cols] : 0.f);
+  if (act == LG_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+  else if (act == LG_ACT_TANH) v = tanhf(v);
+  x[i] = v;
+}
+
+// Keras binary_crossentropy (TF 1.15 eager branch) on probabilities + sigmoid backward.
+__global__ void __launch_bounds__(NT) bce_kernel(const float* __restrict__ p, const float* __restrict__ target,
+                                                 float target_const, int n, float weight, float* loss_accum,
+                                                 float* dlogit) {
+  __shared__ double sh[64];
+  const float eps = 1e-7f, hi = 1.f - 1e-7f;
+  float s = 0.f;
+  const float scale = weight / (float)n;
+  for (int i = threadIdx.x; i < n; i += NT) {
+    float pr = p[i], t = target ? target[i] : target_const;
+    float pc = fminf(fmaxf(pr, eps), hi);
+    s += -(t * logf(pc + eps) + (1.f - t) * logf(1.f - pc + eps));
+    if (dlogit) {
+      float d = 0.f;
+      if (pr >= eps && pr <= hi) d = -(t / (pc + eps) - (1.f - t) / (1.f - pc + eps));
+      dlogit[i] = scale * d * pr * (1.f - pr);
+    }
+  }
+  double a = s, b = 0.0;
+  block_sum2(a, b, sh);
+  if (threadIdx.x == 0 && loss_accum) atomicAdd(loss_accum, (float)(a * (double)scale));
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(NT) l1_tanh_bwd_kernel(const T* __restrict__ y, const T* __restrict__ t,
+                                                         const T* __restrict__ g_in, T* __restrict__ dpre, int64_t n,
+                                                         float scale, float* loss_accum) {
+  __shared__ double sh[64];
+  float s = 0.f;
+  for (int64_t i = ((int64_t)blockIdx.x * NT + threadIdx.x) * V; i < n; i += (int64_t)gridDim.x * NT * V) {
+    float yv[V], tv[V], gv[V], o[V];
+    ldv<T, V>(y + i, yv);
+    ldv<T, V>(t + i, tv);
+    if (g_in) ldv<T, V>(g_in + i, gv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float d = yv[k] - tv[k];
+      s += fabsf(d);
+      float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      o[k] = ((g_in ? gv[k] : 0.f) + scale * sg) * (1.f - yv[k] * yv[k]);
+    }
+    if (dpre) stv<T, V>(dpre + i, o);
+  }
+  double a = s, b = 0.0;
+  block_sum2(a, b, sh);
+  if (threadIdx.x == 0 && loss_accum) atomicAdd(loss_accum, (float)(a * (double)scale));
+}
+
+__global__ void adam_advance_kernel(double* st, double lr, double b1, double b2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = st[0] + 1.0;
+    double p1 = (st[0] == 0.0 ? 1.0 : st[1]) * b1;
+    double p2 = (st[0] == 0.0 ? 1.0 : st[2]) * b2;
+    st[0] = t; st[1] = p1; st[2] = p2;
+    st[3] = lr * sqrt(1.0 - p2) / (1.0 - p1);
+  }
+}
+
+__global__ void __launch_bounds__(NT) adam_apply_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        const double* __restrict__ state, float b1, float b2,
+                                                        float eps, float clip) {
+  const float lr_t = (float)state[3];
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += stride) {
+    float gi = g[i];
+    if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = from_f<D>(to_f(s[i]));
+}
+
+// W[25][A][B] fp32 -> Wt[25][Ap][Bp] bf16 (b contiguous), Wf[25][Bp][Ap] bf16 (a contiguous)
+__global__ void pack_weights_kernel(const float* __restrict__ W, bf16* __restrict__ Wt, bf16* __restrict__ Wf, int A,
+                                    int B, int Ap, int Bp) {
+  const int64_t total = (int64_t)25 * Ap * Bp;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int b = (int)(i % Bp); int64_t t = i / Bp; int a = (int)(t % Ap); int tap = (int)(t / Ap);
+    float v = (a < A && b < B) ? W[((int64_t)tap * A + a) * B + b] : 0.f;
+    bf16 h = __float2bfloat16_rn(v);
+    Wt[i] = h;
+    Wf[((int64_t)tap * Bp + b) * Ap + a] = h;
+  }
+}
+
+inline void chunking(int64_t M, int V, int N, int64_t* per_cta, int* chunks) {
+  // ~4 vector iterations per thread, rounded so that chunk boundaries stay vector aligned
+  int64_t unit = (int64_t)NT * V;
+  int64_t per = unit * 4;
+  int64_t c = (M + per - 1) / per;
+  if (c < 1) c = 1;
+  if (c > 65535) { c = 65535; per = ((M + c - 1) / c + unit - 1) / unit * unit; c = (M + per - 1) / per; }
+  *per_cta = per; *chunks = (int)c;
+  (void)N;
+}
+
+}  // namespace
+
+#define DISPATCH_TV(dtype, M, CALL)                                       \
+  do {                                                                    \
+    if ((dtype) == LG_BF16) {                                             \
+      if ((M) % 8 == 0) { CALL(bf16, 8); } else { CALL(bf16, 1); }        \
+    } else {                                                              \
+      if ((M) % 4 == 0) { CALL(float, 4); } else { CALL(float, 1); }      \
+    }                                                                     \
+  } while (0)
+
+extern "C" int lg_rowstats(const void* z, double* stats, int N, int64_t M, float alpha_pre, int dtype,
+                           void* stream) {
+  LG_REQUIRE(z && stats && N > 0 && M > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(T, V)                                                                              \
+  {                                                                                             \
+    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                          \
+    rowstats_kernel<T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)z, stats, M, per, alpha_pre);   \
+  }
+  DISPATCH_TV(dtype, M, CALL);
+#undef CALL
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_instnorm_act_fwd(const void* z, const double* stats, const float* gamma, const float* beta,
+                                   const void* skip, void* out, int N, int64_t M, float eps, float alpha_pre,
+                                   float alpha_post, int dtype, void* stream) {
+  LG_REQUIRE(z && stats && gamma && beta && out && N > 0 && M > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(T, V)                                                                                        \
+  {                                                                                                       \
+    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                    \
+    instnorm_fwd_kernel<T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)z, stats, gamma, beta, (const T*)skip, \
+                                                          (T*)out, M, per, eps, alpha_pre, alpha_post);   \
+  }
+  DISPATCH_TV(dtype, M, CALL);
+#undef CALL
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_instnorm_act_bwd_reduce(const void* g, const void* z, const double* stats, const float* gamma,
+                                          const float* beta, double* red, int N, int64_t M, float eps,
+                                          float alpha_pre, float alpha_post, int dtype, void* stream) {
+  LG_REQUIRE(g && z && stats && gamma && beta && red && N > 0 && M > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(T, V)                                                                                          \
+  {                                                                                                         \
+    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                      \
+    instnorm_bwd_reduce_kernel<T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)g, (const T*)z, stats, gamma,    \
+                                                                 beta, red, M, per, eps, alpha_pre,         \
+                                                                 alpha_post);                               \
+  }
+  DISPATCH_TV(dtype, M, CALL);
+#undef CALL
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_instnorm_act_bwd_apply(const void* g, const void* z, const double* stats, const double* red,
+                                         const float* gamma, const float* beta, void* dz, float* dgamma,
+                                         float* dbeta, int N, int64_t M, float eps, float alpha_pre,
+                                         float alpha_post, int dtype, void* stream) {
+  LG_REQUIRE(g && z && stats && red && gamma && beta && dz && N > 0 && M > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(T, V)                                                                                            \
+  {                                                                                                           \
+    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                        \
+    instnorm_bwd_apply_kernel<T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)g, (const T*)z, stats, red, gamma,  \
+                                                                beta, (T*)dz, dgamma, dbeta, N, M, per, eps,  \
+                                                                alpha_pre, alpha_post);                       \
+  }
+  DISPATCH_TV(dtype, M, CALL);
+#undef CALL
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_bias_grad(const void* g, float* db, int64_t rows, int C, int dtype, void* stream) {
+  LG_REQUIRE(g && db && rows > 0 && C > 0 && C <= 8192, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = rows * C;
+  const int V = dtype == LG_BF16 ? 8 : 4;
+  const bool periodic = (C % V == 0) && ((NT * V) % C == 0);
+  int64_t unit = (int64_t)NT * V;
+  int64_t per = unit * 8;
+  int64_t ctas = (total + per - 1) / per;
+  int64_t cap = (int64_t)lg_num_sms() * 8;
+  if (ctas > cap) { per = ((total + cap - 1) / cap + unit - 1) / unit * unit; ctas = (total + per - 1) / per; }
+  // per must keep chunk starts on row-pattern boundaries for the periodic path: unit % C == 0 holds.
+  size_t shm = (size_t)C * sizeof(float);
+  if (dtype == LG_BF16) {
+    if (periodic) bias_grad_kernel<bf16, 8, true><<<(int)ctas, NT, shm, st>>>((const bf16*)g, db, total, C, per);
+    else bias_grad_kernel<bf16, 1, false><<<(int)ctas, NT, shm, st>>>((const bf16*)g, db, total, C, per);
+  } else {
+    if (periodic) bias_grad_kernel<float, 4, true><<<(int)ctas, NT, shm, st>>>((const float*)g, db, total, C, per);
+    else bias_grad_kernel<float, 1, false><<<(int)ctas, NT, shm, st>>>((const float*)g, db, total, C, per);
+  }
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_bias_act(float* x, const float* bias, int rows, int cols, int act, void* stream) {
+  LG_REQUIRE(x && rows > 0 && cols > 0, "bad arguments");
+  int n = rows * cols;
+  bias_act_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, bias, rows, cols, act);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_bce_sigmoid(const float* p, const float* target, float target_const, int rows, int cols,
+                              float weight, float* loss_accum, float* dlogit, void* stream) {
+  LG_REQUIRE(p && rows > 0 && cols > 0, "bad arguments");
+  bce_kernel<<<1, NT, 0, (cudaStream_t)stream>>>(p, target, target_const, rows * cols, weight, loss_accum, dlogit);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_l1_tanh_bwd(const void* y, const void* t, const void* g_in, void* dpre, int64_t n, float weight,
+                              float* loss_accum, int dtype, void* stream) {
+  LG_REQUIRE(y && t && n > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float scale = weight / (float)n;
+  int ctas = lg_num_sms() * 4;
+#define CALL(T, V)                                                                                         \
+  {                                                                                                        \
+    int64_t need = (n + (int64_t)NT * V - 1) / ((int64_t)NT * V);                                          \
+    int gsz = (int)(need < ctas ? need : ctas);                                                            \
+    l1_tanh_bwd_kernel<T, V><<<gsz, NT, 0, st>>>((const T*)y, (const T*)t, (const T*)g_in, (T*)dpre, n,    \
+                                                 scale, loss_accum);                                       \
+  }
+  DISPATCH_TV(dtype, n, CALL);
+#undef CALL
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_adam_advance(double* state, double lr, double beta1, double beta2, void* stream) {
+  LG_REQUIRE(state, "bad arguments");
+  adam_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_adam_apply(float* p, const float* g, float* m, float* v, int64_t n, const double* state,
+                             float beta1, float beta2, float eps, float clip, void* stream) {
+  LG_REQUIRE(p && g && m && v && state && n > 0, "bad arguments");
+  int64_t need = (n + NT - 1) / NT;
+  int64_t cap = (int64_t)lg_num_sms() * 8;
+  int gsz = (int)(need < cap ? need : cap);
+  adam_apply_kernel<<<gsz, NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state, beta1, beta2, eps, clip);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream) {
+  LG_REQUIRE(src && dst && n > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t need = (n + 255) / 256;
+  int64_t cap = (int64_t)lg_num_sms() * 16;
+  int gsz = (int)(need < cap ? need : cap);
+  if (src_dtype == LG_F32 && dst_dtype == LG_BF16) cast_kernel<float, bf16><<<gsz, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+  else if (src_dtype == LG_BF16 && dst_dtype == LG_F32) cast_kernel<bf16, float><<<gsz, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+  else if (src_dtype == LG_F32 && dst_dtype == LG_F32) cast_kernel<float, float><<<gsz, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else cast_kernel<bf16, bf16><<<gsz, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int64_t lg_pack_conv_weights(const float* W, void* wpack, int A, int B, void* stream) {
+  if (A <= 0 || B <= 0) { lg_set_error("lg_pack_conv_weights: bad arguments"); return LG_ERR_INVALID; }
+  const int Ap = (A + 15) / 16 * 16, Bp = (B + 15) / 16 * 16;
+  const int64_t half = (int64_t)25 * Ap * Bp;
+  if (wpack == nullptr) return 2 * half * (int64_t)sizeof(bf16);
+  if (W == nullptr) { lg_set_error("lg_pack_conv_weights: W is NULL"); return LG_ERR_INVALID; }
+  bf16* wt = (bf16*)wpack;
+  bf16* wf = wt + half;
+  int gsz = (int)((half + 255) / 256);
+  if (gsz > lg_num_sms() * 16) gsz = lg_num_sms() * 16;
+  pack_weights_kernel<<<gsz, 256, 0, (cudaStream_t)stream>>>(W, wt, wf, A, B, Ap, Bp);
+  LG_LAUNCH_CHECK();
+  return 2 * half * (int64_t)sizeof(bf16);
+}

@@ -1,0 +1,21 @@
+// Internal (non-exported) entry points shared between the translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+int lg_simt_fprop(const void* big, const float* W, const float* bias, void* out, double* stats, int N,
+                  int Hb, int Wb, int A, int B, int s, int dtype, cudaStream_t st);
+int lg_simt_dgrad(const void* small, const float* W, const float* bias, void* out, double* stats, int N,
+                  int Hb, int Wb, int A, int B, int s, int act, int dtype, cudaStream_t st);
+int lg_simt_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A, int B,
+                  int s, int dtype, cudaStream_t st);
+int lg_simt_dense(const void* A, const float* Bm, void* C, int M, int N, int K, int tA, int tB, int acc,
+                  int a_dtype, int c_dtype, cudaStream_t st);
+
+// tcgen05 / TMA path (tc_conv.cu).  Return LG_ERR_UNSUPPORTED when the geometry is not covered.
+int lg_tc_fprop(const void* big, const void* wpack, const float* bias, void* out, double* stats, int N,
+                int Hb, int Wb, int A, int B, int s, cudaStream_t st);
+int lg_tc_dgrad(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N,
+                int Hb, int Wb, int A, int B, int s, int act, cudaStream_t st);
+int lg_tc_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A, int B,
+                int s, cudaStream_t st);
+int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N);
