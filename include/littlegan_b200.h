@@ -101,29 +101,32 @@ int lg_rowstats(const void* z, double* stats, int N, int64_t M, float alpha_pre,
                 void* stream);
 
 /* out = leaky_post( gamma * (pre(z) - mu) / (sigma + eps) + beta ) [+ skip]
- * mu, sigma from stats (population variance), gamma/beta: device scalars. */
+ * mu, sigma from stats (population variance), gamma/beta: device scalars.  z (and dz below) are
+ * z_dtype, out / skip / g are dtype; (z_dtype, dtype) in {(f32,f32), (bf16,bf16), (f32,bf16)} - the
+ * last one is the fp32 dense head feeding a bf16 decoder (model.py:98-102,129-132). */
 int lg_instnorm_act_fwd(const void* z, const double* stats, const float* gamma, const float* beta,
                         const void* skip, void* out, int N, int64_t M, float eps, float alpha_pre,
-                        float alpha_post, int dtype, void* stream);
+                        float alpha_post, int z_dtype, int dtype, void* stream);
 
 /* Backward, pass 1: red double[N][2] += (sum dy, sum dy*xhat), dy = g * leaky_post'(y). */
 int lg_instnorm_act_bwd_reduce(const void* g, const void* z, const double* stats,
                                const float* gamma, const float* beta, double* red, int N,
-                               int64_t M, float eps, float alpha_pre, float alpha_post, int dtype,
-                               void* stream);
+                               int64_t M, float eps, float alpha_pre, float alpha_post, int z_dtype,
+                               int dtype, void* stream);
 /* Backward, pass 2: dz = pre'(z) * (gamma/s) * (dy - mean(dy) - xhat*(s/sigma)*mean(dy*xhat));
  * dgamma += sum_n red[n][1], dbeta += sum_n red[n][0] (added once, by block 0), either may be
  * NULL. */
 int lg_instnorm_act_bwd_apply(const void* g, const void* z, const double* stats, const double* red,
                               const float* gamma, const float* beta, void* dz, float* dgamma,
                               float* dbeta, int N, int64_t M, float eps, float alpha_pre,
-                              float alpha_post, int dtype, void* stream);
+                              float alpha_post, int z_dtype, int dtype, void* stream);
 
 /* ---- Dense (tf.layers.Dense, model.py:62,63,83,120): C[M,N] (+)= op(A)[M,K] * op(B)[K,N] ----
  * A is activation-typed (a_dtype), B fp32, C c_dtype.  transA: A stored [K,M]; transB: B stored
- * [N,K].  accumulate: C += (fp32 C only; also used for split-K, caller zeroes). */
-int lg_gemm(const void* A, const float* Bm, void* C, int M, int N, int K, int transA, int transB,
-            int accumulate, int a_dtype, int c_dtype, void* stream);
+ * [N,K].  accumulate: C += (fp32 C only; also used for split-K, caller zeroes).  bias [N] (or NULL)
+ * is added in the epilogue when accumulate == 0. */
+int lg_gemm(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K,
+            int transA, int transB, int accumulate, int a_dtype, int c_dtype, void* stream);
 /* x[r,c] = act(x[r,c] + bias[c]) in place, fp32. */
 int lg_bias_act(float* x, const float* bias, int rows, int cols, int act, void* stream);
 

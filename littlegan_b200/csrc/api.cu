@@ -108,11 +108,12 @@ extern "C" int lg_conv2d_transpose_dgrad(const void* dy_big, const float* W, con
                          stream);
 }
 
-extern "C" int lg_gemm(const void* A, const float* Bm, void* C, int M, int N, int K, int transA, int transB,
-                       int accumulate, int a_dtype, int c_dtype, void* stream) {
+extern "C" int lg_gemm(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K,
+                       int transA, int transB, int accumulate, int a_dtype, int c_dtype, void* stream) {
   LG_REQUIRE(A && Bm && C && M > 0 && N > 0 && K > 0, "bad arguments");
   LG_REQUIRE(!accumulate || c_dtype == LG_F32, "accumulate needs an fp32 C");
-  lg_simt_dense(A, Bm, C, M, N, K, transA, transB, accumulate, a_dtype, c_dtype, (cudaStream_t)stream);
+  LG_REQUIRE(!accumulate || !bias, "bias is only applied when accumulate == 0");
+  lg_simt_dense(A, Bm, bias, C, M, N, K, transA, transB, accumulate, a_dtype, c_dtype, (cudaStream_t)stream);
   LG_LAUNCH_CHECK();
   return LG_OK;
 }

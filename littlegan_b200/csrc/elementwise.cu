@@ -7,22 +7,25 @@ namespace {
 
 constexpr int NT = 256;
 
-template <typename T> struct Vec;
-template <> struct Vec<float> { static constexpr int N = 4; };
-template <> struct Vec<bf16>  { static constexpr int N = 8; };
-
-// 16-byte vector load/store of V elements as float[V]  (V == Vec<T>::N), or scalar when V == 1.
+// Vector load/store of V elements as float[V]: float x4 (16 B), bf16 x8 (16 B), bf16 x4 (8 B), or scalar.
 template <typename T, int V>
 __device__ __forceinline__ void ldv(const T* p, float* o) {
   if constexpr (V == 1) { o[0] = to_f(p[0]); }
   else if constexpr (sizeof(T) == 4) {
+    static_assert(V == 4, "float vectors are 4 wide");
     float4 v = *reinterpret_cast<const float4*>(p);
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-  } else {
+  } else if constexpr (V == 8) {
     uint4 v = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  } else {
+    static_assert(V == 4, "bf16 vectors are 4 or 8 wide");
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
   }
 }
 template <typename T, int V>
@@ -30,12 +33,18 @@ __device__ __forceinline__ void stv(T* p, const float* o) {
   if constexpr (V == 1) { p[0] = from_f<T>(o[0]); }
   else if constexpr (sizeof(T) == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-  } else {
+  } else if constexpr (V == 8) {
     uint4 v;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = v;
+  } else {
+    uint2 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<uint2*>(p) = v;
   }
 }
 
@@ -75,8 +84,8 @@ __global__ void __launch_bounds__(NT) rowstats_kernel(const T* __restrict__ z, d
 // ------------------------------------------------------------------------------------------------
 // out = leaky_post(gamma * (pre(z) - mu) * inv + beta) [+ skip]
 // ------------------------------------------------------------------------------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(NT) instnorm_fwd_kernel(const T* __restrict__ z, const double* __restrict__ stats,
+template <typename TZ, typename T, int V>
+__global__ void __launch_bounds__(NT) instnorm_fwd_kernel(const TZ* __restrict__ z, const double* __restrict__ stats,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const T* __restrict__ skip, T* __restrict__ out, int64_t M,
                                                           int64_t per_cta, float eps, float alpha_pre, float alpha_post) {
@@ -87,7 +96,7 @@ __global__ void __launch_bounds__(NT) instnorm_fwd_kernel(const T* __restrict__ 
   const int64_t base = (int64_t)n * M;
   for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
     float v[V], o[V];
-    ldv<T, V>(z + base + i, v);
+    ldv<TZ, V>(z + base + i, v);
 #pragma unroll
     for (int k = 0; k < V; ++k) o[k] = leaky_f(fmaf(g, leaky_f(v[k], alpha_pre), b), alpha_post);
     if (skip != nullptr) {
@@ -103,8 +112,8 @@ __global__ void __launch_bounds__(NT) instnorm_fwd_kernel(const T* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // backward pass 1: red[n] += (sum dy, sum dy*xhat)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const T* __restrict__ gp, const T* __restrict__ z,
+template <typename TZ, typename T, int V>
+__global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const T* __restrict__ gp, const TZ* __restrict__ z,
                                                                  const double* __restrict__ stats,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  double* red, int64_t M, int64_t per_cta, float eps,
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const T* __rest
   float s1 = 0.f, s2 = 0.f;
   for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
     float v[V], g[V];
-    ldv<T, V>(z + base + i, v);
+    ldv<TZ, V>(z + base + i, v);
     ldv<T, V>(gp + base + i, g);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
@@ -136,11 +145,11 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const T* __rest
 // ------------------------------------------------------------------------------------------------
 // backward pass 2
 // ------------------------------------------------------------------------------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restrict__ gp, const T* __restrict__ z,
+template <typename TZ, typename T, int V>
+__global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restrict__ gp, const TZ* __restrict__ z,
                                                                 const double* __restrict__ stats, const double* __restrict__ red,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                T* __restrict__ dz, float* dgamma, float* dbeta, int N, int64_t M,
+                                                                TZ* __restrict__ dz, float* dgamma, float* dbeta, int N, int64_t M,
                                                                 int64_t per_cta, float eps, float alpha_pre, float alpha_post) {
   const int n = blockIdx.y;
   if (blockIdx.x == 0 && n == 0 && threadIdx.x < 32) {
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restr
   const int64_t base = (int64_t)n * M;
   for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
     float v[V], g[V], o[V];
-    ldv<T, V>(z + base + i, v);
+    ldv<TZ, V>(z + base + i, v);
     ldv<T, V>(gp + base + i, g);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restr
       float dy = g[k] * leaky_d(y, alpha_post);
       o[k] = scale * (dy - mdy - xh * mdyx) * leaky_d(v[k], alpha_pre);
     }
-    stv<T, V>(dz + base + i, o);
+    stv<TZ, V>(dz + base + i, o);
   }
 }
 
@@ -349,18 +358,31 @@ extern "C" int lg_rowstats(const void* z, double* stats, int N, int64_t M, float
   return LG_OK;
 }
 
+// (z_dtype, dtype) -> <TZ, T, V>; a bf16 z with an fp32 out is not a combination the path uses.
+#define DISPATCH_ZT(zd, od, M, CALL)                                                 \
+  do {                                                                               \
+    if ((zd) == LG_BF16 && (od) == LG_BF16) {                                        \
+      if ((M) % 8 == 0) { CALL(bf16, bf16, 8); } else { CALL(bf16, bf16, 1); }       \
+    } else if ((zd) == LG_F32 && (od) == LG_BF16) {                                  \
+      if ((M) % 4 == 0) { CALL(float, bf16, 4); } else { CALL(float, bf16, 1); }     \
+    } else {                                                                         \
+      if ((M) % 4 == 0) { CALL(float, float, 4); } else { CALL(float, float, 1); }   \
+    }                                                                                \
+  } while (0)
+
 extern "C" int lg_instnorm_act_fwd(const void* z, const double* stats, const float* gamma, const float* beta,
                                    const void* skip, void* out, int N, int64_t M, float eps, float alpha_pre,
-                                   float alpha_post, int dtype, void* stream) {
+                                   float alpha_post, int z_dtype, int dtype, void* stream) {
   LG_REQUIRE(z && stats && gamma && beta && out && N > 0 && M > 0, "bad arguments");
+  LG_REQUIRE(!(z_dtype == LG_BF16 && dtype == LG_F32), "bf16 z with fp32 out is not supported");
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(T, V)                                                                                        \
-  {                                                                                                       \
-    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                    \
-    instnorm_fwd_kernel<T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)z, stats, gamma, beta, (const T*)skip, \
-                                                          (T*)out, M, per, eps, alpha_pre, alpha_post);   \
+#define CALL(TZ, T, V)                                                                                         \
+  {                                                                                                            \
+    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                         \
+    instnorm_fwd_kernel<TZ, T, V><<<dim3(ch, N), NT, 0, st>>>((const TZ*)z, stats, gamma, beta, (const T*)skip, \
+                                                              (T*)out, M, per, eps, alpha_pre, alpha_post);    \
   }
-  DISPATCH_TV(dtype, M, CALL);
+  DISPATCH_ZT(z_dtype, dtype, M, CALL);
 #undef CALL
   LG_LAUNCH_CHECK();
   return LG_OK;
@@ -368,17 +390,18 @@ extern "C" int lg_instnorm_act_fwd(const void* z, const double* stats, const flo
 
 extern "C" int lg_instnorm_act_bwd_reduce(const void* g, const void* z, const double* stats, const float* gamma,
                                           const float* beta, double* red, int N, int64_t M, float eps,
-                                          float alpha_pre, float alpha_post, int dtype, void* stream) {
+                                          float alpha_pre, float alpha_post, int z_dtype, int dtype, void* stream) {
   LG_REQUIRE(g && z && stats && gamma && beta && red && N > 0 && M > 0, "bad arguments");
+  LG_REQUIRE(!(z_dtype == LG_BF16 && dtype == LG_F32), "bf16 z with fp32 g is not supported");
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(T, V)                                                                                          \
-  {                                                                                                         \
-    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                      \
-    instnorm_bwd_reduce_kernel<T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)g, (const T*)z, stats, gamma,    \
-                                                                 beta, red, M, per, eps, alpha_pre,         \
-                                                                 alpha_post);                               \
+#define CALL(TZ, T, V)                                                                                       \
+  {                                                                                                          \
+    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                       \
+    instnorm_bwd_reduce_kernel<TZ, T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)g, (const TZ*)z, stats, gamma, \
+                                                                     beta, red, M, per, eps, alpha_pre,      \
+                                                                     alpha_post);                            \
   }
-  DISPATCH_TV(dtype, M, CALL);
+  DISPATCH_ZT(z_dtype, dtype, M, CALL);
 #undef CALL
   LG_LAUNCH_CHECK();
   return LG_OK;
@@ -387,17 +410,18 @@ extern "C" int lg_instnorm_act_bwd_reduce(const void* g, const void* z, const do
 extern "C" int lg_instnorm_act_bwd_apply(const void* g, const void* z, const double* stats, const double* red,
                                          const float* gamma, const float* beta, void* dz, float* dgamma,
                                          float* dbeta, int N, int64_t M, float eps, float alpha_pre,
-                                         float alpha_post, int dtype, void* stream) {
+                                         float alpha_post, int z_dtype, int dtype, void* stream) {
   LG_REQUIRE(g && z && stats && red && gamma && beta && dz && N > 0 && M > 0, "bad arguments");
+  LG_REQUIRE(!(z_dtype == LG_BF16 && dtype == LG_F32), "bf16 z with fp32 g is not supported");
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(T, V)                                                                                            \
-  {                                                                                                           \
-    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                        \
-    instnorm_bwd_apply_kernel<T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)g, (const T*)z, stats, red, gamma,  \
-                                                                beta, (T*)dz, dgamma, dbeta, N, M, per, eps,  \
-                                                                alpha_pre, alpha_post);                       \
+#define CALL(TZ, T, V)                                                                                          \
+  {                                                                                                             \
+    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                          \
+    instnorm_bwd_apply_kernel<TZ, T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)g, (const TZ*)z, stats, red,      \
+                                                                    gamma, beta, (TZ*)dz, dgamma, dbeta, N, M,  \
+                                                                    per, eps, alpha_pre, alpha_post);           \
   }
-  DISPATCH_TV(dtype, M, CALL);
+  DISPATCH_ZT(z_dtype, dtype, M, CALL);
 #undef CALL
   LG_LAUNCH_CHECK();
   return LG_OK;

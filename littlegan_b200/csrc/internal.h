@@ -8,8 +8,8 @@ int lg_simt_dgrad(const void* small, const float* W, const float* bias, void* ou
                   int Hb, int Wb, int A, int B, int s, int act, int dtype, cudaStream_t st);
 int lg_simt_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A, int B,
                   int s, int dtype, cudaStream_t st);
-int lg_simt_dense(const void* A, const float* Bm, void* C, int M, int N, int K, int tA, int tB, int acc,
-                  int a_dtype, int c_dtype, cudaStream_t st);
+int lg_simt_dense(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K, int tA,
+                  int tB, int acc, int a_dtype, int c_dtype, cudaStream_t st);
 
 // tcgen05 / TMA path (tc_conv.cu).  Return LG_ERR_UNSUPPORTED when the geometry is not covered.
 int lg_tc_fprop(const void* big, const void* wpack, const float* bias, void* out, double* stats, int N,

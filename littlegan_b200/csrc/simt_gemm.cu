@@ -247,7 +247,7 @@ struct WgradProb {
 template <typename TA, typename TC, bool TRANS_A, bool TRANS_B>
 struct DenseProb {
   static constexpr bool A_KFAST = !TRANS_A, B_KFAST = TRANS_B, HAS_STATS = false;
-  const TA* Ap; const float* Bp; TC* C; double* stats;
+  const TA* Ap; const float* Bp; const float* bias; TC* C; double* stats;
   int M, N, K, accumulate, kper;
   int kb, ke;
   struct MCtx { int m; };
@@ -270,7 +270,7 @@ struct DenseProb {
   __device__ float store(int m, int n, float v) const {
     int64_t o = (int64_t)m * N + n;
     if (accumulate) atomicAdd(reinterpret_cast<float*>(C) + o, v);   // fp32 C only (checked on host)
-    else C[o] = from_f<TC>(v);
+    else C[o] = from_f<TC>(bias ? v + bias[n] : v);
     return v;
   }
   __device__ int sample_of(int) const { return 0; }
@@ -351,10 +351,10 @@ int lg_simt_wgrad(const void* big, const void* small, float* dW, int N, int Hb, 
 }
 
 template <typename TA, typename TC, bool TRA, bool TRB>
-static int dense_t(const void* A, const float* Bm, void* C, int M, int N, int K, int accumulate,
-                   cudaStream_t st) {
+static int dense_t(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K,
+                   int accumulate, cudaStream_t st) {
   DenseProb<TA, TC, TRA, TRB> p;
-  p.Ap = (const TA*)A; p.Bp = Bm; p.C = (TC*)C; p.stats = nullptr;
+  p.Ap = (const TA*)A; p.Bp = Bm; p.bias = bias; p.C = (TC*)C; p.stats = nullptr;
   p.M = M; p.N = N; p.K = K; p.accumulate = accumulate;
   int z = 1;
   if (accumulate) {
@@ -368,19 +368,19 @@ static int dense_t(const void* A, const float* Bm, void* C, int M, int N, int K,
 }
 
 template <typename TA, typename TC>
-static int dense_tt(const void* A, const float* Bm, void* C, int M, int N, int K, int tA, int tB, int acc,
-                    cudaStream_t st) {
-  if (tA) return tB ? dense_t<TA, TC, true, true>(A, Bm, C, M, N, K, acc, st)
-                    : dense_t<TA, TC, true, false>(A, Bm, C, M, N, K, acc, st);
-  return tB ? dense_t<TA, TC, false, true>(A, Bm, C, M, N, K, acc, st)
-            : dense_t<TA, TC, false, false>(A, Bm, C, M, N, K, acc, st);
+static int dense_tt(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K, int tA,
+                    int tB, int acc, cudaStream_t st) {
+  if (tA) return tB ? dense_t<TA, TC, true, true>(A, Bm, bias, C, M, N, K, acc, st)
+                    : dense_t<TA, TC, true, false>(A, Bm, bias, C, M, N, K, acc, st);
+  return tB ? dense_t<TA, TC, false, true>(A, Bm, bias, C, M, N, K, acc, st)
+            : dense_t<TA, TC, false, false>(A, Bm, bias, C, M, N, K, acc, st);
 }
 
-int lg_simt_dense(const void* A, const float* Bm, void* C, int M, int N, int K, int tA, int tB, int acc,
-                  int a_dtype, int c_dtype, cudaStream_t st) {
+int lg_simt_dense(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K, int tA,
+                  int tB, int acc, int a_dtype, int c_dtype, cudaStream_t st) {
   if (a_dtype == LG_BF16)
-    return c_dtype == LG_BF16 ? dense_tt<bf16, bf16>(A, Bm, C, M, N, K, tA, tB, acc, st)
-                              : dense_tt<bf16, float>(A, Bm, C, M, N, K, tA, tB, acc, st);
-  return c_dtype == LG_BF16 ? dense_tt<float, bf16>(A, Bm, C, M, N, K, tA, tB, acc, st)
-                            : dense_tt<float, float>(A, Bm, C, M, N, K, tA, tB, acc, st);
+    return c_dtype == LG_BF16 ? dense_tt<bf16, bf16>(A, Bm, bias, C, M, N, K, tA, tB, acc, st)
+                              : dense_tt<bf16, float>(A, Bm, bias, C, M, N, K, tA, tB, acc, st);
+  return c_dtype == LG_BF16 ? dense_tt<float, bf16>(A, Bm, bias, C, M, N, K, tA, tB, acc, st)
+                            : dense_tt<float, float>(A, Bm, bias, C, M, N, K, tA, tB, acc, st);
 }

@@ -1,0 +1,440 @@
+"""EagerTrainer with the reference's surface (`eager_trainer.py:10-303`): losses, `_train_step`,
+`train`, `predict`, checkpoint helpers - the arithmetic of one step is a fixed schedule of
+hand-written CUDA kernels (engine.py), captured into CUDA graphs and replayed.
+
+Data parallelism (new; the reference is single-device): when torch.distributed is initialised
+each rank runs the step on its slice of the batch and the flat gradient arenas are all-reduced
+(average) over NCCL before the value-clip and the Adam update, which is the gradient of the
+global-batch mean - the reference's one-device semantics (SURVEY 8 e).
+"""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import engine as E
+from . import kernels as K
+from .utils import save_image, soft
+
+
+class OutOfRangeError(Exception):
+    """Raised by an iterator's get_next() at the end of an epoch (tf.errors.OutOfRangeError)."""
+
+
+_ALIGN = 64  # elements; every parameter starts on a 256-byte boundary inside the arenas
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class EagerTrainer:
+    def __init__(self, args, generator, discriminator, adjuster, dataset):
+        self.args = args
+        print(" - Initializing Trainer(Executor)...")
+        self.dataset = dataset
+        self.adjuster = adjuster
+        self.discriminator = discriminator
+        self.generator = generator
+        self.models = [self.discriminator, self.generator, self.adjuster]
+        self.global_epoch = 1
+        self.rt = E.Runtime(args) if torch.cuda.is_available() else None
+        for m in self.models:
+            m._rt = self.rt
+
+        # eager_trainer.py:48-63
+        self.part_groups = {
+            "Generator": [range(0, 4), range(4, 8), range(8, 22)],
+            "Discriminator": [range(0, 12), range(12, 16), range(16, 20)],
+            "Adjuster": [range(16, 20)],
+        }
+        self.part_weights = {}
+        for model in self.models:
+            name = model.__class__.__name__
+            w = model.weights
+            self.part_weights[name] = [[w[layer] for layer in group] for group in self.part_groups[name]]
+        self.all_weights = {
+            "Generator": self.generator.weights,
+            "Discriminator": self.discriminator.weights,
+            "Adjuster": [self.adjuster.weights[w] for w in range(16, 20)],
+        }
+        self._build_arenas()
+        # tf.compat.v1.train.AdamOptimizer(lr, beta_1, beta_2) x2, AdamOptimizer(lr) (eager_trainer.py:28-30)
+        self._hyper = {
+            "Generator": (args.lr, args.beta_1, args.beta_2),
+            "Discriminator": (args.lr, args.beta_1, args.beta_2),
+            "Adjuster": (args.lr, 0.9, 0.999),
+        }
+        self._static = None
+        self._graphs = {}
+        self._seen = set()
+        self._pool = None
+        self._noise_gen = None
+        if getattr(args, "result_dir", None) and getattr(args, "init_dirs", False):
+            self._init_dir()
+
+    # ------------------------------------------------------------------ parameter arenas
+    def _build_arenas(self):
+        """Re-home every trained tensor into one flat fp32 arena (D | G | A-own) with matching
+        gradient / Adam-slot arenas, so clip + all-reduce + Adam are one launch per optimiser and
+        a partition group is a contiguous range."""
+        order = [("Discriminator", self.all_weights["Discriminator"]),
+                 ("Generator", self.all_weights["Generator"]),
+                 ("Adjuster", self.all_weights["Adjuster"])]
+        off = 0
+        self._offsets = {}
+        for name, ws in order:
+            offs = []
+            for p in ws:
+                offs.append(off)
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            self._offsets[name] = offs + [off]
+        dev = order[0][1][0].device
+        self.P = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.Gd = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.M = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.V = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.adam_state = {name: torch.zeros(4, dtype=torch.float64, device=dev) for name, _ in order}
+        for name, ws in order:
+            for p, o in zip(ws, self._offsets[name]):
+                n = p.numel()
+                self.P[o:o + n].copy_(p.reshape(-1))
+                p.set_(self.P.untyped_storage(), o, p.shape)
+                p.lg_grad = self.Gd[o:o + n].view(p.shape)
+
+    def _range(self, name, batch_no):
+        """Flat [begin, end) of the tensors `_get_train_weight` selects for this step."""
+        offs = self._offsets[name]
+        a = self.args
+        if a.use_partition and batch_no % (a.partition_interval + 1) == 0:
+            groups = self.part_groups[name]
+            grp = groups[(batch_no // (a.partition_interval + 1)) % len(groups)]
+            base = 16 if name == "Adjuster" else 0
+            return offs[grp[0] - base], offs[grp[-1] - base + 1]
+        return offs[0], offs[-1]
+
+    def _get_train_weight(self, model, batch_no):
+        """eager_trainer.py:104-113."""
+        name = model.__class__.__name__
+        a = self.args
+        if a.use_partition and batch_no % (a.partition_interval + 1) == 0:
+            weights = self.part_weights[name]
+            return weights[(batch_no // (a.partition_interval + 1)) % len(weights)]
+        return self.all_weights[name]
+
+    # ------------------------------------------------------------------ losses (public, forward only)
+    @staticmethod
+    def _bce_mean(target, p):
+        p = p.float().contiguous()
+        acc = torch.zeros(1, dtype=torch.float32, device=p.device)
+        if torch.is_tensor(target):
+            target = target.float().contiguous()
+        K.bce_sigmoid(p, target, 1.0, acc, None)
+        return acc[0]
+
+    @staticmethod
+    def discriminator_loss(real_true_c, real_predict_c, real_predict_pr, fake_predict_pr):
+        """eager_trainer.py:85-91."""
+        b = EagerTrainer._bce_mean
+        return b(real_true_c, real_predict_c) * 2 + b(soft(1.0), real_predict_pr) + b(soft(0.0), fake_predict_pr)
+
+    def _l1_mean(self, image_ori, image_gen):
+        acc = torch.zeros(1, dtype=torch.float32, device=image_gen.device)
+        y = image_gen.contiguous()
+        K.l1_tanh_bwd(y, image_ori.to(y.dtype).contiguous(), None, None, 1.0, acc)
+        return acc[0]
+
+    def generator_loss(self, cond_ori, cond_disc, pr_disc, image_ori, image_gen):
+        """eager_trainer.py:93-96."""
+        b = EagerTrainer._bce_mean
+        return b(soft(1.0), pr_disc) + b(cond_ori, cond_disc) + self.args.l1_lambda * self._l1_mean(image_ori, image_gen)
+
+    def adjuster_loss(self, cond_ori, cond_disc, pr_disc, image_ori, image_adj):
+        """eager_trainer.py:98-102."""
+        return self.generator_loss(cond_ori, cond_disc, pr_disc, image_ori, image_adj)
+
+    # ------------------------------------------------------------------ the step
+    def _alloc_static(self):
+        a, rt = self.args, self.rt
+        B, H, C = a.batch_size, a.init_dim * 16, a.image_channel
+        f32 = torch.float32
+        S = {}
+        S["in_img1"] = rt.empty(B, H, H, C, dtype=f32)      # H2D staging (fp32 as the reference feeds)
+        S["in_img2"] = rt.empty(B, H, H, C, dtype=f32)
+        S["in_new"] = rt.empty(B, H, H, C, dtype=f32)
+        S["cond1"] = rt.empty(B, a.cond_dim, dtype=f32)
+        S["cond2"] = rt.empty(B, a.cond_dim, dtype=f32)
+        S["noise"] = rt.empty(B, a.noise_dim, dtype=f32)
+        S["dimg"] = rt.empty(2 * B, H, H, C)                 # [new_image ; fake_image]
+        S["img2"] = rt.empty(B, H, H, C)
+        S["aimg"] = rt.empty(2 * B, H, H, C)                 # [real_image_1 ; fake_image]
+        S["aimg_t"] = rt.empty(2 * B, H, H, C)               # [real_image_2 ; real_image_1]
+        S["acond_in"] = rt.empty(2 * B, a.cond_dim, dtype=f32)
+        S["acond_t"] = rt.empty(2 * B, a.cond_dim, dtype=f32)
+        S["loss"] = rt.zeros(4, dtype=f32)                   # gen, disc, adj
+        S["adj"] = None
+        return S
+
+    def _conv_layers(self):
+        return self.discriminator.encoder.convs + self.generator.decoder.convs + [self.generator.conv]
+
+    def _prepare_inputs(self, S):
+        """Casts / concatenations of the step inputs (part of the captured step)."""
+        B = self.args.batch_size
+        K.cast(S["in_new"], S["dimg"][:B])
+        K.cast(S["in_img2"], S["img2"])
+        K.cast(S["in_img1"], S["aimg"][:B])
+        S["aimg_t"][:B].copy_(S["img2"])
+        S["aimg_t"][B:].copy_(S["aimg"][:B])
+        # eager_trainer.py:155-156
+        S["acond_t"][:B].copy_(S["cond2"])
+        S["acond_t"][B:].copy_(S["cond1"])
+        torch.add(S["acond_t"], 1.0, out=S["acond_in"]).mul_(0.5)
+
+    def _step_body(self, S, adj_on, batch_no):
+        a, rt = self.args, self.rt
+        B = a.batch_size
+        G, D, A = self.generator, self.discriminator, self.adjuster
+        f32 = torch.float32
+        loss = S["loss"]
+        l_gen, l_disc, l_adj = loss[0:1], loss[1:2], loss[2:3]
+
+        E.refresh_packs(rt, self._conv_layers())
+        self.Gd.zero_()
+        loss.zero_()
+        self._prepare_inputs(S)
+
+        # ---- forward: G, then D on [new_image ; fake] (eager_trainer.py:134-137)
+        fake, (g_hctx, g_dctx, g_x4) = G.forward_ctx(S["noise"], S["cond2"], out=S["dimg"][B:])
+        outs, ectx = E.encoder_forward(rt, D.encoder, S["dimg"])
+        pr, c = E.disc_heads_forward(rt, D, outs[3])
+
+        # ---- losses + gradients w.r.t. the logits (eager_trainer.py:139-140)
+        dl_pr_d = rt.empty(2 * B, 1, dtype=f32)
+        dl_c_d = rt.zeros(2 * B, a.cond_dim, dtype=f32)          # fake half: no D-loss term on fake_c
+        K.bce_sigmoid(c[:B], S["cond1"], 2.0, l_disc, dl_c_d[:B])
+        K.bce_sigmoid(pr[:B], soft(1.0), 1.0, l_disc, dl_pr_d[:B])
+        K.bce_sigmoid(pr[B:], soft(0.0), 1.0, l_disc, dl_pr_d[B:])
+        dl_pr_g = rt.empty(B, 1, dtype=f32)
+        dl_c_g = rt.empty(B, a.cond_dim, dtype=f32)
+        K.bce_sigmoid(pr[B:], soft(1.0), 1.0, l_gen, dl_pr_g)
+        K.bce_sigmoid(c[B:], S["cond2"], 1.0, l_gen, dl_c_g)
+
+        # ---- disc_tape.gradient(disc_loss, D weights): both halves, no input gradient (:145)
+        g4 = E.disc_heads_backward(rt, D, outs[3], dl_pr_d, dl_c_d, wgrad=True)
+        E.encoder_backward(rt, D.encoder, ectx, g4, wgrad=True, input_grad=False)
+
+        # ---- gen_tape.gradient(gen_loss, G weights): dgrad-only through D(fake), then G (:149)
+        ectx_f = [(x[B:], z[B:], st[B:]) for (x, z, st) in ectx]
+        g4 = E.disc_heads_backward(rt, D, outs[3][B:], dl_pr_g, dl_c_g, wgrad=False)
+        g_img = E.encoder_backward(rt, D.encoder, ectx_f, g4, wgrad=False, input_grad=True)
+        dpre = torch.empty_like(fake)
+        K.l1_tanh_bwd(fake, S["img2"], g_img, dpre, a.l1_lambda, l_gen)
+        g = E.final_conv_backward(rt, G.conv, g_x4, dpre, wgrad=True)
+        g = E.decoder_backward(rt, G.decoder, g_dctx, g, wgrad=True)
+        E.head_backward(rt, G.dense, G.norm, g_hctx, g)
+
+        # ---- adjuster sub-step on 2B samples (eager_trainer.py:152-164)
+        if adj_on:
+            S["aimg"][B:].copy_(fake)
+            adj, (a_hctx, a_dctx, a_x4) = A.forward_ctx(S["aimg"], S["acond_in"])
+            outs2, ectx2 = E.encoder_forward(rt, D.encoder, adj)
+            apr, ac = E.disc_heads_forward(rt, D, outs2[3])
+            dl_pr_a = rt.empty(2 * B, 1, dtype=f32)
+            dl_c_a = rt.empty(2 * B, a.cond_dim, dtype=f32)
+            K.bce_sigmoid(apr, soft(1.0), 1.0, l_adj, dl_pr_a)
+            K.bce_sigmoid(ac, S["acond_t"], 1.0, l_adj, dl_c_a)
+            g4 = E.disc_heads_backward(rt, D, outs2[3], dl_pr_a, dl_c_a, wgrad=False)
+            g_img = E.encoder_backward(rt, D.encoder, ectx2, g4, wgrad=False, input_grad=True)
+            dpre = torch.empty_like(adj)
+            K.l1_tanh_bwd(adj, S["aimg_t"], g_img, dpre, a.l1_lambda, l_adj)
+            g = E.final_conv_backward(rt, A.conv, a_x4, dpre, wgrad=False)
+            g = E.decoder_backward(rt, A.decoder, a_dctx, g, wgrad=False)
+            E.head_backward(rt, A.dense, A.norm, a_hctx, g)
+            S["adj"] = adj
+
+        # ---- apply: A (if trained), D, G (eager_trainer.py:164-168); D grads value-clipped (:146-148)
+        dist = _dist()
+        for name in (["Adjuster"] if adj_on else []) + ["Discriminator", "Generator"]:
+            lo, hi = self._range(name, batch_no)
+            grad = self.Gd[lo:hi]
+            if dist is not None:
+                dist.all_reduce(grad, op=dist.ReduceOp.AVG)
+            lr, b1, b2 = self._hyper[name]
+            K.adam_advance(self.adam_state[name], lr, b1, b2)
+            clip = a.clip_range if (name == "Discriminator" and a.use_clip) else 0.0
+            K.adam_apply(self.P[lo:hi], grad, self.M[lo:hi], self.V[lo:hi], self.adam_state[name], b1, b2, 1e-8,
+                         clip)
+
+    def _variant(self, batch_no):
+        a = self.args
+        adj_on = bool(a.train_adj and batch_no > 10)
+        grp = None
+        if a.use_partition and batch_no % (a.partition_interval + 1) == 0:
+            grp = (batch_no // (a.partition_interval + 1)) % 3
+        return adj_on, grp
+
+    def _run_step(self, S, batch_no):
+        adj_on, grp = key = self._variant(batch_no)
+        use_graph = bool(getattr(self.args, "cuda_graph", True))
+        if not use_graph or key not in self._seen:
+            # first occurrence of a variant runs eagerly (it also warms up lazy state before capture)
+            self._seen.add(key)
+            self._step_body(S, adj_on, batch_no)
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(g, pool=self._pool):
+                self._step_body(S, adj_on, batch_no)
+            self._graphs[key] = (g, S["adj"])
+        g, adj = self._graphs[key]
+        S["adj"] = adj
+        g.replay()
+
+    def _to_static(self, dst, src):
+        if isinstance(src, np.ndarray):
+            src = torch.from_numpy(src)
+        dst.copy_(src.reshape(dst.shape), non_blocking=True)
+
+    def _train_step(self, batch_no, iterator, noise=None, new_image=None):
+        """eager_trainer.py:115-169.  `noise` / `new_image` may be injected for reproducible runs;
+        by default noise ~ N(0,1) is drawn on the device and new_image = real_image_1 (the
+        reference's unseeded augmentation, eager_trainer.py:127-131, is a later-round row)."""
+        a = self.args
+        try:
+            real_image_1, real_cond_1 = iterator.get_next()
+            real_image_2, real_cond_2 = iterator.get_next()
+        except OutOfRangeError:
+            return None,
+        if not real_cond_1.shape[0] == real_cond_2.shape[0] == a.batch_size:
+            return False,
+        if a.use_gp:
+            raise NotImplementedError("GP didn't implemented on eager mode")
+        if self.rt is None:
+            raise K._lib.LittleGANError("littlegan_b200 has no CPU path: a CUDA device is required")
+        if self._static is None:
+            self._static = self._alloc_static()
+        S = self._static
+        self._to_static(S["in_img1"], real_image_1)
+        self._to_static(S["in_img2"], real_image_2)
+        self._to_static(S["cond1"], real_cond_1)
+        self._to_static(S["cond2"], real_cond_2)
+        self._to_static(S["in_new"], real_image_1 if new_image is None else new_image)
+        if noise is None:
+            if self._noise_gen is None:
+                self._noise_gen = torch.Generator(device=self.rt.device)
+                rank = _dist().get_rank() if _dist() is not None else 0
+                self._noise_gen.manual_seed(int(getattr(a, "seed", 0)) * 1000003 + rank)
+            S["noise"].normal_(generator=self._noise_gen)
+        else:
+            self._to_static(S["noise"], noise)
+        adj_on, _ = self._variant(batch_no)
+        self._run_step(S, batch_no)
+        B = a.batch_size
+        losses = S["loss"].clone()
+        fake_image = S["dimg"][B:]
+        adj_image = S["adj"] if adj_on else None
+        return True, fake_image, adj_image, losses[0], losses[1], (losses[2] if adj_on else None)
+
+    # ------------------------------------------------------------------ epoch loop (host glue)
+    def train(self):
+        """eager_trainer.py:180-229 (loss scalars are read back every `log_every` steps only)."""
+        a = self.args
+        log_every = int(getattr(a, "log_every", 50))
+        for e in range(self.global_epoch, a.epoch + 1):
+            print("Experiment:", a.exp_name, "Epoch:", e, "Starting...")
+            self.global_epoch = e
+            iterator = self.dataset.get_new_iterator()
+            start_time = time.time()
+            for b in range(1, self.dataset.batches + 1):
+                result = self._train_step(b, iterator)
+                if result[0] is None:
+                    break
+                elif not result[0]:
+                    continue
+                if b % log_every == 0:
+                    vals = [("LossG", result[3]), ("LossD", result[4]), ("LossA", result[5])]
+                    print("  batch %d: " % b + " ".join("%s %.4f" % (k, float(v)) for k, v in vals if v is not None))
+                if getattr(a, "result_dir", None) and os.path.isdir(os.path.join(a.result_dir, "train")):
+                    if b % a.freq_gen == 0:
+                        save_image(result[1], os.path.join(a.result_dir, "train", "gen", "%d-%d.jpg" % (e, b)))
+                        if result[2] is not None:
+                            save_image(result[2], os.path.join(a.result_dir, "train", "adj", "%d-%d.jpg" % (e, b)))
+            torch.cuda.synchronize()
+            print("Time usage:", time.time() - start_time, "s")
+            if getattr(a, "result_dir", None) and os.path.isdir(os.path.join(a.result_dir, "checkpoint")):
+                self.save_checkpoint(os.path.join(a.result_dir, "checkpoint", "%d.pt" % e))
+
+    def _init_dir(self):
+        a = self.args
+        for item in [".", "train/gen", "train/adj", "test/adj", "test/gen", "test/disc", "checkpoint", "log",
+                     "sample", "evaluate/gen", "evaluate/adj", "evaluate/disc", "model"]:
+            os.makedirs(os.path.join(a.result_dir, item), exist_ok=True)
+        with open(os.path.join(a.result_dir, "config.json"), "w") as f:
+            json.dump({k: v for k, v in a.__dict__.items() if isinstance(v, (int, float, str, bool, list, type(None)))}, f)
+
+    def save_checkpoint(self, path):
+        torch.save({"P": self.P, "M": self.M, "V": self.V, "epoch": self.global_epoch,
+                    "adam": {k: v for k, v in self.adam_state.items()}}, path)
+
+    def load_checkpoint(self, path):
+        ck = torch.load(path, map_location=self.P.device)
+        self.P.copy_(ck["P"]); self.M.copy_(ck["M"]); self.V.copy_(ck["V"])
+        for k, v in ck["adam"].items():
+            self.adam_state[k].copy_(v)
+        self.global_epoch = ck["epoch"]
+
+    def export_model_checkpoint(self):
+        """eager_trainer.py:300-303: weights only."""
+        path = os.path.join(self.args.result_dir, "model", "model.pt")
+        torch.save({"P": self.P, "offsets": self._offsets}, path)
+
+    def plot(self):
+        """eager_trainer.py:247-263: parameter summary (Keras plot_model has no equivalent here)."""
+        lines = []
+        for m in [self.discriminator.encoder, self.generator.decoder, self.discriminator, self.generator,
+                  self.adjuster]:
+            lines.append("%s: %d tensors, %d parameters" % (m.__class__.__name__, len(m.weights),
+                                                            sum(w.numel() for w in m.weights)))
+        return "\n".join(lines)
+
+    # ------------------------------------------------------------------ predict
+    @torch.no_grad()
+    def predict(self, noise, cond, image, gen_image_save_path=None, json_save_path=None, adj_image_save_path=None):
+        """eager_trainer.py:265-298: 1 G + 2 D + 2 A forward passes, four MSE scalars."""
+        G, D, A = self.generator, self.discriminator, self.adjuster
+        gen_image = G([noise, cond])
+        if gen_image_save_path is not None:
+            save_image(gen_image, gen_image_save_path)
+        dev = gen_image.device
+        cond_d = (torch.from_numpy(cond) if isinstance(cond, np.ndarray) else cond).to(dev, torch.float32)
+        save = dict()
+        save["real_cond"] = cond_d
+        save["real_pr"], save["real_c"] = D(image)
+        save["fake_pr"], save["fake_c"] = D(gen_image)
+        mse = lambda t, p: float(((t - p) ** 2).mean(dim=-1).mean(dim=0))
+        save["real_pr_mse"] = mse(soft(1.0), save["real_pr"])
+        save["real_c_mse"] = mse(cond_d, save["real_c"])
+        save["fake_pr_mse"] = mse(soft(0.0), save["fake_pr"])
+        save["fake_c_mse"] = mse(cond_d, save["fake_c"])
+        for x in ["real_cond", "real_pr", "real_c", "fake_c", "fake_pr"]:
+            save[x] = torch.round(save[x] * 100).to(torch.int64).cpu().tolist()
+        if json_save_path is not None:
+            with open(json_save_path, "w") as f:
+                json.dump(save, f)
+        adj_fake_image, adj_real_image = None, None
+        if self.args.train_adj:
+            adj_real_image = A([image, cond])          # note: raw cond here, as the reference (:292)
+            adj_fake_image = A([gen_image, cond])
+            if adj_image_save_path is not None:
+                save_image(torch.cat([adj_real_image, adj_fake_image], 0), adj_image_save_path)
+        return gen_image, save, adj_real_image, adj_fake_image

@@ -1,0 +1,242 @@
+"""Forward / hand-written backward passes of the LittleGAN networks on the C-ABI kernels.
+
+The reference differentiates with tf.GradientTape (eager_trainer.py:133-163); here every pass is
+an explicit sequence of kernel launches that computes exactly the gradients the train step needs
+(13 encoder + 7 decoder conv passes per step).  A pass returns its outputs plus a
+`ctx` list of (layer input, pre-norm conv output z, per-sample statistics) for the backward.
+
+Every tensor is NHWC-contiguous; activations are `rt.act_dtype` (bf16 or fp32), the dense heads,
+statistics, losses, weight gradients and optimiser state are fp32/fp64.
+"""
+import torch
+
+from . import kernels as K
+
+
+class Runtime:
+    """Per-process execution settings derived from the config (`dtype`)."""
+
+    def __init__(self, args):
+        mode = getattr(args, "dtype", "bf16")
+        if mode not in ("bf16", "fp32"):
+            raise ValueError("dtype must be 'bf16' or 'fp32'")
+        self.act_dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+        self.alpha = float(args.leaky_alpha)
+        self.device = torch.device("cuda")
+        self.want_tc = mode == "bf16" and getattr(args, "tensor_cores", True)
+        self._tc_cache = {}
+
+    def use_tc(self, op, N, Hb, Wb, A, B, s):
+        if not self.want_tc:
+            return False
+        key = (op, N, Hb, Wb, A, B, s)
+        r = self._tc_cache.get(key)
+        if r is None:
+            r = K.tc_available() and K.tc_supported(op, N, Hb, Wb, A, B, s)
+            self._tc_cache[key] = r
+        return r
+
+    def empty(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float64):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+
+def _grad(p):
+    """Gradient slot of a parameter (a view into the trainer's flat gradient arena)."""
+    g = getattr(p, "lg_grad", None)
+    if g is None:
+        raise RuntimeError("parameter has no gradient slot; construct an EagerTrainer first")
+    return g
+
+
+def refresh_packs(rt, conv_layers):
+    """Re-derive the bf16 operand copies of the conv kernels (after any weight change)."""
+    if not rt.want_tc or not K.tc_available():
+        return
+    for layer in conv_layers:
+        if layer.wpack is None:
+            A, B = layer.kernel.shape[2], layer.kernel.shape[3]
+            layer.wpack = torch.empty(K.pack_conv_weights_bytes(A, B), dtype=torch.uint8, device=rt.device)
+        K.pack_conv_weights(layer.kernel, layer.wpack)
+
+
+# --------------------------------------------------------------------------------------------
+# encoder (model.py:18-27): 4 x [Conv2D s2 -> IN -> LeakyReLU]; dropout is the identity
+# --------------------------------------------------------------------------------------------
+def encoder_forward(rt, enc, x):
+    N = x.shape[0]
+    stats = rt.zeros(4, N, 2)
+    outs, ctx = [], []
+    for i in range(4):
+        conv, norm = enc.convs[i], enc.norms[i]
+        _, Hb, Wb, A = x.shape
+        B = conv.filters
+        z = rt.empty(N, Hb // 2, Wb // 2, B)
+        tc = rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, 2)
+        K.conv2d_fprop(x, conv.kernel, conv.bias, z, stats[i], 2, conv.wpack, tc)
+        a = rt.empty(N, Hb // 2, Wb // 2, B)
+        K.instnorm_act_fwd(z, stats[i], norm.gamma, norm.beta, None, a, norm.epsilon, 1.0, rt.alpha)
+        ctx.append((x, z, stats[i]))
+        outs.append(a)
+        x = a
+    return outs, ctx
+
+
+def encoder_backward(rt, enc, ctx, g, wgrad, input_grad):
+    """g: gradient w.r.t. the last encoder output.  wgrad: accumulate kernel/bias/gamma/beta
+    gradients.  Returns the gradient w.r.t. the encoder input if `input_grad`."""
+    N = g.shape[0]
+    red = rt.zeros(4, N, 2)
+    for i in (3, 2, 1, 0):
+        conv, norm = enc.convs[i], enc.norms[i]
+        x, z, stats = ctx[i]
+        dz = torch.empty_like(z)
+        K.instnorm_act_bwd(g.view_as(z), z, stats, norm.gamma, norm.beta, red[i], dz,
+                           _grad(norm.gamma) if wgrad else None, _grad(norm.beta) if wgrad else None,
+                           norm.epsilon, 1.0, rt.alpha)
+        _, Hb, Wb, A = x.shape
+        B = conv.filters
+        if wgrad:
+            K.bias_grad(dz, _grad(conv.bias))
+            K.conv2d_wgrad(x, dz, _grad(conv.kernel), 2, rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2))
+        if i > 0 or input_grad:
+            g = torch.empty_like(x)
+            K.conv2d_dgrad(dz, conv.kernel, None, g, None, 2, K.ACT_NONE, conv.wpack,
+                           rt.use_tc(K.OP_DGRAD, N, Hb, Wb, A, B, 2))
+        else:
+            g = None
+    return g
+
+
+# --------------------------------------------------------------------------------------------
+# decoder (model.py:43-51): 4 x [(+skip) -> Conv2DTranspose s2 -> IN -> LeakyReLU]
+# `skips_after[i]` is added to the OUTPUT of layer i (i.e. it is the reference's add[i+1]);
+# add[0] is folded into whatever produced the decoder input.
+# --------------------------------------------------------------------------------------------
+def decoder_forward(rt, dec, x, skips_after=(None, None, None)):
+    N = x.shape[0]
+    stats = rt.zeros(4, N, 2)
+    ctx = []
+    for i in range(4):
+        conv, norm = dec.convs[i], dec.norms[i]
+        _, Hs, Ws, B = x.shape
+        A = conv.filters
+        z = rt.empty(N, 2 * Hs, 2 * Ws, A)
+        tc = rt.use_tc(K.OP_DGRAD, N, 2 * Hs, 2 * Ws, A, B, 2)
+        K.conv2d_dgrad(x, conv.kernel, conv.bias, z, stats[i], 2, K.ACT_NONE, conv.wpack, tc)
+        a = torch.empty_like(z)
+        skip = skips_after[i] if i < 3 else None
+        K.instnorm_act_fwd(z, stats[i], norm.gamma, norm.beta, skip, a, norm.epsilon, 1.0, rt.alpha)
+        ctx.append((x, z, stats[i]))
+        x = a
+    return x, ctx
+
+
+def decoder_backward(rt, dec, ctx, g, wgrad):
+    """Returns the gradient w.r.t. the decoder input (always needed: the heads sit below)."""
+    N = g.shape[0]
+    red = rt.zeros(4, N, 2)
+    for i in (3, 2, 1, 0):
+        conv, norm = dec.convs[i], dec.norms[i]
+        x, z, stats = ctx[i]
+        dz = torch.empty_like(z)
+        K.instnorm_act_bwd(g, z, stats, norm.gamma, norm.beta, red[i], dz,
+                           _grad(norm.gamma) if wgrad else None, _grad(norm.beta) if wgrad else None,
+                           norm.epsilon, 1.0, rt.alpha)
+        _, Hb, Wb, A = z.shape
+        B = x.shape[3]
+        if wgrad:
+            K.bias_grad(dz, _grad(conv.bias))
+            K.conv2d_wgrad(dz, x, _grad(conv.kernel), 2, rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2))
+        g = torch.empty_like(x)
+        K.conv2d_fprop(dz, conv.kernel, None, g, None, 2, conv.wpack, rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, 2))
+    return g
+
+
+# --------------------------------------------------------------------------------------------
+# final Conv2DTranspose(image_channel, k, stride 1, tanh) (model.py:86,104)
+# --------------------------------------------------------------------------------------------
+def final_conv_forward(rt, conv, x, out=None):
+    N, H, W, B = x.shape
+    A = conv.filters
+    if out is None:
+        out = rt.empty(N, H, W, A)
+    K.conv2d_dgrad(x, conv.kernel, conv.bias, out, None, 1, K.ACT_TANH, conv.wpack,
+                   rt.use_tc(K.OP_DGRAD, N, H, W, A, B, 1))
+    return out
+
+
+def final_conv_backward(rt, conv, x, dpre, wgrad):
+    """dpre: gradient w.r.t. the pre-tanh output.  Returns the gradient w.r.t. x."""
+    N, H, W, B = x.shape
+    A = conv.filters
+    if wgrad:
+        K.bias_grad(dpre, _grad(conv.bias))
+        K.conv2d_wgrad(dpre, x, _grad(conv.kernel), 1, rt.use_tc(K.OP_WGRAD, N, H, W, A, B, 1))
+    g = torch.empty_like(x)
+    K.conv2d_fprop(dpre, conv.kernel, None, g, None, 1, conv.wpack, rt.use_tc(K.OP_FPROP, N, H, W, A, B, 1))
+    return g
+
+
+# --------------------------------------------------------------------------------------------
+# dense -> LeakyReLU -> IN head of Generator / Adjuster (model.py:98-102, 129-132); fp32 inside
+# --------------------------------------------------------------------------------------------
+def head_forward(rt, dense, norm, xin, out_shape, skip=None):
+    N, Kin = xin.shape
+    F = dense.units
+    h = rt.empty(N, F, dtype=torch.float32)
+    K.gemm(xin, dense.kernel, h, N, F, Kin, bias=dense.bias)
+    stats = rt.zeros(N, 2)
+    K.rowstats(h, stats, rt.alpha)
+    out = rt.empty(*out_shape)
+    K.instnorm_act_fwd(h, stats, norm.gamma, norm.beta, skip, out, norm.epsilon, rt.alpha, 1.0)
+    return out, (xin, h, stats)
+
+
+def head_backward(rt, dense, norm, ctx, g):
+    xin, h, stats = ctx
+    N, Kin = xin.shape
+    F = dense.units
+    red = rt.zeros(N, 2)
+    dh = torch.empty_like(h)
+    K.instnorm_act_bwd(g.view(N, F), h, stats, norm.gamma, norm.beta, red, dh, _grad(norm.gamma), _grad(norm.beta),
+                       norm.epsilon, rt.alpha, 1.0)
+    K.bias_grad(dh, _grad(dense.bias))
+    K.gemm(xin, dh, _grad(dense.kernel), Kin, F, N, transA=True, accumulate=True)
+
+
+# --------------------------------------------------------------------------------------------
+# discriminator heads (model.py:62-63,70-72): flatten(HWC) -> Dense(1, sigmoid), Dense(cond, sigmoid)
+# --------------------------------------------------------------------------------------------
+def disc_heads_forward(rt, disc, feat):
+    N = feat.shape[0]
+    f = feat.view(N, -1)
+    F = f.shape[1]
+    outs = []
+    for dense in (disc.dense_pr, disc.dense_cond):
+        o = rt.zeros(N, dense.units, dtype=torch.float32)
+        K.gemm(f, dense.kernel, o, N, dense.units, F, accumulate=True)
+        K.bias_act(o, dense.bias, K.ACT_SIGMOID)
+        outs.append(o)
+    return outs[0], outs[1]
+
+
+def disc_heads_backward(rt, disc, feat, dl_pr, dl_c, wgrad):
+    """dl_*: gradients w.r.t. the pre-sigmoid logits (fp32).  Returns d(feat)."""
+    N = feat.shape[0]
+    f = feat.view(N, -1)
+    F = f.shape[1]
+    df = rt.zeros(N, F, dtype=torch.float32)
+    for dense, dl in ((disc.dense_pr, dl_pr), (disc.dense_cond, dl_c)):
+        if dl is None:
+            continue
+        U = dense.units
+        if wgrad:
+            K.gemm(f, dl, _grad(dense.kernel), F, U, N, transA=True, accumulate=True)
+            K.bias_grad(dl, _grad(dense.bias))
+        K.gemm(dl, dense.kernel, df, N, F, U, transB=True, accumulate=True)
+    if rt.act_dtype == torch.float32:
+        return df.view_as(feat)
+    return K.cast(df, torch.empty_like(feat))

@@ -1,0 +1,128 @@
+"""FID feature statistics and Frechet distance (reference `fid.py:73-188`).
+
+`calculate_activation_statistics` keeps the reference's signature; the statistics pass is a
+streaming fp64 accumulation of sum(x) and sum(x x^T) on the GPU (csrc/fid.cu) instead of
+materialising the [N, 2048] fp64 activation matrix and calling np.mean / np.cov
+(`fid.py:95,186-187`).  With torch.distributed initialised every rank accumulates its shard and
+the (n, S1, S2) triple is all-reduced once (SURVEY 8 e).
+
+The Inception-2015 pool_3 forward itself (`fid.py:36-106`) needs an external weight download and
+is a later-round row: `sess` here is any callable mapping an image batch
+[b,H,W,3] (0..255) to a CUDA fp32 feature matrix [b,d]; pass `sess=None` with a 2-D input to
+feed precomputed activations.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from . import kernels as K
+
+
+class InvalidFIDException(Exception):
+    pass
+
+
+class FeatureStatistics:
+    """Streaming accumulator: update(X[b,d] fp32 cuda) ... finalize() -> (mu, sigma) fp64."""
+
+    def __init__(self, d, device=None, shift=None):
+        dev = device or torch.device("cuda")
+        self.d, self.n = d, 0
+        self.S1 = torch.zeros(d, dtype=torch.float64, device=dev)
+        self.S2 = torch.zeros(d, d, dtype=torch.float64, device=dev)
+        self.shift = None if shift is None else shift.to(dev, torch.float64).contiguous()
+
+    def update(self, X):
+        if X.dim() != 2 or X.shape[1] != self.d:
+            raise ValueError("expected features of shape [b, %d]" % self.d)
+        X = X.to(torch.float32).contiguous()
+        if self.shift is None:
+            # centre on the first batch's mean: removes the cancellation in S2 - n mu mu^T
+            self.shift = X.double().mean(dim=0).contiguous()
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.broadcast(self.shift, src=0)
+        K.fid_accumulate(X, self.shift, self.S1, self.S2)
+        self.n += X.shape[0]
+
+    def finalize(self):
+        import torch.distributed as dist
+        n = self.n
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            cnt = torch.tensor([n], dtype=torch.float64, device=self.S1.device)
+            dist.all_reduce(cnt)
+            dist.all_reduce(self.S1)
+            dist.all_reduce(self.S2)
+            n = int(cnt.item())
+        if n < 2:
+            raise InvalidFIDException("need at least two samples")
+        mu = torch.empty_like(self.S1)
+        sigma = torch.empty_like(self.S2)
+        K.fid_finalize(self.S1, self.S2, self.shift, mu, sigma, n)
+        return mu, sigma
+
+
+def get_activations(images, sess, batch_size=50, verbose=False):
+    """fid.py:73-106 as a generator of CUDA feature batches; the N % batch tail is dropped as in
+    the reference (`fid.py:89-94`)."""
+    d0 = images.shape[0]
+    if batch_size > d0:
+        print("warning: batch size is bigger than the data size. setting batch size to data size")
+        batch_size = d0
+    n_batches = d0 // batch_size
+    for i in range(n_batches):
+        if verbose:
+            print("\rPropagating batch %d/%d" % (i + 1, n_batches), end="", flush=True)
+        batch = images[i * batch_size:(i + 1) * batch_size]
+        if sess is None:
+            feats = batch
+        else:
+            feats = sess(batch)
+        if isinstance(feats, np.ndarray):
+            feats = torch.from_numpy(feats)
+        yield feats.reshape(batch_size, -1).to("cuda", torch.float32, non_blocking=True)
+    if verbose:
+        print(" done")
+
+
+def calculate_activation_statistics(images, sess=None, batch_size=50, verbose=False, as_numpy=True):
+    """fid.py:169-188 -> (mu [d], sigma [d,d]) in fp64."""
+    acc = None
+    for feats in get_activations(images, sess, batch_size, verbose):
+        if acc is None:
+            acc = FeatureStatistics(feats.shape[1], feats.device)
+        acc.update(feats)
+    mu, sigma = acc.finalize()
+    if as_numpy:
+        return mu.cpu().numpy(), sigma.cpu().numpy()
+    return mu, sigma
+
+
+def _trace_sqrt_product(s1, s2):
+    """Tr sqrtm(s1 s2) for symmetric PSD s1, s2 via two symmetric eigendecompositions (fp64, GPU):
+    the spectrum of s1 s2 equals that of s1^(1/2) s2 s1^(1/2)."""
+    w, v = torch.linalg.eigh(s1)
+    root = (v * w.clamp_min(0).sqrt()) @ v.T
+    m = root @ s2 @ root
+    lam = torch.linalg.eigvalsh((m + m.T) * 0.5)
+    return lam.clamp_min(0).sqrt().sum()
+
+
+def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
+    """fid.py:112-163: ||mu1-mu2||^2 + Tr s1 + Tr s2 - 2 Tr sqrtm(s1 s2), fp64 on the GPU.
+    The reference's scipy.linalg.sqrtm (Schur) is replaced by the symmetric form above; the
+    non-finite fallback (add eps*I to both covariances, `fid.py:148-152`) is kept."""
+    dev = torch.device("cuda")
+    t = lambda x: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(dev, torch.float64)
+    mu1, mu2 = torch.atleast_1d(t(mu1)), torch.atleast_1d(t(mu2))
+    sigma1, sigma2 = torch.atleast_2d(t(sigma1)), torch.atleast_2d(t(sigma2))
+    assert mu1.shape == mu2.shape, "Training and test mean vectors have different lengths"
+    assert sigma1.shape == sigma2.shape, "Training and test covariances have different dimensions"
+    diff = mu1 - mu2
+    tr = _trace_sqrt_product(sigma1, sigma2)
+    if not torch.isfinite(tr):
+        warnings.warn("fid calculation produces singular product; adding %s to diagonal of cov estimates" % eps)
+        offset = torch.eye(sigma1.shape[0], dtype=torch.float64, device=dev) * eps
+        tr = _trace_sqrt_product(sigma1 + offset, sigma2 + offset)
+    return float(diff.dot(diff) + torch.trace(sigma1) + torch.trace(sigma2) - 2 * tr)

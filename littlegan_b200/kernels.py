@@ -1,0 +1,179 @@
+"""Thin torch-tensor wrappers over the C-ABI (one Python function per entry point).
+
+PyTorch is plumbing here: device memory, streams, distributed.  Every function launches
+hand-written sm_100a kernels on torch's current CUDA stream and returns immediately.
+"""
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_SIGMOID, ACT_TANH, BF16, F32, OP_DGRAD, OP_FPROP, OP_WGRAD, check  # noqa: F401
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise _lib.LittleGANError("littlegan_b200 ops need CUDA tensors (no CPU fallback)")
+            if not t.is_contiguous():
+                raise _lib.LittleGANError("littlegan_b200 ops need contiguous (NHWC) tensors")
+
+
+def dt(t):
+    return _DT[t.dtype]
+
+
+def tc_supported(op, N, Hb, Wb, A, B, stride):
+    return bool(_lib.load().lg_conv2d_tc_supported(op, N, Hb, Wb, A, B, stride))
+
+
+def tc_available():
+    return bool(_lib.load().lg_tensor_core_path_available())
+
+
+# ------------------------------------------------------------------------------------------- conv
+def conv2d_fprop(big, W, bias, out, stats, stride, wpack=None, use_tc=False):
+    """small = conv(big): big [N,Hb,Wb,A], W [5,5,A,B] fp32, out [N,Hb/s,Wb/s,B]."""
+    _cuda(big, W, bias, out, stats, wpack)
+    N, Hb, Wb, A = big.shape
+    B = out.shape[3]
+    check(_lib.load().lg_conv2d_fprop(_p(big), _p(W), _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
+                                      stride, dt(big), int(use_tc), _st()), "lg_conv2d_fprop")
+    return out
+
+
+def conv2d_dgrad(small, W, bias, out, stats, stride, act=ACT_NONE, wpack=None, use_tc=False):
+    """big = conv_transpose(small): small [N,Hs,Ws,B], W [5,5,A,B] fp32, out [N,s*Hs,s*Ws,A]."""
+    _cuda(small, W, bias, out, stats, wpack)
+    N, Hb, Wb, A = out.shape
+    B = small.shape[3]
+    check(_lib.load().lg_conv2d_dgrad(_p(small), _p(W), _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
+                                      stride, act, dt(small), int(use_tc), _st()), "lg_conv2d_dgrad")
+    return out
+
+
+def conv2d_wgrad(big, small, dW, stride, use_tc=False):
+    """dW[5,5,A,B] += correlation(big, small)."""
+    _cuda(big, small, dW)
+    N, Hb, Wb, A = big.shape
+    B = small.shape[3]
+    check(_lib.load().lg_conv2d_wgrad(_p(big), _p(small), _p(dW), N, Hb, Wb, A, B, stride, dt(big), int(use_tc),
+                                      _st()), "lg_conv2d_wgrad")
+
+
+def pack_conv_weights_bytes(A, B):
+    return int(check(_lib.load().lg_pack_conv_weights(None, None, A, B, None)))
+
+
+def pack_conv_weights(W, wpack):
+    _cuda(W, wpack)
+    A, B = W.shape[2], W.shape[3]
+    check(_lib.load().lg_pack_conv_weights(_p(W), _p(wpack), A, B, _st()), "lg_pack_conv_weights")
+
+
+def bias_grad(g, db):
+    _cuda(g, db)
+    C = g.shape[-1]
+    check(_lib.load().lg_bias_grad(_p(g), _p(db), g.numel() // C, C, dt(g), _st()), "lg_bias_grad")
+
+
+# ------------------------------------------------------------------------------------------- norm
+def rowstats(z, stats, alpha_pre=1.0):
+    _cuda(z, stats)
+    N = z.shape[0]
+    check(_lib.load().lg_rowstats(_p(z), _p(stats), N, z.numel() // N, alpha_pre, dt(z), _st()), "lg_rowstats")
+
+
+def instnorm_act_fwd(z, stats, gamma, beta, skip, out, eps, alpha_pre, alpha_post):
+    _cuda(z, stats, gamma, beta, skip, out)
+    N = z.shape[0]
+    check(_lib.load().lg_instnorm_act_fwd(_p(z), _p(stats), _p(gamma), _p(beta), _p(skip), _p(out), N,
+                                          z.numel() // N, eps, alpha_pre, alpha_post, dt(z), dt(out), _st()),
+          "lg_instnorm_act_fwd")
+    return out
+
+
+def instnorm_act_bwd(g, z, stats, gamma, beta, red, dz, dgamma, dbeta, eps, alpha_pre, alpha_post):
+    """Two passes: per-sample reductions into `red` (zeroed by the caller), then dz."""
+    _cuda(g, z, stats, gamma, beta, red, dz, dgamma, dbeta)
+    N = z.shape[0]
+    M = z.numel() // N
+    lib = _lib.load()
+    check(lib.lg_instnorm_act_bwd_reduce(_p(g), _p(z), _p(stats), _p(gamma), _p(beta), _p(red), N, M, eps,
+                                         alpha_pre, alpha_post, dt(z), dt(g), _st()), "lg_instnorm_act_bwd_reduce")
+    check(lib.lg_instnorm_act_bwd_apply(_p(g), _p(z), _p(stats), _p(red), _p(gamma), _p(beta), _p(dz), _p(dgamma),
+                                        _p(dbeta), N, M, eps, alpha_pre, alpha_post, dt(z), dt(g), _st()),
+          "lg_instnorm_act_bwd_apply")
+    return dz
+
+
+# ------------------------------------------------------------------------------------------ dense
+def gemm(A, Bm, C, M, N, K, bias=None, transA=False, transB=False, accumulate=False):
+    _cuda(A, Bm, C, bias)
+    check(_lib.load().lg_gemm(_p(A), _p(Bm), _p(bias), _p(C), M, N, K, int(transA), int(transB), int(accumulate),
+                              dt(A), dt(C), _st()), "lg_gemm")
+    return C
+
+
+def bias_act(x, bias, act):
+    _cuda(x, bias)
+    rows, cols = x.shape
+    check(_lib.load().lg_bias_act(_p(x), _p(bias), rows, cols, act, _st()), "lg_bias_act")
+    return x
+
+
+# ----------------------------------------------------------------------------------------- losses
+def bce_sigmoid(p, target, weight, loss_accum, dlogit):
+    """target: tensor [rows, cols] or python float (constant target)."""
+    rows, cols = p.shape
+    tt = target if torch.is_tensor(target) else None
+    tc = 0.0 if tt is not None else float(target)
+    _cuda(p, tt, loss_accum, dlogit)
+    check(_lib.load().lg_bce_sigmoid(_p(p), _p(tt), tc, rows, cols, weight, _p(loss_accum), _p(dlogit), _st()),
+          "lg_bce_sigmoid")
+
+
+def l1_tanh_bwd(y, t, g_in, dpre, weight, loss_accum):
+    _cuda(y, t, g_in, dpre, loss_accum)
+    check(_lib.load().lg_l1_tanh_bwd(_p(y), _p(t), _p(g_in), _p(dpre), y.numel(), weight, _p(loss_accum), dt(y),
+                                     _st()), "lg_l1_tanh_bwd")
+
+
+# -------------------------------------------------------------------------------------- optimiser
+def adam_advance(state, lr, beta1, beta2):
+    _cuda(state)
+    check(_lib.load().lg_adam_advance(_p(state), lr, beta1, beta2, _st()), "lg_adam_advance")
+
+
+def adam_apply(p, g, m, v, state, beta1, beta2, eps, clip):
+    _cuda(p, g, m, v, state)
+    check(_lib.load().lg_adam_apply(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(state), beta1, beta2, eps, clip,
+                                    _st()), "lg_adam_apply")
+
+
+def cast(src, dst):
+    _cuda(src, dst)
+    check(_lib.load().lg_cast(_p(src), _p(dst), src.numel(), dt(src), dt(dst), _st()), "lg_cast")
+    return dst
+
+
+# -------------------------------------------------------------------------------------------- FID
+def fid_accumulate(X, shift, S1, S2):
+    _cuda(X, shift, S1, S2)
+    n, d = X.shape
+    check(_lib.load().lg_fid_accumulate(_p(X), _p(shift), _p(S1), _p(S2), n, d, _st()), "lg_fid_accumulate")
+
+
+def fid_finalize(S1, S2, shift, mu, sigma, n):
+    _cuda(S1, S2, shift, mu, sigma)
+    check(_lib.load().lg_fid_finalize(_p(S1), _p(S2), _p(shift), _p(mu), _p(sigma), n, S1.numel(), _st()),
+          "lg_fid_finalize")

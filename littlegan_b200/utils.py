@@ -1,0 +1,47 @@
+"""utils.py of the reference: label smoothing constant, image rescaling, grid writer.
+`soft` is on the hot path (loss targets, utils.py:47-48); the rest is host-side I/O glue."""
+import numpy as np
+import torch
+
+
+def soft(x):
+    return 0.96 * x + 0.02
+
+
+def data_rescale(x):
+    return x / 127.5 - 1
+
+
+def inverse_rescale(y):
+    return torch.round((y + 1) * 127.5) if torch.is_tensor(y) else np.round((np.asarray(y) + 1) * 127.5)
+
+
+def save_image(image, path=None, shape=(None, None)):
+    """utils.py:6-44: writes one image or a grid (column-major fill, as the reference does)."""
+    from PIL import Image
+    image = inverse_rescale(image)
+    if torch.is_tensor(image):
+        image = image.detach().float().cpu().numpy()
+    image = np.clip(image, 0, 255).astype(np.uint8)
+    if image.ndim == 4:
+        width, height = shape
+        if width is None and height is None:
+            height = int(np.ceil(np.sqrt(image.shape[0])))
+        if width is None:
+            width = int(np.ceil(image.shape[0] / height))
+        if height is None:
+            height = int(np.ceil(image.shape[0] / width))
+        ih, iw, ic = image.shape[1:4]
+        grid = np.zeros((width * ih, height * iw, ic), np.uint8)
+        for index, img in enumerate(image):
+            y, x = index // width, index % width
+            grid[x * ih:(x + 1) * ih, y * iw:(y + 1) * iw] = img
+        image = grid
+    if image.shape[2] == 1:
+        pil = Image.fromarray(image[:, :, 0], "L")
+    else:
+        pil = Image.fromarray(image, "RGB")
+    if path is None:
+        pil.show()
+    else:
+        pil.save(path)

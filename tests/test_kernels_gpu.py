@@ -1,0 +1,228 @@
+"""Per-kernel parity against the CPU oracle (fp64), through the C-ABI.  -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fid_oracle
+from oracle import littlegan_oracle as O
+from tests.util import rel_err, tol
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+# (N, Hb, Wb, A, B, stride)
+GEOMS = [
+    (2, 16, 16, 3, 8, 2),      # 3-channel edge layer
+    (3, 8, 8, 16, 24, 2),
+    (5, 4, 4, 8, 48, 2),       # tiny maps: one tile spans several samples
+    (1, 12, 12, 5, 7, 1),      # stride 1, odd channel counts
+    (2, 16, 16, 3, 32, 1),     # final-conv geometry
+    (2, 32, 32, 64, 128, 2),   # enc2 / dec3 shape at reduced resolution
+]
+
+
+def _rand(shape, seed, dtype, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(shape, generator=g, dtype=torch.float64) * scale)
+    return x.to(dtype)           # rounded to the storage type; the oracle sees the rounded values
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_fprop(geom, dtype):
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = geom
+    x = _rand((N, Hb, Wb, A), 1, dtype)
+    W = _rand((5, 5, A, B), 2, torch.float32, 0.1)
+    b = _rand((B,), 3, torch.float32)
+    ref = O.conv2d_same(x.double(), W.double(), b.double(), s)
+    out = torch.empty(N, Hb // s, Wb // s, B, dtype=dtype, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.conv2d_fprop(x.cuda(), W.cuda(), b.cuda(), out, stats, s)
+    assert rel_err(out, ref) < tol(dtype)
+    ref_stats = torch.stack([ref.reshape(N, -1).sum(1), (ref.reshape(N, -1) ** 2).sum(1)], 1)
+    assert rel_err(stats, ref_stats) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_dgrad(geom, act, dtype):
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = geom
+    x = _rand((N, Hb // s, Wb // s, B), 4, dtype)
+    W = _rand((5, 5, A, B), 5, torch.float32, 0.1)
+    b = _rand((A,), 6, torch.float32)
+    pre = O.conv2d_transpose_same(x.double(), W.double(), b.double(), s)
+    ref = torch.tanh(pre) if act else pre
+    out = torch.empty(N, Hb, Wb, A, dtype=dtype, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.conv2d_dgrad(x.cuda(), W.cuda(), b.cuda(), out, stats, s, act)
+    assert rel_err(out, ref) < tol(dtype)
+    ref_stats = torch.stack([pre.reshape(N, -1).sum(1), (pre.reshape(N, -1) ** 2).sum(1)], 1)
+    assert rel_err(stats, ref_stats) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_wgrad(geom, dtype):
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = geom
+    big = _rand((N, Hb, Wb, A), 7, dtype)
+    small = _rand((N, Hb // s, Wb // s, B), 8, dtype)
+    W = torch.zeros(5, 5, A, B, dtype=torch.float64, requires_grad=True)
+    y = O.conv2d_same(big.double(), W, torch.zeros(B, dtype=torch.float64), s)
+    (ref,) = torch.autograd.grad((y * small.double()).sum(), W)
+    dW = torch.zeros(5, 5, A, B, dtype=torch.float32, device="cuda")
+    K.conv2d_wgrad(big.cuda(), small.cuda(), dW, s)
+    assert rel_err(dW, ref) < 1e-4          # inputs are shared exactly; accumulation is fp32
+    K.conv2d_wgrad(big.cuda(), small.cuda(), dW, s)   # accumulates
+    assert rel_err(dW, 2 * ref) < 1e-4
+
+
+def test_conv_adjoint_identity():
+    """<fprop(x), y> == <x, dgrad(y)> - size-independent property, at a full-size layer."""
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = 2, 64, 64, 64, 128, 2
+    x = _rand((N, Hb, Wb, A), 11, torch.float32).cuda()
+    y = _rand((N, Hb // s, Wb // s, B), 12, torch.float32).cuda()
+    W = _rand((5, 5, A, B), 13, torch.float32, 0.05).cuda()
+    fx = torch.empty_like(y)
+    K.conv2d_fprop(x, W, None, fx, None, s)
+    dy = torch.empty_like(x)
+    K.conv2d_dgrad(y, W, None, dy, None, s)
+    lhs = (fx.double() * y.double()).sum()
+    rhs = (x.double() * dy.double()).sum()
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5
+
+
+@pytest.mark.parametrize("zdt,odt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.float32, torch.bfloat16)])
+@pytest.mark.parametrize("shape", [(3, 8, 8, 16), (2, 4, 4, 6), (4, 1030)])
+@pytest.mark.parametrize("alphas", [(1.0, 0.3), (0.3, 1.0)])
+def test_instnorm_fwd_bwd(shape, alphas, zdt, odt):
+    from littlegan_b200 import kernels as K
+    a_pre, a_post = alphas
+    N = shape[0]
+    z = _rand(shape, 20, zdt, 2.0) + 0.5
+    z = z.to(zdt)
+    skip = _rand(shape, 21, odt)
+    gout = _rand(shape, 22, odt)
+    gamma = torch.tensor([1.3]); beta = torch.tensor([-0.2])
+    zr = z.double().requires_grad_(True)
+    gr = gamma.double().requires_grad_(True); br = beta.double().requires_grad_(True)
+    u = torch.nn.functional.leaky_relu(zr, a_pre)
+    ref = torch.nn.functional.leaky_relu(O.instance_norm(u, gr, br), a_post) + skip.double()
+    dz_ref, dg_ref, db_ref = torch.autograd.grad((ref * gout.double()).sum(), [zr, gr, br])
+
+    zc = z.cuda()
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.rowstats(zc, stats, a_pre)
+    out = torch.empty(shape, dtype=odt, device="cuda")
+    K.instnorm_act_fwd(zc, stats, gamma.cuda(), beta.cuda(), skip.cuda(), out, 1e-3, a_pre, a_post)
+    assert rel_err(out, ref) < tol(odt)
+
+    red = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    dz = torch.empty_like(zc)
+    dgam = torch.zeros(1, device="cuda"); dbet = torch.zeros(1, device="cuda")
+    K.instnorm_act_bwd(gout.cuda(), zc, stats, gamma.cuda(), beta.cuda(), red, dz, dgam, dbet, 1e-3, a_pre, a_post)
+    assert rel_err(dz, dz_ref) < tol(zdt) * 2
+    assert rel_err(dgam, dg_ref) < 1e-3 and rel_err(dbet, db_ref) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,C", [(512, 64), (100, 384), (333, 3), (64, 32), (7, 1)])
+def test_bias_grad(rows, C, dtype):
+    from littlegan_b200 import kernels as K
+    g = _rand((rows, C), 30, dtype)
+    db = torch.zeros(C, device="cuda")
+    K.bias_grad(g.cuda(), db)
+    assert rel_err(db, g.double().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("tA,tB,acc", [(False, False, False), (True, False, True), (False, True, True),
+                                       (False, False, True)])
+@pytest.mark.parametrize("adt", DTYPES)
+def test_gemm(tA, tB, acc, adt):
+    from littlegan_b200 import kernels as K
+    M, N, Kd = 37, 70, 1000
+    A = _rand((Kd, M) if tA else (M, Kd), 40, adt)
+    Bm = _rand((N, Kd) if tB else (Kd, N), 41, torch.float32)
+    bias = None if acc else _rand((N,), 42, torch.float32)
+    ref = (A.double().T if tA else A.double()) @ (Bm.double().T if tB else Bm.double())
+    if bias is not None:
+        ref = ref + bias.double()
+    C = torch.zeros(M, N, device="cuda")
+    K.gemm(A.cuda(), Bm.cuda(), C, M, N, Kd, bias=None if bias is None else bias.cuda(), transA=tA, transB=tB,
+           accumulate=acc)
+    assert rel_err(C, ref) < 1e-4
+
+
+def test_bce_and_l1():
+    from littlegan_b200 import kernels as K
+    rows, cols = 6, 5
+    logits = _rand((rows, cols), 50, torch.float32, 3.0)
+    logits[0, 0] = 40.0          # saturates the sigmoid: clipped region, zero gradient
+    logits[1, 1] = -40.0
+    t = O.soft((torch.rand(rows, cols) < 0.5).float() * 2 - 1)
+    lr = logits.clone().requires_grad_(True)
+    ref = O.bce(t, torch.sigmoid(lr)) * 2.0
+    (dref,) = torch.autograd.grad(ref, lr)
+    p = torch.sigmoid(logits).cuda()
+    acc = torch.zeros(1, device="cuda"); dl = torch.empty(rows, cols, device="cuda")
+    K.bce_sigmoid(p, t.cuda(), 2.0, acc, dl)
+    assert abs(float(acc) - float(ref)) / abs(float(ref)) < 1e-5
+    assert float((dl.cpu() - dref).abs().max()) < 1e-6
+    acc.zero_()
+    K.bce_sigmoid(p, 0.98, 1.0, acc, None)
+    assert abs(float(acc) - float(O.bce(torch.full((rows, cols), 0.98), torch.sigmoid(logits)))) < 1e-5
+
+    for dtype in DTYPES:
+        y = torch.tanh(_rand((2, 8, 8, 3), 51, torch.float32)).to(dtype)
+        tgt = _rand((2, 8, 8, 3), 52, dtype)
+        gin = _rand((2, 8, 8, 3), 53, dtype)
+        pre = torch.atanh(y.double().clamp(-0.999, 0.999)).requires_grad_(True)
+        yy = torch.tanh(pre)
+        loss = 0.02 * (tgt.double() - yy).abs().mean()
+        (dref,) = torch.autograd.grad(loss + (yy * gin.double()).sum(), pre)
+        acc = torch.zeros(1, device="cuda"); dpre = torch.empty(2, 8, 8, 3, dtype=dtype, device="cuda")
+        K.l1_tanh_bwd(y.cuda(), tgt.cuda(), gin.cuda(), dpre, 0.02, acc)
+        assert abs(float(acc) - float(0.02 * (tgt.double() - y.double()).abs().mean())) < 1e-5
+        ok = y.double().abs() < 0.998
+        assert rel_err(dpre.cpu()[ok], dref[ok]) < tol(dtype)
+
+
+def test_adam_matches_tf_form():
+    from littlegan_b200 import kernels as K
+    n = 1000
+    p0 = _rand((n,), 60, torch.float32);
+    opt = O.TFAdam(5e-5, 0.5, 0.9)
+    p_ref = p0.clone().double()
+    p = p0.clone().cuda(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    state = torch.zeros(4, dtype=torch.float64, device="cuda")
+    for step in range(3):
+        g = _rand((n,), 61 + step, torch.float32)
+        opt.apply([(g.double().clamp(-0.5, 0.5), p_ref)])
+        K.adam_advance(state, 5e-5, 0.5, 0.9)
+        K.adam_apply(p, g.cuda(), m, v, state, 0.5, 0.9, 1e-8, 0.5)
+    assert float(state[0]) == 3.0
+    assert float((p.cpu().double() - p_ref).abs().max()) < 1e-7
+
+
+def test_fid_statistics_and_distance():
+    """Pinned row: np.mean / np.cov / scipy sqrtm are the reference's own arithmetic."""
+    from littlegan_b200 import fid
+    rng = np.random.RandomState(0)
+    n, d = 1037, 200
+    base = rng.randn(n, d).astype(np.float32) @ rng.randn(d, d).astype(np.float32) * 0.1 + 3.0
+    mu_ref, sig_ref = fid_oracle.activation_statistics(base[: fid_oracle.used_rows(n, 100)])
+    mu, sigma = fid.calculate_activation_statistics(torch.from_numpy(base), None, batch_size=100)
+    assert np.abs(mu - mu_ref).max() < 1e-10
+    assert np.abs(sigma - sig_ref).max() / np.abs(sig_ref).max() < 1e-10
+    assert np.abs(sigma - sigma.T).max() == 0.0
+    other = rng.randn(900, d).astype(np.float32) * 0.7 + 2.5
+    mu2, sig2 = fid_oracle.activation_statistics(other)
+    ref = fid_oracle.frechet_distance(mu_ref, sig_ref, mu2, sig2)
+    got = fid.calculate_frechet_distance(mu, sigma, mu2, sig2)
+    assert abs(got - ref) / abs(ref) < 1e-6
+    assert abs(fid.calculate_frechet_distance(mu, sigma, mu, sigma)) < 1e-6 * np.trace(sig_ref)

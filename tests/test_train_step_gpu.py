@@ -1,0 +1,163 @@
+"""End-to-end parity of the model forwards and the full train step against the CPU oracle with
+identical weights and inputs.  -m gpu."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import littlegan_oracle as O
+from tests.util import build_product, product_args, product_weights_to_oracle, rel_err, small_args, tol
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class _ListIterator:
+    def __init__(self, items):
+        self.items, self.i = items, 0
+
+    def get_next(self):
+        from littlegan_b200.eager_trainer import OutOfRangeError
+        if self.i >= len(self.items):
+            raise OutOfRangeError()
+        self.i += 1
+        return self.items[self.i - 1]
+
+
+def _setup(oargs, dtype, cuda_graph=False, seed=0):
+    from littlegan_b200.eager_trainer import EagerTrainer
+    pargs = product_args(oargs, dtype=dtype, cuda_graph=cuda_graph)
+    gen, disc, adj = build_product(pargs, seed)
+    W = product_weights_to_oracle(gen, disc, adj)
+    trainer = EagerTrainer(pargs, gen, disc, adj, None)
+    return pargs, gen, disc, adj, trainer, W
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_model_forwards(dtype):
+    oargs = small_args()
+    pargs, gen, disc, adj, trainer, W = _setup(oargs, dtype)
+    i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=3)
+    t = tol(torch.float32 if dtype == "fp32" else torch.bfloat16)
+    with torch.no_grad():
+        Wd = {k: [w.double() for w in v] for k, v in W.items()}
+        ref_img = O.generator(oargs, noise.double(), c2.double(), Wd["G"])
+        ref_pr, ref_c = O.discriminator(oargs, i1.double(), Wd["D"])
+        ref_adj = O.adjuster(oargs, i1.double(), ((c2 + 1) * 0.5).double(), Wd["D"], Wd["G"], Wd["A"])
+        ref_enc = O.encoder(oargs, i1.double(), Wd["D"][:16])
+    img = gen([noise, c2])
+    pr, c = disc(i1)
+    adj_img = adj([i1, (c2 + 1) * 0.5])
+    enc = disc.encoder(i1)
+    assert rel_err(img, ref_img) < t * 3
+    assert rel_err(pr, ref_pr) < t * 3 and rel_err(c, ref_c) < t * 3
+    assert rel_err(adj_img, ref_adj) < t * 3
+    for a, b in zip(enc, ref_enc):
+        assert rel_err(a, b) < t * 3
+
+
+def _one_step_parity(oargs, batch_no, B, t_loss, t_grad, t_w):
+    pargs, gen, disc, adj, trainer, W = _setup(oargs, "fp32")
+    ot = O.OracleTrainer(oargs, W, dtype=torch.float64)
+    i1, c1, i2, c2, noise = O.synthetic_batch(oargs, B, seed=5)
+    ref = ot.train_step(batch_no, i1, c1, i2, c2, noise, return_grads=True)
+    res = trainer._train_step(batch_no, _ListIterator([(i1, c1), (i2, c2)]), noise=noise)
+    assert res[0] is True
+    assert rel_err(res[1], ref["fake_image"]) < 1e-4
+    assert abs(float(res[3]) - float(ref["gen_loss"])) < t_loss * abs(float(ref["gen_loss"]))
+    assert abs(float(res[4]) - float(ref["disc_loss"])) < t_loss * abs(float(ref["disc_loss"]))
+    if ref["adj_loss"] is not None:
+        assert rel_err(res[2], ref["adj_image"]) < 1e-4
+        assert abs(float(res[5]) - float(ref["adj_loss"])) < t_loss * abs(float(ref["adj_loss"]))
+    else:
+        assert res[2] is None and res[5] is None
+    # gradients (the arenas keep the unclipped gradient; the oracle's D grads are clipped)
+    names = {"D": disc.weights, "G": gen.weights, "A": adj.weights[16:20]}
+    worst = 0.0
+    for key, ws in names.items():
+        if ref["grads"][key] is None:
+            continue
+        for idx, gref in ref["grads"][key].items():
+            got = ws[idx].lg_grad
+            if key == "D" and oargs.use_clip:
+                got = got.clamp(-oargs.clip_range, oargs.clip_range)
+            e = rel_err(got, gref)
+            worst = max(worst, e)
+            assert e < t_grad, (key, idx, e)
+    # updated weights
+    for key, ws in names.items():
+        for idx, w in enumerate(ws):
+            assert rel_err(w, ot.W[key][idx]) < t_w, (key, idx)
+    return worst
+
+
+@pytest.mark.parametrize("batch_no", [3, 11, 15, 20])
+def test_train_step_small_fp32(batch_no):
+    """batch 3: G+D only; 11: with adjuster; 15/20: partition groups 0 and 1 (b % 5 == 0)."""
+    oargs = small_args(use_partition=True)
+    _one_step_parity(oargs, batch_no, 4, 1e-4, 1e-4, 1e-5)
+
+
+def test_train_step_full_size_fp32():
+    """The real 128x128 architecture (cond 40), batch 2, full step with adjuster."""
+    oargs = O.make_args(cond_dim=40, batch_size=2, use_partition=False)
+    _one_step_parity(oargs, 11, 2, 1e-4, 1e-4, 1e-5)
+
+
+def test_use_gp_raises():
+    oargs = small_args(use_gp=True)
+    pargs, gen, disc, adj, trainer, W = _setup(oargs, "fp32")
+    i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=5)
+    with pytest.raises(NotImplementedError):
+        trainer._train_step(1, _ListIterator([(i1, c1), (i2, c2)]))
+
+
+def test_iterator_protocol():
+    oargs = small_args()
+    pargs, gen, disc, adj, trainer, W = _setup(oargs, "fp32")
+    i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=5)
+    assert trainer._train_step(1, _ListIterator([(i1, c1)])) == (None,)          # OutOfRange
+    assert trainer._train_step(1, _ListIterator([(i1, c1), (i2[:3], c2[:3])])) == (False,)  # short batch
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_trajectory_graph_vs_oracle(dtype):
+    """Loss trajectory over 30 steps on the reduced architecture: CUDA-graph replay path against
+    the oracle (fp32), within 1% (north_star) - crosses b>10 (adjuster on) and partition steps."""
+    oargs = small_args(use_partition=True, lr=2e-4)
+    pargs, gen, disc, adj, trainer, W = _setup(oargs, dtype, cuda_graph=True)
+    ot = O.OracleTrainer(oargs, W, dtype=torch.float32)
+    steps = 30
+    for b in range(1, steps + 1):
+        i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=100 + b)
+        ref = ot.train_step(b, i1, c1, i2, c2, noise)
+        res = trainer._train_step(b, _ListIterator([(i1, c1), (i2, c2)]), noise=noise)
+        for got, want in ((res[3], ref["gen_loss"]), (res[4], ref["disc_loss"]), (res[5], ref["adj_loss"])):
+            if want is None:
+                assert got is None
+                continue
+            assert abs(float(got) - float(want)) < 0.01 * abs(float(want)), (b, float(got), float(want))
+    assert len(trainer._graphs) >= 2     # the replay path was actually exercised
+
+
+def test_trajectory_full_size_golden():
+    """100-step G/D/A loss trajectory of the real architecture (cond 40, batch 4) against the
+    oracle's committed trajectory (tests/golden/trajectory_full.json, made by
+    tests/golden/make_golden.py), within 1%."""
+    path = os.path.join(GOLD, "trajectory_full.json")
+    if not os.path.exists(path):
+        pytest.skip("golden trajectory not generated")
+    gold = json.load(open(path))
+    oargs = O.make_args(**gold["args"])
+    for dtype in ("fp32", "bf16"):
+        pargs, gen, disc, adj, trainer, W = _setup(oargs, dtype, cuda_graph=True, seed=gold["seed"])
+        B = gold["args"]["batch_size"]
+        for b in range(1, len(gold["gen"]) + 1):
+            i1, c1, i2, c2, noise = O.synthetic_batch(oargs, B, seed=gold["data_seed"] + b)
+            res = trainer._train_step(b, _ListIterator([(i1, c1), (i2, c2)]), noise=noise)
+            want = (gold["gen"][b - 1], gold["disc"][b - 1], gold["adj"][b - 1])
+            for got, w in zip(res[3:6], want):
+                if w is None:
+                    continue
+                assert abs(float(got) - w) < 0.01 * abs(w), (dtype, b, float(got), w)
