@@ -215,6 +215,17 @@ __global__ void __launch_bounds__(NT) bias_grad_kernel(const T* __restrict__ g, 
   for (int c = threadIdx.x; c < C; c += NT) atomicAdd(&db[c], shc[c]);
 }
 
+template <typename T>
+__global__ void __launch_bounds__(NT) colsum_wide_kernel(const T* __restrict__ g, float* db, int64_t rows, int C,
+                                                         int64_t rows_per) {
+  const int c = blockIdx.x * NT + threadIdx.x;
+  if (c >= C) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) acc += to_f(g[r * C + c]);
+  atomicAdd(&db[c], acc);
+}
+
 // ------------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------------
@@ -428,9 +439,17 @@ extern "C" int lg_instnorm_act_bwd_apply(const void* g, const void* z, const dou
 }
 
 extern "C" int lg_bias_grad(const void* g, float* db, int64_t rows, int C, int dtype, void* stream) {
-  LG_REQUIRE(g && db && rows > 0 && C > 0 && C <= 8192, "bad arguments");
+  LG_REQUIRE(g && db && rows > 0 && C > 0, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = rows * C;
+  if (C > 4096) {   // wide, short matrices (the dense heads): one thread per column, coalesced over columns
+    int64_t rows_per = (rows + 7) / 8;
+    dim3 grid((C + NT - 1) / NT, (unsigned)((rows + rows_per - 1) / rows_per));
+    if (dtype == LG_BF16) colsum_wide_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)g, db, rows, C, rows_per);
+    else colsum_wide_kernel<float><<<grid, NT, 0, st>>>((const float*)g, db, rows, C, rows_per);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+  }
   const int V = dtype == LG_BF16 ? 8 : 4;
   const bool periodic = (C % V == 0) && ((NT * V) % C == 0);
   int64_t unit = (int64_t)NT * V;

@@ -1,7 +1,393 @@
-// placeholder - replaced by the tcgen05 implementation
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels (bf16 operands, fp32 accumulate).
+//
+//   fprop (OP_F): small[m=(n,i,j)][b] = sum_{tap,a} big[n, s*i+ky-pad, s*j+kx-pad, a] * Wf[tap][b][a]
+//   dgrad (OP_T): per output phase (py,px):
+//                 big[n, s*i+py, s*j+px, a] = sum_{taps of the phase, b} small[n,i+di,j+dj,b] * Wt[tap][a][b]
+//
+// GEMM view: M = 128 positions of the small map per tile, N = output-channel tile (<= 256), K =
+// (tap, channel chunk of KC).  The A operand (activations) is fetched by ONE 4-D TMA box per
+// k-block straight from the NHWC tensor: element strides (s,s) implement the conv stride, negative
+// / overflowing start coordinates are zero-filled by TMA and implement the SAME padding - there is
+// no im2col buffer and no zero insertion.  The B operand (weights) is a 3-D TMA box of the packed
+// bf16 kernel.  Both land in 128B/64B-swizzled K-major tiles that tcgen05.mma consumes directly;
+// accumulators live in TMEM (double buffered) and are drained by 4 epilogue warps that add the
+// bias, accumulate the per-sample InstanceNorm statistics, apply tanh where asked and store bf16.
+//
+// Persistent: grid = min(#tiles, #SMs); warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue.
+#include <cuda.h>
+#include <stdio.h>
+
 #include "common.cuh"
 #include "internal.h"
-int lg_tc_supported(int, int, int, int, int, int, int) { return 0; }
-int lg_tc_fprop(const void*, const void*, const float*, void*, double*, int, int, int, int, int, int, cudaStream_t) { lg_set_error("tcgen05 path: unsupported geometry"); return LG_ERR_UNSUPPORTED; }
-int lg_tc_dgrad(const void*, const void*, const float*, void*, double*, int, int, int, int, int, int, int, cudaStream_t) { lg_set_error("tcgen05 path: unsupported geometry"); return LG_ERR_UNSUPPORTED; }
-int lg_tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t) { lg_set_error("tcgen05 path: unsupported geometry"); return LG_ERR_UNSUPPORTED; }
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int OP_F = 0, OP_T = 1;
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+  int Nimg, Hs, Ws, Hb, Wb, s, pad;
+  int Kch;        // contraction channels per tap (A for fprop, B for dgrad)
+  int Nch;        // real output channels (B for fprop, A for dgrad)
+  int KC;         // channel chunk per k-block (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B)
+  int NT;         // UMMA N (output-channel tile, multiple of 16)
+  int n_tiles;    // channel tiles
+  int BW, BH, BN; // tile box in small-map coordinates, BW*BH*BN == 128
+  int tilesW, tilesH, tilesN;
+  int m_tiles, total_tiles, phases;
+  int stages, stage_bytes, a_bytes;
+  int act;
+  const float* bias;
+  bf16* out;
+  double* stats;
+};
+
+struct TapList { int n; int k[5]; int d[5]; };
+
+// taps of one output phase along one axis: k in the phase iff (ph + pad - k) % s == 0
+__device__ __forceinline__ TapList phase_taps(int ph, int s, int pad) {
+  TapList t; t.n = 0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    int d = ph + pad - k;
+    if (d % s == 0) { t.k[t.n] = k; t.d[t.n] = d / s; ++t.n; }
+  }
+  return t;
+}
+
+struct TileCoord { int ph_y, ph_x, nt, n0, i0, j0; };
+
+template <int OP>
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+  TileCoord c;
+  const int per_phase = p.m_tiles * p.n_tiles;
+  int q = t / per_phase, r = t - q * per_phase;
+  // heavier phases (more taps) first: q = 0 -> (1,1), 1 -> (1,0), 2 -> (0,1), 3 -> (0,0)
+  if (OP == OP_T && p.s == 2) { c.ph_y = (q < 2) ? 1 : 0; c.ph_x = (q & 1) ? 0 : 1; }
+  else { c.ph_y = 0; c.ph_x = 0; }
+  c.nt = r % p.n_tiles;
+  int mt = r / p.n_tiles;
+  int tw = mt % p.tilesW; mt /= p.tilesW;
+  int th = mt % p.tilesH;
+  int tn = mt / p.tilesH;
+  c.n0 = tn * p.BN; c.i0 = th * p.BH; c.j0 = tw * p.BW;
+  return c;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full = bars;                       // [stages]   TMA -> MMA
+  uint64_t* empty = bars + MAX_STAGES;         // [stages]   MMA -> TMA
+  uint64_t* tfull = bars + 2 * MAX_STAGES;     // [2]        MMA -> epilogue
+  uint64_t* tempty = bars + 2 * MAX_STAGES + 2;// [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (2 * p.NT <= 32) ? 32 : (2 * p.NT <= 64) ? 64 : (2 * p.NT <= 128) ? 128
+                             : (2 * p.NT <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kc_per_tap = p.Kch / p.KC;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile<OP>(p, t);
+        TapList ty, tx;
+        if (OP == OP_T) { ty = phase_taps(c.ph_y, p.s, p.pad); tx = phase_taps(c.ph_x, p.s, p.pad); }
+        else { ty.n = tx.n = 5; for (int k = 0; k < 5; ++k) { ty.k[k] = tx.k[k] = k; ty.d[k] = tx.d[k] = k - p.pad; } }
+        for (int iy = 0; iy < ty.n; ++iy) {
+          for (int ix = 0; ix < tx.n; ++ix) {
+            const int tap = ty.k[iy] * 5 + tx.k[ix];
+            // start coordinates of the activation box (W, H) for this tap
+            const int cw = (OP == OP_F) ? p.s * c.j0 + tx.d[ix] : c.j0 + tx.d[ix];
+            const int chh = (OP == OP_F) ? p.s * c.i0 + ty.d[iy] : c.i0 + ty.d[iy];
+            for (int kc = 0; kc < kc_per_tap; ++kc) {
+              tc::mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+              uint8_t* sb = sa + p.a_bytes;
+              tc::mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
+              tc::tma_load_4d(sa, &tmA, &full[stage], kc * p.KC, cw, chh, c.n0);
+              tc::tma_load_3d(sb, &tmB, &full[stage], kc * p.KC, c.nt * p.NT, tap);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(TILE_M, p.NT, 0, 0);
+      const uint32_t layout = (p.KC == 64) ? 2u : 4u;          // SWIZZLE_128B / SWIZZLE_64B
+      const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;            // 8 rows of KC bf16
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile<OP>(p, t);
+        int ntaps = 25;
+        if (OP == OP_T) ntaps = phase_taps(c.ph_y, p.s, p.pad).n * phase_taps(c.ph_x, p.s, p.pad).n;
+        const int num_kb = ntaps * kc_per_tap;
+        tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = sa + (uint32_t)p.a_bytes;
+          const int ksteps = p.KC / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = tc::make_sdesc(sa + k * 32, 16, sbo, layout);
+            const uint64_t db = tc::make_sdesc(sb + k * 32, 16, sbo, layout);
+            tc::mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          tc::mma_commit(&empty[stage]);                 // frees the smem slot when the MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit(&tfull[acc]);                     // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue ==========================================
+    const int q = warp & 3;                              // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                       // row of the tile == TMEM lane
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord c = decode_tile<OP>(p, t);
+      const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+      const int n = c.n0 + bn, i = c.i0 + bh, j = c.j0 + bw;
+      const bool valid = n < p.Nimg;
+      int64_t off;
+      if (OP == OP_F) off = (((int64_t)n * p.Hs + i) * p.Ws + j) * p.Nch;
+      else off = (((int64_t)n * p.Hb + (p.s * i + c.ph_y)) * p.Wb + (p.s * j + c.ph_x)) * p.Nch;
+      bf16* orow = p.out + off;
+      const int ch0 = c.nt * p.NT;
+
+      tc::mbar_wait(&tfull[acc], acc_phase);
+      tc::fence_after_sync();
+      float s1 = 0.f, s2 = 0.f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+      for (int cb = 0; cb < p.NT; cb += 16) {
+        float v[16];
+        tc::tmem_ld16(taddr + cb, v);
+        const int chb = ch0 + cb;
+        if (chb >= p.Nch) continue;                       // channel padding (uniform over the CTA)
+        if (chb + 16 <= p.Nch && (p.Nch & 7) == 0) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            float a = v[e] + (p.bias ? __ldg(p.bias + chb + e) : 0.f);
+            float b = v[e + 1] + (p.bias ? __ldg(p.bias + chb + e + 1) : 0.f);
+            s1 += a + b; s2 += a * a + b * b;
+            if (p.act == LG_ACT_TANH) { a = tanhf(a); b = tanhf(b); }
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + chb);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        } else {
+          for (int e = 0; e < 16 && chb + e < p.Nch; ++e) {
+            float a = v[e] + (p.bias ? __ldg(p.bias + chb + e) : 0.f);
+            s1 += a; s2 += a * a;
+            if (p.act == LG_ACT_TANH) a = tanhf(a);
+            if (valid) orow[chb + e] = __float2bfloat16_rn(a);
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16)
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      if (p.stats != nullptr) {
+        // rows of one warp belong to one sample whenever BW*BH >= 32 (checked on the host)
+        if (!valid) { s1 = 0.f; s2 = 0.f; }
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0 && valid) {
+          atomicAdd(&p.stats[2 * n], (double)s1);
+          atomicAdd(&p.stats[2 * n + 1], (double)s2);
+        }
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Geometry shared by the support query and the launcher.  Returns false if not covered.
+bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
+  if (s != 1 && s != 2) return false;
+  const int Hs = Hb / s, Ws = Wb / s;
+  if (!is_pow2(Hs) || !is_pow2(Ws) || Ws > 128 || Hs * Ws < 32) return false;
+  const int Kch = (op == OP_F) ? A : B;
+  const int Nch = (op == OP_F) ? B : A;
+  if (Kch % 32 != 0) return false;
+  const int Npad = (Nch + 15) / 16 * 16;
+  int n_tiles = (Npad + 255) / 256;
+  if (Npad % n_tiles != 0 || (Npad / n_tiles) % 16 != 0) return false;
+  p->Nimg = Nimg; p->Hs = Hs; p->Ws = Ws; p->Hb = Hb; p->Wb = Wb; p->s = s; p->pad = (s == 2) ? 1 : 2;
+  p->Kch = Kch; p->Nch = Nch; p->KC = (Kch % 64 == 0) ? 64 : 32;
+  p->NT = Npad / n_tiles; p->n_tiles = n_tiles;
+  p->BW = Ws < 128 ? Ws : 128;
+  p->BH = (128 / p->BW) < Hs ? (128 / p->BW) : Hs;
+  p->BN = 128 / (p->BW * p->BH);
+  if (p->BW * p->BH * p->BN != 128 || p->BW * p->BH < 32) return false;
+  p->tilesW = Ws / p->BW; p->tilesH = Hs / p->BH; p->tilesN = (Nimg + p->BN - 1) / p->BN;
+  p->m_tiles = p->tilesW * p->tilesH * p->tilesN;
+  p->phases = (op == OP_T) ? s * s : 1;
+  p->total_tiles = p->m_tiles * p->n_tiles * p->phases;
+  p->a_bytes = TILE_M * p->KC * 2;
+  p->stage_bytes = p->a_bytes + p->NT * p->KC * 2;
+  int st = SMEM_BUDGET / p->stage_bytes;
+  p->stages = st > MAX_STAGES ? MAX_STAGES : st;
+  if (p->stages < 2) return false;
+  if (op == OP_F && (s * p->BW > 256 || s * p->BH > 256)) return false;
+  return true;
+}
+
+size_t smem_bytes(const TcParams& p) { return (size_t)p.stages * p.stage_bytes + 1024 + 256; }
+
+int encode_act_map(CUtensorMap* m, const void* base, int Nimg, int H, int W, int C, int boxC, int boxW, int boxH,
+                   int boxN, int estride, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { lg_set_error("cuTensorMapEncodeTiled entry point not available"); return LG_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)(boxW * estride), (cuuint32_t)(boxH * estride), (cuuint32_t)boxN};
+  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { lg_set_error("cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return LG_ERR_CUDA; }
+  return LG_OK;
+}
+
+// packed weights [25][rows][cols] bf16, cols contiguous (the contraction channels)
+int encode_w_map(CUtensorMap* m, const void* base, int rows, int cols, int boxCols, int boxRows,
+                 CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { lg_set_error("cuTensorMapEncodeTiled entry point not available"); return LG_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 25};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+  cuuint32_t box[3] = {(cuuint32_t)boxCols, (cuuint32_t)boxRows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { lg_set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LG_ERR_CUDA; }
+  return LG_OK;
+}
+
+template <int OP>
+int launch_tc(const void* act_in, const void* wpack, const float* bias, void* out, double* stats, int Nimg, int Hb,
+              int Wb, int A, int B, int s, int act, cudaStream_t st) {
+  TcParams p;
+  if (!plan(OP, Nimg, Hb, Wb, A, B, s, &p)) {
+    lg_set_error("tcgen05 path: unsupported geometry");
+    return LG_ERR_UNSUPPORTED;
+  }
+  p.act = act; p.bias = bias; p.out = (bf16*)out; p.stats = stats;
+  const int Ap = (A + 15) / 16 * 16, Bp = (B + 15) / 16 * 16;
+  const bf16* wt = (const bf16*)wpack;                  // [25][Ap][Bp]
+  const bf16* wf = wt + (size_t)25 * Ap * Bp;           // [25][Bp][Ap]
+  const CUtensorMapSwizzle sw = p.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tmA, tmB;
+  int e;
+  if (OP == OP_F) {
+    e = encode_act_map(&tmA, act_in, Nimg, Hb, Wb, A, p.KC, p.BW, p.BH, p.BN, s, sw);
+    if (e) return e;
+    e = encode_w_map(&tmB, wf, Bp, Ap, p.KC, p.NT, sw);
+  } else {
+    e = encode_act_map(&tmA, act_in, Nimg, p.Hs, p.Ws, B, p.KC, p.BW, p.BH, p.BN, 1, sw);
+    if (e) return e;
+    e = encode_w_map(&tmB, wt, Ap, Bp, p.KC, p.NT, sw);
+  }
+  if (e) return e;
+  const size_t shm = smem_bytes(p);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[OP]) {
+    cudaFuncSetAttribute(tc_conv_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set[OP] = true;
+  }
+  int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
+  tc_conv_kernel<OP><<<grid, NUM_THREADS, shm, st>>>(tmA, tmB, p);
+  return LG_OK;
+}
+
+}  // namespace
+
+int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N) {
+  if (op == LG_OP_WGRAD) return 0;
+  TcParams p;
+  return plan(op == LG_OP_FPROP ? OP_F : OP_T, N, Hb, Wb, A, B, s, &p) ? 1 : 0;
+}
+
+int lg_tc_fprop(const void* big, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
+                int Wb, int A, int B, int s, cudaStream_t st) {
+  return launch_tc<OP_F>(big, wpack, bias, out, stats, N, Hb, Wb, A, B, s, LG_ACT_NONE, st);
+}
+
+int lg_tc_dgrad(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
+                int Wb, int A, int B, int s, int act, cudaStream_t st) {
+  return launch_tc<OP_T>(small, wpack, bias, out, stats, N, Hb, Wb, A, B, s, act, st);
+}
+
+int lg_tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t) {
+  lg_set_error("tcgen05 wgrad: not implemented yet");
+  return LG_ERR_UNSUPPORTED;
+}

@@ -22,6 +22,7 @@ _INIT_SEED = [0]
 def set_init_seed(seed):
     """Seed of the Glorot-uniform initialiser stream (Keras default init, unseeded there)."""
     _INIT_SEED[0] = int(seed)
+    _GEN.clear()               # restart the stream: equal seeds give equal weights
 
 
 _GEN = {}

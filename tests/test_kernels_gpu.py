@@ -93,7 +93,8 @@ def test_conv_adjoint_identity():
     K.conv2d_dgrad(y, W, None, dy, None, s)
     lhs = (fx.double() * y.double()).sum()
     rhs = (x.double() * dy.double()).sum()
-    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5
+    scale = (fx.double() * y.double()).abs().sum()       # the inner product itself nearly cancels
+    assert abs(float(lhs - rhs)) / float(scale) < 1e-6
 
 
 @pytest.mark.parametrize("zdt,odt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
@@ -131,7 +132,7 @@ def test_instnorm_fwd_bwd(shape, alphas, zdt, odt):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("rows,C", [(512, 64), (100, 384), (333, 3), (64, 32), (7, 1)])
+@pytest.mark.parametrize("rows,C", [(512, 64), (100, 384), (333, 3), (64, 32), (7, 1), (6, 24576)])
 def test_bias_grad(rows, C, dtype):
     from littlegan_b200 import kernels as K
     g = _rand((rows, C), 30, dtype)
@@ -206,7 +207,7 @@ def test_adam_matches_tf_form():
         K.adam_advance(state, 5e-5, 0.5, 0.9)
         K.adam_apply(p, g.cuda(), m, v, state, 0.5, 0.9, 1e-8, 0.5)
     assert float(state[0]) == 3.0
-    assert float((p.cpu().double() - p_ref).abs().max()) < 1e-7
+    assert float((p.cpu().double() - p_ref).abs().max()) < 5e-7   # fp32 rounding of p ~ 1
 
 
 def test_fid_statistics_and_distance():
@@ -226,3 +227,69 @@ def test_fid_statistics_and_distance():
     got = fid.calculate_frechet_distance(mu, sigma, mu2, sig2)
     assert abs(got - ref) / abs(ref) < 1e-6
     assert abs(fid.calculate_frechet_distance(mu, sigma, mu, sigma)) < 1e-6 * np.trace(sig_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 / TMA path (bf16 operands): same oracle, weights pre-rounded to bf16 so that the only
+# differences are fp32 accumulation order and the bf16 rounding of the stored output.
+# ------------------------------------------------------------------------------------------------
+TC_F = [
+    (2, 64, 64, 64, 128, 2),     # enc2 geometry, SWIZZLE_128B
+    (3, 16, 16, 256, 384, 2),    # enc4: tile spans 2 samples (3rd tile half empty), N split 2x192
+    (2, 128, 128, 32, 64, 2),    # dec4 dgrad: KC=32 / SWIZZLE_64B
+    (2, 32, 32, 64, 32, 1),      # stride-1 fprop
+]
+TC_T = [
+    (2, 64, 64, 64, 128, 2, 0),
+    (3, 16, 16, 256, 384, 2, 0),
+    (2, 128, 128, 32, 64, 2, 0),
+    (2, 128, 128, 3, 64, 2, 0),  # enc1 dgrad: 3 output channels padded to N=16
+    (2, 128, 128, 3, 32, 1, 1),  # final conv: stride 1, tanh
+]
+
+
+def _pack(W):
+    from littlegan_b200 import kernels as K
+    A, B = W.shape[2], W.shape[3]
+    buf = torch.empty(K.pack_conv_weights_bytes(A, B), dtype=torch.uint8, device="cuda")
+    K.pack_conv_weights(W, buf)
+    return buf
+
+
+@pytest.mark.parametrize("geom", TC_F)
+def test_tc_fprop(geom):
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = geom
+    assert K.tc_supported(K.OP_FPROP, N, Hb, Wb, A, B, s)
+    x = _rand((N, Hb, Wb, A), 1, torch.bfloat16)
+    W = _rand((5, 5, A, B), 2, torch.bfloat16, 0.05).float()
+    b = _rand((B,), 3, torch.float32)
+    ref = O.conv2d_same(x.double(), W.double(), b.double(), s)
+    out = torch.zeros(N, Hb // s, Wb // s, B, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    Wc = W.cuda()
+    K.conv2d_fprop(x.cuda(), Wc, b.cuda(), out, stats, s, wpack=_pack(Wc), use_tc=True)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2
+    ref_stats = torch.stack([ref.reshape(N, -1).sum(1), (ref.reshape(N, -1) ** 2).sum(1)], 1)
+    assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
+
+
+@pytest.mark.parametrize("geom", TC_T)
+def test_tc_dgrad(geom):
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s, act = geom
+    assert K.tc_supported(K.OP_DGRAD, N, Hb, Wb, A, B, s)
+    x = _rand((N, Hb // s, Wb // s, B), 4, torch.bfloat16)
+    W = _rand((5, 5, A, B), 5, torch.bfloat16, 0.05).float()
+    b = _rand((A,), 6, torch.float32)
+    pre = O.conv2d_transpose_same(x.double(), W.double(), b.double(), s)
+    ref = torch.tanh(pre) if act else pre
+    out = torch.zeros(N, Hb, Wb, A, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    Wc = W.cuda()
+    K.conv2d_dgrad(x.cuda(), Wc, b.cuda(), out, stats, s, act, wpack=_pack(Wc), use_tc=True)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2
+    ref_stats = torch.stack([pre.reshape(N, -1).sum(1), (pre.reshape(N, -1) ** 2).sum(1)], 1)
+    assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4

@@ -82,7 +82,12 @@ def _one_step_parity(oargs, batch_no, B, t_loss, t_grad, t_w):
             got = ws[idx].lg_grad
             if key == "D" and oargs.use_clip:
                 got = got.clamp(-oargs.clip_range, oargs.clip_range)
-            e = rel_err(got, gref)
+            if gref.numel() == 1:
+                # scalar gamma/beta gradients: d(gamma) is analytically ~0 (the next layer's norm
+                # removes the scale), i.e. a sum of O(1) terms that cancels - bound it absolutely
+                e = abs(float(got) - float(gref)) / max(abs(float(gref)), 1e-2)
+            else:
+                e = rel_err(got, gref)
             worst = max(worst, e)
             assert e < t_grad, (key, idx, e)
     # updated weights
@@ -125,9 +130,9 @@ def test_iterator_protocol():
 def test_trajectory_graph_vs_oracle(dtype):
     """Loss trajectory over 30 steps on the reduced architecture: CUDA-graph replay path against
     the oracle (fp32), within 1% (north_star) - crosses b>10 (adjuster on) and partition steps."""
-    oargs = small_args(use_partition=True, lr=2e-4)
+    oargs = small_args(use_partition=True)
     pargs, gen, disc, adj, trainer, W = _setup(oargs, dtype, cuda_graph=True)
-    ot = O.OracleTrainer(oargs, W, dtype=torch.float32)
+    ot = O.OracleTrainer(oargs, W, dtype=torch.float64)
     steps = 30
     for b in range(1, steps + 1):
         i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=100 + b)
