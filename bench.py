@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Headline benchmark: LittleGAN G+D(+Adjuster) train step, images/sec at 128x128 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                        # the CPU restatement, host cores
+
+One "step" = one full `_train_step` (batch_no > 10: generator + discriminator + adjuster
+sub-step, use_partition off, sample.config.json hyper-parameters, cond_dim 40) on a synthetic
+CelebA-shaped batch.  Per-GPU batch is fixed at 64 (configs[1]; at 8 GPUs this is configs[2]'s
+global batch 512) => weak scaling.  images/sec counts `batch_size` images per step (the
+reference's progress bar counts 2x that, eager_trainer.py:213).
+
+`value`   : device-resident inputs, K CUDA-graph replays between two CUDA events (max over ranks).
+`e2e`     : the public API (`EagerTrainer._train_step(batch_no, iterator)`) with pinned HOST
+            batches: every step includes the host->device copies of both real batches and a
+            device->host read of the three loss scalars.
+`roofline`: the dominant tcgen05 conv kernel timed alone with CUDA events (algorithmic FLOPs /
+            launch duration) against the measured bf16 peak in MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 64
+COND_DIM = 40
+# conv MACs per image: E = encoder fwd, Dc = decoder + final conv fwd
+E_MAC, DC_MAC = 596.4e6, 825.8e6
+STEP_FLOP_PER_IMG = 2 * (7 * DC_MAC + 13 * E_MAC)      # 27.07 GFLOP, adjuster on
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tf=p["bf16_tflops"], tf_sus=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], src="measured")
+    except Exception:
+        return dict(tf=1590.0, tf_sus=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _bench_args(batch):
+    from littlegan_b200.config import Arg
+    return Arg.from_dict(batch_size=batch, attr=list(range(COND_DIM)), use_partition=False, train_adj=True,
+                         dtype="bf16", cuda_graph=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (CPU restatement of the TF-1.15 path) on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(sample_batch, steps, warmup):
+    import torch
+    from oracle import littlegan_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oargs = O.make_args(cond_dim=COND_DIM, batch_size=sample_batch, use_partition=False, train_adj=True)
+    tr = O.OracleTrainer(oargs, O.init_weights(oargs, 0), dtype=torch.float32)
+    data = O.synthetic_batch(oargs, sample_batch, seed=0)
+    for i in range(warmup):
+        tr.train_step(11 + i, *data)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        tr.train_step(11 + warmup + i, *data)
+    dt = time.perf_counter() - t0
+    return sample_batch * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 16
+    rate, ms, cores = cpu_oracle_rate(sample, a.steps, a.warmup)
+    unit = "images/sec"
+    line = {
+        "impl": "reference", "metric": "LittleGAN G+D+A train step throughput @128x128", "value": rate,
+        "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "littlegan-128 full train step (G+D+Adjuster), cond 40",
+                   "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * a.gpus},
+        "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": "full train step on a %d-image slice of the batch, oracle restatement in "
+                                   "PyTorch-CPU fp32 (TF 1.15 not installable)" % sample},
+        "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+def dominant_kernel_roofline(peaks):
+    """Times the largest tcgen05 conv geometry alone (dec2 forward == enc3 dgrad: small 16x16x256 ->
+    big 32x32x128, 209.7 MMAC/img) with CUDA events on the launching stream."""
+    import torch
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = PER_GPU_BATCH * 2, 32, 32, 128, 256, 2
+    if not K.tc_supported(K.OP_DGRAD, N, Hb, Wb, A, B, s):
+        return None
+    x = torch.randn(N, Hb // s, Wb // s, B, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(5, 5, A, B, device="cuda") * 0.05)
+    bias = torch.zeros(A, device="cuda")
+    wp = torch.empty(K.pack_conv_weights_bytes(A, B), dtype=torch.uint8, device="cuda")
+    K.pack_conv_weights(W, wp)
+    out = torch.empty(N, Hb, Wb, A, device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    reps, tot = 10, 0.0
+    for i in range(3 + reps):
+        flush.zero_()                                   # evict L2 between launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        K.conv2d_dgrad(x, W, bias, out, stats, s, K.ACT_NONE, wp, True)
+        e1.record()
+        e1.synchronize()
+        if i >= 3:
+            tot += e0.elapsed_time(e1)
+    ms = tot / reps
+    flops = 2.0 * 25 * A * B * N * (Hb // s) * (Wb // s)
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "tc_conv_kernel<dgrad> dec2 (16x16x256 -> 32x32x128), batch %d" % N,
+            "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
+            "peak_source": peaks["src"] + " bf16 burst", "ms_per_launch": ms, "traffic": None}
+
+
+def run_product(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from littlegan_b200 import kernels as K
+    from littlegan_b200 import model as M
+    from littlegan_b200.dataset import DevicePrefetcher, SyntheticCelebA
+    from littlegan_b200.eager_trainer import EagerTrainer
+
+    args = _bench_args(PER_GPU_BATCH)
+    M.set_init_seed(0)
+    dec, enc = M.Decoder(args), M.Encoder(args)
+    gen, disc = M.Generator(args, dec), M.Discriminator(args, enc)
+    adj = M.Adjuster(args, disc, gen)
+    data = SyntheticCelebA(args, batches=10 ** 9, seed=1 + rank, pool=8)
+    trainer = EagerTrainer(args, gen, disc, adj, data)
+    it = DevicePrefetcher(data.get_new_iterator(), depth=4)
+    B = PER_GPU_BATCH
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up through the public API (first step eager, second captures the graph)
+    b = 11
+    for _ in range(max(a.warmup, 3)):
+        b += 1
+        trainer._train_step(b, it)
+    torch.cuda.synchronize()
+    graph = trainer._graphs[(True, None)][0]
+    launches = K.launch_count_of_last_capture()
+
+    # ---- device-resident timing: K replays of the captured step
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        graph.replay()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1) / a.steps
+
+    # ---- end to end through the public API, host batches, loss read-back every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        b += 1
+        res = trainer._train_step(b, it)
+        losses = (float(res[3]), float(res[4]), float(res[5]))
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / a.steps
+    clocks = sampler.stop() if rank == 0 else None
+    assert all(x == x for x in losses), "non-finite loss"
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = _peaks()
+        gb = B * world
+        H = args.init_dim * 16
+        h2d = 2 * (B * H * H * args.image_channel * 4 + B * args.cond_dim * 4)
+        value = gb / (ms_dev * 1e-3)
+        line = {
+            "metric": "LittleGAN G+D+A train step throughput @128x128", "value": value, "unit": "images/sec",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "littlegan-128 full train step (G+D+Adjuster), cond 40, batch 64/GPU",
+                       "per_gpu_batch": B, "global_batch": gb, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/sec", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+            "gpu_launches": launches * a.steps,
+            "step_tensor_frac": STEP_FLOP_PER_IMG * B / (ms_dev * 1e-3) / 1e12 / peaks["tf_sus"],
+            "last_losses": {"gen": losses[0], "disc": losses[1], "adj": losses[2]},
+        }
+        if world == 1:
+            line["roofline"] = dominant_kernel_roofline(peaks)
+            if not a.no_cpu_baseline:
+                rate, ms, cores = cpu_oracle_rate(16, 4, 1)
+                line["cpu_baseline"] = {
+                    "value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+                    "sample": "4 full train steps on a 16-image batch (configs[0]), oracle restatement in "
+                              "PyTorch-CPU fp32 (TF 1.15 not installable)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_product(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,3 +44,57 @@ class SyntheticCelebA:
 
     def get_new_iterator(self):
         return _Iterator(self)
+
+
+class DevicePrefetcher:
+    """Wraps an iterator of pinned host batches: the host->device copy of the next batches is
+    issued on a side stream while the current step computes (the role of tf.data's prefetch,
+    dataset.py:23).  get_next() returns CUDA tensors and makes the consumer stream wait for their
+    copy; a buffer is recycled only after the consumer has read it."""
+
+    def __init__(self, iterator, depth=4):
+        self.it = iterator
+        self.stream = torch.cuda.Stream()
+        self.depth = depth
+        self.ring = []            # (copy-done event, image_dev, cond_dev, consumed event)
+        self.bufs = None
+        self.slot = 0
+        self.done = False
+        self._prev = None         # consumed-event of the buffer handed out by the previous get_next
+        for _ in range(depth):
+            self._issue()
+
+    def _issue(self):
+        if self.done:
+            return
+        try:
+            img, cond = self.it.get_next()
+        except OutOfRangeError:
+            self.done = True
+            return
+        if self.bufs is None:
+            self.bufs = [(torch.empty(img.shape, dtype=img.dtype, device="cuda"),
+                          torch.empty(cond.shape, dtype=cond.dtype, device="cuda"),
+                          torch.cuda.Event()) for _ in range(self.depth + 2)]
+        dimg, dcond, consumed = self.bufs[self.slot % len(self.bufs)]
+        self.slot += 1
+        self.stream.wait_event(consumed)        # no-op until the event has been recorded once
+        with torch.cuda.stream(self.stream):
+            dimg.copy_(img, non_blocking=True)
+            dcond.copy_(cond, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.ring.append((ev, dimg, dcond, consumed))
+
+    def get_next(self):
+        cur = torch.cuda.current_stream()
+        if self._prev is not None:
+            self._prev.record(cur)              # the consumer's reads of the previous buffer are queued by now
+            self._prev = None
+        if not self.ring:
+            raise OutOfRangeError()
+        ev, dimg, dcond, consumed = self.ring.pop(0)
+        cur.wait_event(ev)
+        self._prev = consumed
+        self._issue()
+        return dimg, dcond

@@ -293,8 +293,10 @@ class EagerTrainer:
             g = torch.cuda.CUDAGraph()
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()
+            n0 = K.launch_count()
             with torch.cuda.graph(g, pool=self._pool):
                 self._step_body(S, adj_on, batch_no)
+            K.note_capture(K.launch_count() - n0)
             self._graphs[key] = (g, S["adj"])
         g, adj = self._graphs[key]
         S["adj"] = adj

@@ -6,7 +6,28 @@ hand-written sm_100a kernels on torch's current CUDA stream and returns immediat
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_SIGMOID, ACT_TANH, BF16, F32, OP_DGRAD, OP_FPROP, OP_WGRAD, check  # noqa: F401
+from ._lib import ACT_NONE, ACT_SIGMOID, ACT_TANH, BF16, F32, OP_DGRAD, OP_FPROP, OP_WGRAD  # noqa: F401
+
+# every C-ABI compute call launches exactly one kernel of this library; counted for bench.py
+_LAUNCHES = [0]
+_LAST_CAPTURE = [0]
+
+
+def check(ret, what=""):
+    _LAUNCHES[0] += 1
+    return _lib.check(ret, what)
+
+
+def launch_count():
+    return _LAUNCHES[0]
+
+
+def note_capture(n):
+    _LAST_CAPTURE[0] = n
+
+
+def launch_count_of_last_capture():
+    return _LAST_CAPTURE[0]
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -71,7 +92,7 @@ def conv2d_wgrad(big, small, dW, stride, use_tc=False):
 
 
 def pack_conv_weights_bytes(A, B):
-    return int(check(_lib.load().lg_pack_conv_weights(None, None, A, B, None)))
+    return int(_lib.check(_lib.load().lg_pack_conv_weights(None, None, A, B, None)))
 
 
 def pack_conv_weights(W, wpack):

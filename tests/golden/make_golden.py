@@ -2,6 +2,8 @@
 
     python tests/golden/make_golden.py [--steps 100]
 
+trajectory_full_fp64.json : the same run with the oracle in fp64 (the fp32-vs-fp64 gap is the noise
+                       floor of this chaotic, Adam-normalised system).
 trajectory_full.json : 100-step G/D/A loss trajectory of the real architecture (cond 40, batch 4),
                        initial weights = the product builders' seeded Glorot init (seed 0),
                        inputs = oracle.synthetic_batch(seed = data_seed + step).
@@ -24,11 +26,11 @@ from oracle import littlegan_oracle as O  # noqa: E402
 from tests.util import build_product, product_args, product_weights_to_oracle, small_args  # noqa: E402
 
 
-def trajectory(steps):
+def trajectory(steps, dtype=torch.float32, name="trajectory_full.json"):
     cfg = dict(cond_dim=40, batch_size=4, use_partition=True)
     oargs = O.make_args(**cfg)
     gen, disc, adj = build_product(product_args(oargs, dtype="fp32"), seed=0)
-    ot = O.OracleTrainer(oargs, product_weights_to_oracle(gen, disc, adj), dtype=torch.float32)
+    ot = O.OracleTrainer(oargs, product_weights_to_oracle(gen, disc, adj), dtype=dtype)
     out = dict(args=cfg, seed=0, data_seed=1000, gen=[], disc=[], adj=[])
     for b in range(1, steps + 1):
         r = ot.train_step(b, *O.synthetic_batch(oargs, cfg["batch_size"], seed=1000 + b))
@@ -36,7 +38,7 @@ def trajectory(steps):
         out["disc"].append(float(r["disc_loss"]))
         out["adj"].append(None if r["adj_loss"] is None else float(r["adj_loss"]))
         print(b, out["gen"][-1], out["disc"][-1], out["adj"][-1], flush=True)
-    with open(os.path.join(HERE, "trajectory_full.json"), "w") as f:
+    with open(os.path.join(HERE, name), "w") as f:
         json.dump(out, f)
 
 
@@ -58,6 +60,9 @@ def small_step():
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--fp64", action="store_true", help="also write the fp64 oracle trajectory (noise floor)")
     a = ap.parse_args()
     small_step()
     trajectory(a.steps)
+    if a.fp64:
+        trajectory(a.steps, torch.float64, "trajectory_full_fp64.json")

@@ -1,0 +1,85 @@
+"""Host-side logic of the product that needs no GPU: config layering, builders' surface and
+`.weights` ordering, parameter arenas, partition ranges, error behaviour."""
+import json
+import os
+
+import pytest
+import torch
+
+from littlegan_b200.config import Arg
+from tests.util import build_product, product_args, small_args
+
+
+def test_arg_layering(tmp_path):
+    (tmp_path / "sample.config.json").write_text(open(
+        os.path.join(os.path.dirname(__file__), "..", "littlegan_b200", "sample.config.json")).read())
+    (tmp_path / "lab.config.json").write_text(json.dumps({"batch_size": 8, "attr": None, "dtype": "fp32"}))
+    a = Arg(["train", "exp1", "-e", "lab", "-g", "0,1", "--debug"], config_dir=str(tmp_path))
+    assert a.batch_size == 8 and a.cond_dim == 40 and a.gpu == [0, 1] and a.debug
+    assert a.prefetch == a.prefetch_batch * 8 and a.result_dir.endswith("exp1") and a.dtype == "fp32"
+    b = Arg.from_dict()
+    assert b.cond_dim == 7 and b.noise_dim == 93 and b.conv_filter == [384, 256, 128, 64, 32]
+    assert b.dtype == "bf16" and b.cuda_graph is True
+
+
+def test_builders_surface_and_weight_order():
+    pargs = product_args(small_args())
+    gen, disc, adj = build_product(pargs)
+    assert len(disc.weights) == 20 and len(gen.weights) == 22 and len(adj.weights) == 38
+    enc = disc.encoder
+    assert disc.weights[0] is enc.conv1.kernel and disc.weights[3] is enc.norm1.beta
+    assert disc.weights[16] is disc.dense_pr.kernel and disc.weights[19] is disc.dense_cond.bias
+    assert gen.weights[0] is gen.dense.kernel and gen.weights[2] is gen.norm.gamma
+    assert gen.weights[4] is gen.decoder.conv1.kernel and gen.weights[20] is gen.conv.kernel
+    assert adj.encoder is disc.encoder and adj.decoder is gen.decoder and adj.conv is gen.conv
+    assert adj.weights[16] is adj.dense.kernel and adj.weights[19] is adj.norm.beta
+    cf, k = pargs.conv_filter, pargs.kernel_size
+    assert tuple(enc.conv1.kernel.shape) == (k, k, 3, cf[4])            # HWIO
+    assert tuple(gen.decoder.conv1.kernel.shape) == (k, k, cf[1], cf[0])  # [k,k,out,in]
+    assert tuple(gen.conv.kernel.shape) == (k, k, 3, cf[4])
+    assert tuple(gen.dense.kernel.shape) == (pargs.noise_dim + pargs.cond_dim, pargs.init_dim ** 2 * cf[0])
+
+
+def test_trainer_arenas_and_partition_ranges():
+    from littlegan_b200.eager_trainer import EagerTrainer
+    pargs = product_args(small_args(use_partition=True))
+    gen, disc, adj = build_product(pargs)
+    before = [w.clone() for w in gen.weights]
+    tr = EagerTrainer(pargs, gen, disc, adj, None)
+    for w, b in zip(gen.weights, before):                     # re-homing keeps values and identity
+        assert torch.equal(w, b) and w.untyped_storage().data_ptr() == tr.P.untyped_storage().data_ptr()
+        assert w.lg_grad.shape == w.shape
+    assert tr.part_weights["Generator"][1][0] is gen.weights[4]
+    assert tr.all_weights["Adjuster"][0] is adj.weights[16]
+    offs = tr._offsets["Generator"]
+    assert tr._range("Generator", 3) == (offs[0], offs[-1])
+    assert tr._range("Generator", 5) == (offs[4], offs[8])    # (5//5)%3 = 1 -> tensors 4..7
+    assert tr._range("Generator", 15) == (offs[0], offs[4])
+    d = tr._offsets["Discriminator"]
+    assert tr._range("Discriminator", 10) == (d[16], d[20])
+    a_ = tr._offsets["Adjuster"]
+    assert tr._range("Adjuster", 15) == (a_[0], a_[4])
+    assert tr._get_train_weight(gen, 5)[0] is gen.weights[4] and len(tr._get_train_weight(disc, 3)) == 20
+    assert tr._variant(5) == (False, 1) and tr._variant(11) == (True, None) and tr._variant(15) == (True, 0)
+    gen.weights[0].zero_()                                     # weights are views of the arena
+    assert float(tr.P[offs[0]:offs[0] + 8].abs().sum()) == 0.0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_no_cpu_fallback():
+    from littlegan_b200._lib import LittleGANError
+    from littlegan_b200 import kernels as K
+    pargs = product_args(small_args())
+    gen, disc, adj = build_product(pargs)
+    with pytest.raises(LittleGANError):
+        gen([torch.zeros(2, pargs.noise_dim), torch.zeros(2, pargs.cond_dim)])
+    with pytest.raises(LittleGANError):
+        K.rowstats(torch.zeros(2, 8), torch.zeros(2, 2, dtype=torch.float64))
+
+
+def test_instance_norm_only_reference_mode():
+    from littlegan_b200.instance import InstanceNormalization
+    with pytest.raises(NotImplementedError):
+        InstanceNormalization(axis=3)
+    n = InstanceNormalization()
+    assert n.epsilon == 1e-3 and tuple(n.gamma.shape) == (1,) and float(n.gamma) == 1.0 and float(n.beta) == 0.0

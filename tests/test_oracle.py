@@ -1,0 +1,184 @@
+"""CPU tests of the oracle itself (no GPU): definition-level loops for the TF conv semantics,
+closed forms for the norm backward and TF-Adam, the committed golden vectors, and the FID oracle
+against NumPy/SciPy called directly."""
+import json
+import math
+import os
+
+import numpy as np
+import torch
+
+from oracle import fid_oracle
+from oracle import littlegan_oracle as O
+from tests.util import build_product, product_args, product_weights_to_oracle, small_args
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+D = torch.float64
+
+
+def _loop_conv(x, w, b, s, pad):
+    N, H, W_, A = x.shape
+    B = w.shape[3]
+    y = torch.zeros(N, H // s, W_ // s, B, dtype=D)
+    for i in range(H // s):
+        for j in range(W_ // s):
+            for ky in range(5):
+                for kx in range(5):
+                    yy, xx = s * i + ky - pad, s * j + kx - pad
+                    if 0 <= yy < H and 0 <= xx < W_:
+                        y[:, i, j] += x[:, yy, xx] @ w[ky, kx]
+    return y + b
+
+
+def _loop_convT(x, w, b, s, pad):
+    N, H, W_, Bc = x.shape
+    A = w.shape[2]
+    y = torch.zeros(N, H * s, W_ * s, A, dtype=D)
+    for i in range(H):
+        for j in range(W_):
+            for ky in range(5):
+                for kx in range(5):
+                    Y, X = s * i + ky - pad, s * j + kx - pad
+                    if 0 <= Y < H * s and 0 <= X < W_ * s:
+                        y[:, Y, X] += x[:, i, j] @ w[ky, kx].T
+    return y + b
+
+
+def test_conv_definitions():
+    g = torch.Generator().manual_seed(0)
+    for s, pad in ((2, 1), (1, 2)):
+        x = torch.randn(2, 8, 8, 3, generator=g, dtype=D)
+        w = torch.randn(5, 5, 3, 4, generator=g, dtype=D)
+        b = torch.randn(4, generator=g, dtype=D)
+        assert (O.conv2d_same(x, w, b, s) - _loop_conv(x, w, b, s, pad)).abs().max() < 1e-12
+        xs = torch.randn(2, 4, 4, 4, generator=g, dtype=D)
+        bt = torch.randn(3, generator=g, dtype=D)
+        assert (O.conv2d_transpose_same(xs, w, bt, s) - _loop_convT(xs, w, bt, s, pad)).abs().max() < 1e-12
+
+
+def test_transpose_is_adjoint_of_conv():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 16, 16, 5, generator=g, dtype=D)
+    y = torch.randn(2, 8, 8, 7, generator=g, dtype=D)
+    w = torch.randn(5, 5, 5, 7, generator=g, dtype=D)
+    z0, z5 = torch.zeros(7, dtype=D), torch.zeros(5, dtype=D)
+    lhs = (O.conv2d_same(x, w, z0, 2) * y).sum()
+    rhs = (x * O.conv2d_transpose_same(y, w, z5, 2)).sum()
+    assert abs(float(lhs - rhs)) < 1e-9 * abs(float(lhs))
+
+
+def test_instance_norm_closed_form_backward():
+    """dx = (gamma/s)(g - mean g - xhat (s/sigma) mean(g xhat)), eps on the std."""
+    g_ = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 4, 4, 6, generator=g_, dtype=D, requires_grad=True)
+    gamma = torch.tensor([1.7], dtype=D, requires_grad=True)
+    beta = torch.tensor([0.3], dtype=D, requires_grad=True)
+    y = O.instance_norm(x, gamma, beta)
+    gout = torch.randn(y.shape, generator=g_, dtype=D)
+    dx, dg, db = torch.autograd.grad((y * gout).sum(), [x, gamma, beta])
+    xd = x.detach()
+    mu = xd.mean(dim=(1, 2, 3), keepdim=True)
+    sigma = ((xd - mu) ** 2).mean(dim=(1, 2, 3), keepdim=True).sqrt()
+    s = sigma + 1e-3
+    xh = (xd - mu) / s
+    mg = gout.mean(dim=(1, 2, 3), keepdim=True)
+    mgx = (gout * xh).mean(dim=(1, 2, 3), keepdim=True)
+    dx_cf = gamma.detach() / s * (gout - mg - xh * (s / sigma) * mgx)
+    assert (dx - dx_cf).abs().max() < 1e-12
+    assert abs(float(dg - (gout * xh).sum())) < 1e-10 and abs(float(db - gout.sum())) < 1e-10
+    # mean ~ 0, std slightly below 1 because eps is added to the std, not the variance
+    y0 = O.instance_norm(xd, torch.ones(1, dtype=D), torch.zeros(1, dtype=D))
+    assert abs(float(y0[0].mean())) < 1e-12
+    assert abs(float(y0[0].std(unbiased=False)) - float(sigma[0] / s[0])) < 1e-12
+
+
+def test_bce_matches_keras_form():
+    t = torch.tensor([[0.98, -0.94], [0.02, 0.98]], dtype=D)
+    p = torch.tensor([[0.3, 0.9], [1.0, 0.0]], dtype=D)
+    pc = p.clamp(1e-7, 1 - 1e-7)
+    want = (-(t * torch.log(pc + 1e-7) + (1 - t) * torch.log(1 - pc + 1e-7))).mean(-1).mean()
+    assert abs(float(O.bce(t, p) - want)) < 1e-9
+    pr = p.clone().requires_grad_(True)
+    (gr,) = torch.autograd.grad(O.bce(t, pr), pr)
+    assert float(gr[0, 0]) != 0.0 and float(gr[1, 0]) == 0.0   # p = 1.0 lies outside [1e-7, 1-1e-7]
+    pr2 = torch.tensor([[1.0 + 1e-3, -1e-3]], dtype=D, requires_grad=True)
+    (g2,) = torch.autograd.grad(O.bce(t[:1], pr2), pr2)
+    assert float(g2.abs().max()) == 0.0    # outside the clip range the gradient is zero
+
+
+def test_tf_adam_form():
+    opt = O.TFAdam(0.1, 0.5, 0.9)
+    p = torch.tensor([1.0], dtype=D)
+    g = torch.tensor([0.2], dtype=D)
+    opt.apply([(g, p)])
+    m, v = 0.5 * 0.2, 0.1 * 0.04
+    lr_t = 0.1 * math.sqrt(1 - 0.9) / (1 - 0.5)
+    assert abs(float(p) - (1.0 - lr_t * m / (math.sqrt(v) + 1e-8))) < 1e-12
+    opt.apply([])                         # a step that trains other variables still advances t
+    assert opt.t == 2
+
+
+def test_partition_schedule():
+    a = small_args(use_partition=True)
+    tr = O.OracleTrainer(a, O.init_weights(a))
+    assert tr._train_idx("G", 3) == list(range(22))
+    assert tr._train_idx("G", 5) == [4, 5, 6, 7]          # (5//5)%3 = 1
+    assert tr._train_idx("D", 10) == [16, 17, 18, 19]      # (10//5)%3 = 2
+    assert tr._train_idx("D", 15) == list(range(12))
+    assert tr._train_idx("A", 15) == [0, 1, 2, 3]
+
+
+def test_parameter_counts_match_survey():
+    a = O.make_args(cond_dim=7)
+    W = O.init_weights(a)
+    assert sum(w.numel() for w in W["D"]) == 3683856
+    assert sum(w.numel() for w in W["G"]) == 6017869
+    assert sum(w.numel() for w in W["A"]) == 196610
+    a = O.make_args(cond_dim=40)
+    W = O.init_weights(a)
+    assert [sum(w.numel() for w in W[k]) for k in "DGA"] == [4494897, 6828877, 1007618]
+
+
+def test_golden_small_step_is_reproduced():
+    """The committed fixture pins the oracle: any drift of oracle/ shows up here."""
+    gold = np.load(os.path.join(GOLD, "small_step.npz"))
+    oargs = small_args(use_partition=True)
+    gen, disc, adj = build_product(product_args(oargs, dtype="fp32"), seed=0)
+    ot = O.OracleTrainer(oargs, product_weights_to_oracle(gen, disc, adj), dtype=torch.float64)
+    r = ot.train_step(11, *O.synthetic_batch(oargs, 4, seed=5), return_grads=True)
+    assert np.abs(r["fake_image"].numpy() - gold["fake_image"]).max() < 1e-6
+    assert np.abs(r["adj_image"].numpy() - gold["adj_image"]).max() < 1e-6
+    got = np.array([float(r["gen_loss"]), float(r["disc_loss"]), float(r["adj_loss"])])
+    assert np.abs(got - gold["losses"]).max() < 1e-9
+    for key in "DGA":
+        gs = np.array([float(g.sum()) for g in r["grads"][key].values()])
+        assert np.allclose(gs, gold["grad_sum_" + key], rtol=1e-7, atol=1e-9)
+
+
+def test_golden_trajectory_prefix_is_reproduced():
+    gold = json.load(open(os.path.join(GOLD, "trajectory_full.json")))
+    assert len(gold["gen"]) == 100 and gold["adj"][9] is None and gold["adj"][10] is not None
+    oargs = O.make_args(**gold["args"])
+    gen, disc, adj = build_product(product_args(oargs, dtype="fp32"), seed=gold["seed"])
+    ot = O.OracleTrainer(oargs, product_weights_to_oracle(gen, disc, adj), dtype=torch.float32)
+    r = ot.train_step(1, *O.synthetic_batch(oargs, 4, seed=gold["data_seed"] + 1))
+    assert abs(float(r["gen_loss"]) - gold["gen"][0]) < 1e-4 * gold["gen"][0]
+    assert abs(float(r["disc_loss"]) - gold["disc"][0]) < 1e-4 * gold["disc"][0]
+
+
+def test_fid_oracle_is_numpy_scipy():
+    rng = np.random.RandomState(0)
+    act = rng.randn(300, 16) @ rng.randn(16, 16) + 2.0
+    mu, sigma = fid_oracle.activation_statistics(act)
+    assert np.allclose(mu, act.mean(0)) and np.allclose(sigma, np.cov(act, rowvar=False))
+    assert fid_oracle.used_rows(1037, 100) == 1000 and fid_oracle.used_rows(30, 50) == 30
+    act2 = rng.randn(200, 16) * 0.5 + 1.0
+    mu2, sig2 = fid_oracle.activation_statistics(act2)
+    d = fid_oracle.frechet_distance(mu, sigma, mu2, sig2)
+    assert d > 0 and abs(fid_oracle.frechet_distance(mu, sigma, mu, sigma)) < 1e-6
+    # symmetric-form cross-check of Tr sqrtm(s1 s2)
+    w, v = np.linalg.eigh(sigma)
+    root = (v * np.sqrt(np.clip(w, 0, None))) @ v.T
+    tr = np.sqrt(np.clip(np.linalg.eigvalsh(root @ sig2 @ root), 0, None)).sum()
+    alt = ((mu - mu2) ** 2).sum() + np.trace(sigma) + np.trace(sig2) - 2 * tr
+    assert abs(alt - d) < 1e-8 * abs(d)
