@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "tc_host.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
@@ -251,23 +252,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+using tc_host::EncodeTiledFn;
+using tc_host::get_encode;
+using tc_host::is_pow2;
+using tc_host::encode_act_map;
 
 // Geometry shared by the support query and the launcher.  Returns false if not covered.
 bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
@@ -301,21 +289,6 @@ bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
 }
 
 size_t smem_bytes(const TcParams& p) { return (size_t)p.stages * p.stage_bytes + 1024 + 256; }
-
-int encode_act_map(CUtensorMap* m, const void* base, int Nimg, int H, int W, int C, int boxC, int boxW, int boxH,
-                   int boxN, int estride, CUtensorMapSwizzle sw) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { lg_set_error("cuTensorMapEncodeTiled entry point not available"); return LG_ERR_CUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)(boxW * estride), (cuuint32_t)(boxH * estride), (cuuint32_t)boxN};
-  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { lg_set_error("cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return LG_ERR_CUDA; }
-  return LG_OK;
-}
 
 // packed weights [25][rows][cols] bf16, cols contiguous (the contraction channels)
 int encode_w_map(CUtensorMap* m, const void* base, int rows, int cols, int boxCols, int boxRows,
@@ -371,8 +344,10 @@ int launch_tc(const void* act_in, const void* wpack, const float* bias, void* ou
 
 }  // namespace
 
+int lg_tc_wgrad_supported(int Nimg, int Hb, int Wb, int A, int B, int s);   // tc_wgrad.cu
+
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N) {
-  if (op == LG_OP_WGRAD) return 0;
+  if (op == LG_OP_WGRAD) return lg_tc_wgrad_supported(N, Hb, Wb, A, B, s);
   TcParams p;
   return plan(op == LG_OP_FPROP ? OP_F : OP_T, N, Hb, Wb, A, B, s, &p) ? 1 : 0;
 }
@@ -385,9 +360,4 @@ int lg_tc_fprop(const void* big, const void* wpack, const float* bias, void* out
 int lg_tc_dgrad(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
                 int Wb, int A, int B, int s, int act, cudaStream_t st) {
   return launch_tc<OP_T>(small, wpack, bias, out, stats, N, Hb, Wb, A, B, s, act, st);
-}
-
-int lg_tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t) {
-  lg_set_error("tcgen05 wgrad: not implemented yet");
-  return LG_ERR_UNSUPPORTED;
 }

@@ -1,0 +1,237 @@
+// tcgen05 weight-gradient kernel (bf16 operands, fp32 accumulate, fp32 atomics into dW):
+//
+//   dW[tap][a][b] += sum_{pos=(n,i,j)} big[n, s*i+ky-pad, s*j+kx-pad, a] * small[n,i,j,b]
+//
+// GEMM view: D[(tap,a)][b], M = 128 rows = (128/min(A,128)) taps x min(A,128) channels of the big
+// map, N = b-tile (<= 256), K = positions.  Both operands are MN-major (channels contiguous, the
+// contraction index = position has a stride), which tcgen05 consumes directly from the NHWC
+// tensors: every k-block is a set of 4-D TMA boxes {64|32 channels x 64 positions}; the big-map
+// boxes use element strides (s,s) and a per-tap start offset (zero-filled out of bounds), so the
+// 25 shifted views never exist in memory.  Split-K over position slices fills the GPU; each CTA
+// reduces its 128 x NT fp32 tile into dW with 16-byte vector reductions (red.global.add.v4.f32),
+// where a thread owns a (tap,a) row and therefore contiguous b.
+//
+// One tile x one k-slice per CTA: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "internal.h"
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int KP = 64;                   // positions per k-block
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct WgParams {
+  int Nimg, Hs, Ws, Hb, Wb, s, pad, A, B;
+  int a_blk;            // channels per big-map TMA box: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+  int rows_per_tap;     // min(A, 128)
+  int taps_per_tile;    // 128 / rows_per_tap
+  int a_tiles;          // ceil(A / 128)
+  int groups;           // ceil(25 / taps_per_tile)
+  int NT, n_tiles;      // b tile (multiple of 64)
+  int BW, BH, BN;       // position box in small-map coordinates, BW*BH*BN == 64
+  int pbW, pbH, pbN;    // position boxes along W, H, N
+  int total_kb, kb_per_slice;
+  int stages, stage_bytes, a_bytes;
+  float* dW;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant__ CUtensorMap tmSmall,
+                const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tfull = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = p.NT <= 32 ? 32 : p.NT <= 64 ? 64 : p.NT <= 128 ? 128 : 256;
+
+  // tile decode: blockIdx.x -> (tap group, a tile, b tile); blockIdx.y -> k slice
+  int t = blockIdx.x;
+  const int nt = t % p.n_tiles; t /= p.n_tiles;
+  const int at = t % p.a_tiles;
+  const int grp = t / p.a_tiles;
+  const int kb0 = blockIdx.y * p.kb_per_slice;
+  const int kb1 = min(p.total_kb, kb0 + p.kb_per_slice);
+  const int num_kb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmBig);
+    tc::tma_prefetch_desc(&tmSmall);
+    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(tfull, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nbox_a = 128 / p.a_blk;                 // big-map boxes per stage
+  const int nbox_b = p.NT / 64;                     // small-map boxes per stage
+  const int a_box_bytes = KP * p.a_blk * 2;
+  const int b_box_bytes = KP * 64 * 2;
+
+  if (warp == 0) {
+    if (lane == 0 && num_kb > 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int r = kb;
+        const int pw = r % p.pbW; r /= p.pbW;
+        const int ph = r % p.pbH;
+        const int pn = r / p.pbH;
+        const int j0 = pw * p.BW, i0 = ph * p.BH, n0 = pn * p.BN;
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+        uint8_t* sb = sa + p.a_bytes;
+        tc::mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
+        for (int bi = 0; bi < nbox_a; ++bi) {
+          const int row0 = bi * p.a_blk;
+          int tap = grp * p.taps_per_tile + row0 / p.rows_per_tap;
+          if (tap > 24) tap = 24;                                   // padding rows: computed, never stored
+          const int ch = at * 128 + row0 % p.rows_per_tap;
+          const int ky = tap / 5, kx = tap - 5 * ky;
+          tc::tma_load_4d(sa + bi * a_box_bytes, &tmBig, &full[stage], ch, p.s * j0 + kx - p.pad,
+                          p.s * i0 + ky - p.pad, n0);
+        }
+        for (int bi = 0; bi < nbox_b; ++bi)
+          tc::tma_load_4d(sb + bi * b_box_bytes, &tmSmall, &full[stage], nt * p.NT + bi * 64, j0, i0, n0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && num_kb > 0) {
+      const uint32_t idesc = tc::make_idesc(128, p.NT, 1, 1);        // both operands MN-major
+      const uint32_t layout_a = (p.a_blk == 64) ? 2u : 4u;
+      const uint32_t sbo_a = 8u * (uint32_t)p.a_blk * 2u;            // 8 positions x a_blk channels
+      const uint32_t lbo_a = (uint32_t)a_box_bytes;                  // next block of a_blk channels
+      const uint32_t sbo_b = 1024u, lbo_b = (uint32_t)b_box_bytes;
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
+        tc::fence_after_sync();
+        const uint32_t sa = tc::smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t sb = sa + (uint32_t)p.a_bytes;
+#pragma unroll
+        for (int k = 0; k < KP / 16; ++k) {
+          const uint64_t da = tc::make_sdesc(sa + k * 2 * sbo_a, lbo_a, sbo_a, layout_a);
+          const uint64_t db = tc::make_sdesc(sb + k * 2 * sbo_b, lbo_b, sbo_b, 2u);
+          tc::mma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        tc::mma_commit(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      tc::mma_commit(tfull);
+    }
+  } else if (num_kb > 0) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tap = grp * p.taps_per_tile + row / p.rows_per_tap;
+    const int a = at * 128 + row % p.rows_per_tap;
+    const bool valid = tap < 25 && a < p.A;
+    float* orow = p.dW + ((int64_t)tap * p.A + a) * p.B + nt * p.NT;
+    tc::mbar_wait(tfull, 0);
+    tc::fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int cb = 0; cb < p.NT; cb += 16) {
+      float v[16];
+      tc::tmem_ld16(taddr + cb, v);
+      if (valid) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) red_add_v4(orow + cb + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+bool plan_wgrad(int Nimg, int Hb, int Wb, int A, int B, int s, WgParams* p) {
+  if (s != 1 && s != 2) return false;
+  const int Hs = Hb / s, Ws = Wb / s;
+  if (!tc_host::is_pow2(Hs) || !tc_host::is_pow2(Ws) || Ws > 64) return false;
+  if (A % 32 != 0 || (A > 64 && A % 128 != 0 && A != 64) || B % 64 != 0) return false;
+  if (A != 32 && A != 64 && A % 128 != 0) return false;
+  p->Nimg = Nimg; p->Hs = Hs; p->Ws = Ws; p->Hb = Hb; p->Wb = Wb; p->s = s; p->pad = (s == 2) ? 1 : 2;
+  p->A = A; p->B = B;
+  p->a_blk = (A % 64 == 0) ? 64 : 32;
+  p->rows_per_tap = A < 128 ? A : 128;
+  p->taps_per_tile = 128 / p->rows_per_tap;
+  p->a_tiles = (A + 127) / 128;
+  p->groups = (25 + p->taps_per_tile - 1) / p->taps_per_tile;
+  int n_tiles = (B + 255) / 256;
+  while (B % n_tiles != 0 || (B / n_tiles) % 64 != 0) { if (++n_tiles > B / 64) return false; }
+  p->n_tiles = n_tiles; p->NT = B / n_tiles;
+  p->BW = Ws < KP ? Ws : KP;
+  p->BH = (KP / p->BW) < Hs ? (KP / p->BW) : Hs;
+  p->BN = KP / (p->BW * p->BH);
+  if (p->BW * p->BH * p->BN != KP) return false;
+  p->pbW = Ws / p->BW; p->pbH = Hs / p->BH; p->pbN = (Nimg + p->BN - 1) / p->BN;
+  p->total_kb = p->pbW * p->pbH * p->pbN;
+  p->a_bytes = KP * 128 * 2;
+  p->stage_bytes = p->a_bytes + KP * p->NT * 2;
+  int st = SMEM_BUDGET / p->stage_bytes;
+  p->stages = st > MAX_STAGES ? MAX_STAGES : st;
+  if (p->stages < 2) return false;
+  const int tiles = p->groups * p->a_tiles * p->n_tiles;
+  int slices = (2 * lg_num_sms() + tiles - 1) / tiles;
+  int max_slices = (p->total_kb + 3) / 4;                 // at least ~4 k-blocks per CTA
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  p->kb_per_slice = (p->total_kb + slices - 1) / slices;
+  return true;
+}
+
+}  // namespace
+
+int lg_tc_wgrad_supported(int Nimg, int Hb, int Wb, int A, int B, int s) {
+  WgParams p;
+  return plan_wgrad(Nimg, Hb, Wb, A, B, s, &p) ? 1 : 0;
+}
+
+int lg_tc_wgrad(const void* big, const void* small, float* dW, int Nimg, int Hb, int Wb, int A, int B, int s,
+                cudaStream_t st) {
+  WgParams p;
+  if (!plan_wgrad(Nimg, Hb, Wb, A, B, s, &p)) {
+    lg_set_error("tcgen05 wgrad: unsupported geometry");
+    return LG_ERR_UNSUPPORTED;
+  }
+  p.dW = dW;
+  CUtensorMap tmBig, tmSmall;
+  const CUtensorMapSwizzle sw_a = p.a_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  int e = tc_host::encode_act_map(&tmBig, big, Nimg, Hb, Wb, A, p.a_blk, p.BW, p.BH, p.BN, s, sw_a);
+  if (e) return e;
+  e = tc_host::encode_act_map(&tmSmall, small, Nimg, p.Hs, p.Ws, B, 64, p.BW, p.BH, p.BN, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (e) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const size_t shm = (size_t)p.stages * p.stage_bytes + 1024 + 256;
+  const int tiles = p.groups * p.a_tiles * p.n_tiles;
+  const int slices = (p.total_kb + p.kb_per_slice - 1) / p.kb_per_slice;
+  tc_wgrad_kernel<<<dim3(tiles, slices), NUM_THREADS, shm, st>>>(tmBig, tmSmall, p);
+  return LG_OK;
+}

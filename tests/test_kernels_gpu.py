@@ -293,3 +293,30 @@ def test_tc_dgrad(geom):
     assert rel_err(out, ref) < 1e-2
     ref_stats = torch.stack([pre.reshape(N, -1).sum(1), (pre.reshape(N, -1) ** 2).sum(1)], 1)
     assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
+
+
+TC_W = [
+    (4, 64, 64, 64, 128, 2),     # enc2 / dec3: 2 taps per 128-row tile
+    (6, 32, 32, 128, 256, 2),    # enc3 / dec2
+    (5, 16, 16, 256, 384, 2),    # enc4 / dec1: 2 a-tiles, b split 2 x 192, 8x8 position boxes (odd batch)
+    (3, 128, 128, 32, 64, 2),    # dec4: 32-channel boxes (SWIZZLE_64B), 4 taps per tile
+    (2, 32, 32, 64, 64, 1),      # stride 1
+]
+
+
+@pytest.mark.parametrize("geom", TC_W)
+def test_tc_wgrad(geom):
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = geom
+    assert K.tc_supported(K.OP_WGRAD, N, Hb, Wb, A, B, s)
+    big = _rand((N, Hb, Wb, A), 7, torch.bfloat16)
+    small = _rand((N, Hb // s, Wb // s, B), 8, torch.bfloat16)
+    W = torch.zeros(5, 5, A, B, dtype=torch.float64, requires_grad=True)
+    y = O.conv2d_same(big.double(), W, torch.zeros(B, dtype=torch.float64), s)
+    (ref,) = torch.autograd.grad((y * small.double()).sum(), W)
+    dW = torch.zeros(5, 5, A, B, dtype=torch.float32, device="cuda")
+    K.conv2d_wgrad(big.cuda(), small.cuda(), dW, s, use_tc=True)
+    torch.cuda.synchronize()
+    assert rel_err(dW, ref) < 1e-4          # bf16 operands are exact inputs; accumulation is fp32
+    K.conv2d_wgrad(big.cuda(), small.cuda(), dW, s, use_tc=True)
+    assert rel_err(dW, 2 * ref) < 1e-4
