@@ -74,6 +74,15 @@ int lg_conv2d_dgrad(const void* small, const float* W, const void* wpack, const 
 int lg_conv2d_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb,
                     int A, int B, int stride, int dtype, int use_tc, void* stream);
 
+/* wgrad on the tcgen05 path when `big` is stored with A_big >= A channels (zero padded so that TMA can
+ * fetch it: the 3-channel image layers use A_big = 16).  dW stays [5,5,A,B]; bf16 activations only. */
+int lg_conv2d_wgrad_padded(const void* big, const void* small, float* dW, int N, int Hb, int Wb,
+                           int A_big, int A, int B, int stride, void* stream);
+
+/* dst[row, 0:Cpad] = (src[row, 0:C], 0, ..., 0): channel padding of an NHWC tensor (rows = N*H*W). */
+int lg_pad_channels(const void* src, void* dst, int64_t rows, int C, int Cpad, int dtype,
+                    void* stream);
+
 /* Conv2DTranspose spelled out (thin aliases; same arithmetic as above). */
 int lg_conv2d_transpose_fprop(const void* x_small, const float* W, const void* wpack,
                               const float* bias, void* y_big, double* stats, int N, int Hb, int Wb,

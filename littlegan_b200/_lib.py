@@ -25,6 +25,8 @@ SIGNATURES = {
     "lg_conv2d_fprop": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_conv2d_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lg_conv2d_wgrad_padded": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lg_pad_channels": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
     "lg_conv2d_transpose_fprop": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_conv2d_transpose_dgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_pack_conv_weights": (_i64, [_vp, _vp, _i, _i, _vp]),

@@ -93,6 +93,16 @@ extern "C" int lg_conv2d_wgrad(const void* big, const void* small, float* dW, in
   return LG_OK;
 }
 
+extern "C" int lg_conv2d_wgrad_padded(const void* big, const void* small, float* dW, int N, int Hb, int Wb,
+                                      int A_big, int A, int B, int stride, void* stream) {
+  if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, LG_BF16)) return e;
+  LG_REQUIRE(big && small && dW && A_big >= A, "bad arguments");
+  int e = lg_tc_wgrad_padded(big, small, dW, N, Hb, Wb, A_big, A, B, stride, (cudaStream_t)stream);
+  if (e) return e;
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
 extern "C" int lg_conv2d_transpose_fprop(const void* x_small, const float* W, const void* wpack,
                                          const float* bias, void* y_big, double* stats, int N, int Hb, int Wb,
                                          int A_out, int B_in, int stride, int act, int dtype, int use_tc,

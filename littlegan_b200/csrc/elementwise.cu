@@ -318,6 +318,18 @@ __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = from_f<D>(to_f(s[i]));
 }
 
+// dst[row][0..Cp) = src[row][0..C) followed by zeros (3-channel images -> 16-channel TMA-able rows)
+template <typename T>
+__global__ void pad_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t rows, int C, int Cp) {
+  const int64_t total = rows * Cp;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / Cp;
+    const int c = (int)(i - r * Cp);
+    dst[i] = c < C ? src[r * C + c] : from_f<T>(0.f);
+  }
+}
+
 // W[25][A][B] fp32 -> Wt[25][Ap][Bp] bf16 (b contiguous), Wf[25][Bp][Ap] bf16 (a contiguous)
 __global__ void pack_weights_kernel(const float* __restrict__ W, bf16* __restrict__ Wt, bf16* __restrict__ Wf, int A,
                                     int B, int Ap, int Bp) {
@@ -533,6 +545,19 @@ extern "C" int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int
   else if (src_dtype == LG_BF16 && dst_dtype == LG_F32) cast_kernel<bf16, float><<<gsz, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
   else if (src_dtype == LG_F32 && dst_dtype == LG_F32) cast_kernel<float, float><<<gsz, 256, 0, st>>>((const float*)src, (float*)dst, n);
   else cast_kernel<bf16, bf16><<<gsz, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_pad_channels(const void* src, void* dst, int64_t rows, int C, int Cpad, int dtype, void* stream) {
+  LG_REQUIRE(src && dst && rows > 0 && C > 0 && Cpad >= C, "bad arguments");
+  const int64_t total = rows * Cpad;
+  int64_t need = (total + 255) / 256, cap = (int64_t)lg_num_sms() * 16;
+  int gsz = (int)(need < cap ? need : cap);
+  if (dtype == LG_BF16)
+    pad_channels_kernel<bf16><<<gsz, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows, C, Cpad);
+  else
+    pad_channels_kernel<float><<<gsz, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, rows, C, Cpad);
   LG_LAUNCH_CHECK();
   return LG_OK;
 }

@@ -18,4 +18,6 @@ int lg_tc_dgrad(const void* small, const void* wpack, const float* bias, void* o
                 int Hb, int Wb, int A, int B, int s, int act, cudaStream_t st);
 int lg_tc_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A, int B,
                 int s, cudaStream_t st);
+int lg_tc_wgrad_padded(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A, int A_real,
+                       int B, int s, cudaStream_t st);
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N);

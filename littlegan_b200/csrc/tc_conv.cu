@@ -35,7 +35,7 @@ struct TcParams {
   int Nimg, Hs, Ws, Hb, Wb, s, pad;
   int Kch;        // contraction channels per tap (A for fprop, B for dgrad)
   int Nch;        // real output channels (B for fprop, A for dgrad)
-  int KC;         // channel chunk per k-block (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B)
+  int KC;         // channel chunk per k-block (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B)
   int NT;         // UMMA N (output-channel tile, multiple of 16)
   int n_tiles;    // channel tiles
   int BW, BH, BN; // tile box in small-map coordinates, BW*BH*BN == 128
@@ -143,7 +143,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(TILE_M, p.NT, 0, 0);
-      const uint32_t layout = (p.KC == 64) ? 2u : 4u;          // SWIZZLE_128B / SWIZZLE_64B
+      const uint32_t layout = (p.KC == 64) ? 2u : (p.KC == 32) ? 4u : 6u;   // SWIZZLE_128B / 64B / 32B
       const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;            // 8 rows of KC bf16
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -264,12 +264,12 @@ bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
   if (!is_pow2(Hs) || !is_pow2(Ws) || Ws > 128 || Hs * Ws < 32) return false;
   const int Kch = (op == OP_F) ? A : B;
   const int Nch = (op == OP_F) ? B : A;
-  if (Kch % 32 != 0) return false;
+  if (Kch % 16 != 0) return false;
   const int Npad = (Nch + 15) / 16 * 16;
   int n_tiles = (Npad + 255) / 256;
   if (Npad % n_tiles != 0 || (Npad / n_tiles) % 16 != 0) return false;
   p->Nimg = Nimg; p->Hs = Hs; p->Ws = Ws; p->Hb = Hb; p->Wb = Wb; p->s = s; p->pad = (s == 2) ? 1 : 2;
-  p->Kch = Kch; p->Nch = Nch; p->KC = (Kch % 64 == 0) ? 64 : 32;
+  p->Kch = Kch; p->Nch = Nch; p->KC = (Kch % 64 == 0) ? 64 : (Kch % 32 == 0) ? 32 : 16;
   p->NT = Npad / n_tiles; p->n_tiles = n_tiles;
   p->BW = Ws < 128 ? Ws : 128;
   p->BH = (128 / p->BW) < Hs ? (128 / p->BW) : Hs;
@@ -318,7 +318,8 @@ int launch_tc(const void* act_in, const void* wpack, const float* bias, void* ou
   const int Ap = (A + 15) / 16 * 16, Bp = (B + 15) / 16 * 16;
   const bf16* wt = (const bf16*)wpack;                  // [25][Ap][Bp]
   const bf16* wf = wt + (size_t)25 * Ap * Bp;           // [25][Bp][Ap]
-  const CUtensorMapSwizzle sw = p.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle sw = p.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : p.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap tmA, tmB;
   int e;
   if (OP == OP_F) {

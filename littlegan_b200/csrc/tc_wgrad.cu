@@ -30,7 +30,9 @@ constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct WgParams {
   int Nimg, Hs, Ws, Hb, Wb, s, pad, A, B;
-  int a_blk;            // channels per big-map TMA box: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+  int A_real;           // rows of dW per tap (A may be zero-padded storage, e.g. 3 -> 16)
+  int b_blk;            // channels per small-map TMA box: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+  int a_blk;            // channels per big-map TMA box: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B), 16 (SWIZZLE_32B)
   int rows_per_tap;     // min(A, 128)
   int taps_per_tile;    // 128 / rows_per_tap
   int a_tiles;          // ceil(A / 128)
@@ -84,9 +86,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int nbox_a = 128 / p.a_blk;                 // big-map boxes per stage
-  const int nbox_b = p.NT / 64;                     // small-map boxes per stage
+  const int nbox_b = p.NT / p.b_blk;                // small-map boxes per stage
   const int a_box_bytes = KP * p.a_blk * 2;
-  const int b_box_bytes = KP * 64 * 2;
+  const int b_box_bytes = KP * p.b_blk * 2;
 
   if (warp == 0) {
     if (lane == 0 && num_kb > 0) {
@@ -111,17 +113,18 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
                           p.s * i0 + ky - p.pad, n0);
         }
         for (int bi = 0; bi < nbox_b; ++bi)
-          tc::tma_load_4d(sb + bi * b_box_bytes, &tmSmall, &full[stage], nt * p.NT + bi * 64, j0, i0, n0);
+          tc::tma_load_4d(sb + bi * b_box_bytes, &tmSmall, &full[stage], nt * p.NT + bi * p.b_blk, j0, i0, n0);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && num_kb > 0) {
       const uint32_t idesc = tc::make_idesc(128, p.NT, 1, 1);        // both operands MN-major
-      const uint32_t layout_a = (p.a_blk == 64) ? 2u : 4u;
+      const uint32_t layout_a = (p.a_blk == 64) ? 2u : (p.a_blk == 32) ? 4u : 6u;
       const uint32_t sbo_a = 8u * (uint32_t)p.a_blk * 2u;            // 8 positions x a_blk channels
       const uint32_t lbo_a = (uint32_t)a_box_bytes;                  // next block of a_blk channels
-      const uint32_t sbo_b = 1024u, lbo_b = (uint32_t)b_box_bytes;
+      const uint32_t layout_b = (p.b_blk == 64) ? 2u : 4u;
+      const uint32_t sbo_b = 8u * (uint32_t)p.b_blk * 2u, lbo_b = (uint32_t)b_box_bytes;
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         tc::mbar_wait(&full[stage], phase);
@@ -131,7 +134,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
 #pragma unroll
         for (int k = 0; k < KP / 16; ++k) {
           const uint64_t da = tc::make_sdesc(sa + k * 2 * sbo_a, lbo_a, sbo_a, layout_a);
-          const uint64_t db = tc::make_sdesc(sb + k * 2 * sbo_b, lbo_b, sbo_b, 2u);
+          const uint64_t db = tc::make_sdesc(sb + k * 2 * sbo_b, lbo_b, sbo_b, layout_b);
           tc::mma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
         }
         tc::mma_commit(&empty[stage]);
@@ -144,8 +147,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
     const int row = q * 32 + lane;
     const int tap = grp * p.taps_per_tile + row / p.rows_per_tap;
     const int a = at * 128 + row % p.rows_per_tap;
-    const bool valid = tap < 25 && a < p.A;
-    float* orow = p.dW + ((int64_t)tap * p.A + a) * p.B + nt * p.NT;
+    const bool valid = tap < 25 && a < p.A_real;
+    float* orow = p.dW + ((int64_t)tap * p.A_real + a) * p.B + nt * p.NT;
     tc::mbar_wait(tfull, 0);
     tc::fence_after_sync();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -167,21 +170,23 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
   }
 }
 
-bool plan_wgrad(int Nimg, int Hb, int Wb, int A, int B, int s, WgParams* p) {
+// A = channels of `big` as stored (16, 32, 64 or a multiple of 128); A_real <= A rows of dW per tap.
+bool plan_wgrad(int Nimg, int Hb, int Wb, int A, int A_real, int B, int s, WgParams* p) {
   if (s != 1 && s != 2) return false;
   const int Hs = Hb / s, Ws = Wb / s;
-  if (!tc_host::is_pow2(Hs) || !tc_host::is_pow2(Ws) || Ws > 64) return false;
-  if (A % 32 != 0 || (A > 64 && A % 128 != 0 && A != 64) || B % 64 != 0) return false;
-  if (A != 32 && A != 64 && A % 128 != 0) return false;
+  if (!tc_host::is_pow2(Hs) || !tc_host::is_pow2(Ws) || Ws > 128 || Hs * Ws < KP) return false;
+  if ((B % 64 != 0 && B != 32) || A_real > A || A_real < 1) return false;
+  if (A != 16 && A != 32 && A != 64 && A % 128 != 0) return false;
   p->Nimg = Nimg; p->Hs = Hs; p->Ws = Ws; p->Hb = Hb; p->Wb = Wb; p->s = s; p->pad = (s == 2) ? 1 : 2;
-  p->A = A; p->B = B;
-  p->a_blk = (A % 64 == 0) ? 64 : 32;
+  p->A = A; p->A_real = A_real; p->B = B;
+  p->a_blk = (A % 64 == 0) ? 64 : A;
   p->rows_per_tap = A < 128 ? A : 128;
   p->taps_per_tile = 128 / p->rows_per_tap;
   p->a_tiles = (A + 127) / 128;
   p->groups = (25 + p->taps_per_tile - 1) / p->taps_per_tile;
+  p->b_blk = (B % 64 == 0) ? 64 : 32;
   int n_tiles = (B + 255) / 256;
-  while (B % n_tiles != 0 || (B / n_tiles) % 64 != 0) { if (++n_tiles > B / 64) return false; }
+  while (B % n_tiles != 0 || (B / n_tiles) % p->b_blk != 0) { if (++n_tiles > B / p->b_blk) return false; }
   p->n_tiles = n_tiles; p->NT = B / n_tiles;
   p->BW = Ws < KP ? Ws : KP;
   p->BH = (KP / p->BW) < Hs ? (KP / p->BW) : Hs;
@@ -207,22 +212,29 @@ bool plan_wgrad(int Nimg, int Hb, int Wb, int A, int B, int s, WgParams* p) {
 
 int lg_tc_wgrad_supported(int Nimg, int Hb, int Wb, int A, int B, int s) {
   WgParams p;
-  return plan_wgrad(Nimg, Hb, Wb, A, B, s, &p) ? 1 : 0;
+  return plan_wgrad(Nimg, Hb, Wb, A, A, B, s, &p) ? 1 : 0;
 }
 
 int lg_tc_wgrad(const void* big, const void* small, float* dW, int Nimg, int Hb, int Wb, int A, int B, int s,
                 cudaStream_t st) {
+  return lg_tc_wgrad_padded(big, small, dW, Nimg, Hb, Wb, A, A, B, s, st);
+}
+
+int lg_tc_wgrad_padded(const void* big, const void* small, float* dW, int Nimg, int Hb, int Wb, int A, int A_real,
+                       int B, int s, cudaStream_t st) {
   WgParams p;
-  if (!plan_wgrad(Nimg, Hb, Wb, A, B, s, &p)) {
+  if (!plan_wgrad(Nimg, Hb, Wb, A, A_real, B, s, &p)) {
     lg_set_error("tcgen05 wgrad: unsupported geometry");
     return LG_ERR_UNSUPPORTED;
   }
   p.dW = dW;
   CUtensorMap tmBig, tmSmall;
-  const CUtensorMapSwizzle sw_a = p.a_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle sw_a = p.a_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : p.a_blk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   int e = tc_host::encode_act_map(&tmBig, big, Nimg, Hb, Wb, A, p.a_blk, p.BW, p.BH, p.BN, s, sw_a);
   if (e) return e;
-  e = tc_host::encode_act_map(&tmSmall, small, Nimg, p.Hs, p.Ws, B, 64, p.BW, p.BH, p.BN, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  e = tc_host::encode_act_map(&tmSmall, small, Nimg, p.Hs, p.Ws, B, p.b_blk, p.BW, p.BH, p.BN, 1,
+                              p.b_blk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (e) return e;
   static bool attr_set = false;
   if (!attr_set) {

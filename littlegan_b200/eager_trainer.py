@@ -230,7 +230,7 @@ class EagerTrainer:
         E.encoder_backward(rt, D.encoder, ectx, g4, wgrad=True, input_grad=False)
 
         # ---- gen_tape.gradient(gen_loss, G weights): dgrad-only through D(fake), then G (:149)
-        ectx_f = [(x[B:], z[B:], st[B:]) for (x, z, st) in ectx]
+        ectx_f = [(x[B:], z[B:], st[B:], None) for (x, z, st, _) in ectx]
         g4 = E.disc_heads_backward(rt, D, outs[3][B:], dl_pr_g, dl_c_g, wgrad=False)
         g_img = E.encoder_backward(rt, D.encoder, ectx_f, g4, wgrad=False, input_grad=True)
         dpre = torch.empty_like(fake)

@@ -43,6 +43,15 @@ class Runtime:
         return torch.zeros(*shape, dtype=dtype, device=self.device)
 
 
+def _padded_for_tc(rt, x, op, B, s):
+    """3-channel maps cannot be fetched by TMA (6-byte pixels): give the tcgen05 path a copy padded
+    to 16 channels (one cheap pass over a tensor that is 1/20th of the layer's output)."""
+    N, Hb, Wb, A = x.shape
+    if A >= 16 or not rt.want_tc or not rt.use_tc(op, N, Hb, Wb, 16, B, s):
+        return None
+    return K.pad_channels(x, rt.empty(N, Hb, Wb, 16))
+
+
 def _grad(p):
     """Gradient slot of a parameter (a view into the trainer's flat gradient arena)."""
     g = getattr(p, "lg_grad", None)
@@ -74,11 +83,15 @@ def encoder_forward(rt, enc, x):
         _, Hb, Wb, A = x.shape
         B = conv.filters
         z = rt.empty(N, Hb // 2, Wb // 2, B)
-        tc = rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, 2)
-        K.conv2d_fprop(x, conv.kernel, conv.bias, z, stats[i], 2, conv.wpack, tc)
+        xpad = _padded_for_tc(rt, x, K.OP_FPROP, B, 2)
+        if xpad is not None:
+            K.conv2d_fprop(xpad, conv.kernel, conv.bias, z, stats[i], 2, conv.wpack, True)
+        else:
+            tc = rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, 2)
+            K.conv2d_fprop(x, conv.kernel, conv.bias, z, stats[i], 2, conv.wpack, tc)
         a = rt.empty(N, Hb // 2, Wb // 2, B)
         K.instnorm_act_fwd(z, stats[i], norm.gamma, norm.beta, None, a, norm.epsilon, 1.0, rt.alpha)
-        ctx.append((x, z, stats[i]))
+        ctx.append((x, z, stats[i], xpad))
         outs.append(a)
         x = a
     return outs, ctx
@@ -91,7 +104,7 @@ def encoder_backward(rt, enc, ctx, g, wgrad, input_grad):
     red = rt.zeros(4, N, 2)
     for i in (3, 2, 1, 0):
         conv, norm = enc.convs[i], enc.norms[i]
-        x, z, stats = ctx[i]
+        x, z, stats, xpad = ctx[i]
         dz = torch.empty_like(z)
         K.instnorm_act_bwd(g.view_as(z), z, stats, norm.gamma, norm.beta, red[i], dz,
                            _grad(norm.gamma) if wgrad else None, _grad(norm.beta) if wgrad else None,
@@ -100,7 +113,10 @@ def encoder_backward(rt, enc, ctx, g, wgrad, input_grad):
         B = conv.filters
         if wgrad:
             K.bias_grad(dz, _grad(conv.bias))
-            K.conv2d_wgrad(x, dz, _grad(conv.kernel), 2, rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2))
+            if xpad is not None and rt.use_tc(K.OP_WGRAD, N, Hb, Wb, 16, B, 2):
+                K.conv2d_wgrad_padded(xpad, dz, _grad(conv.kernel), 2)
+            else:
+                K.conv2d_wgrad(x, dz, _grad(conv.kernel), 2, rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2))
         if i > 0 or input_grad:
             g = torch.empty_like(x)
             K.conv2d_dgrad(dz, conv.kernel, None, g, None, 2, K.ACT_NONE, conv.wpack,
@@ -172,11 +188,18 @@ def final_conv_backward(rt, conv, x, dpre, wgrad):
     """dpre: gradient w.r.t. the pre-tanh output.  Returns the gradient w.r.t. x."""
     N, H, W, B = x.shape
     A = conv.filters
+    dpad = _padded_for_tc(rt, dpre, K.OP_FPROP, B, 1)
     if wgrad:
         K.bias_grad(dpre, _grad(conv.bias))
-        K.conv2d_wgrad(dpre, x, _grad(conv.kernel), 1, rt.use_tc(K.OP_WGRAD, N, H, W, A, B, 1))
+        if dpad is not None and rt.use_tc(K.OP_WGRAD, N, H, W, 16, B, 1):
+            K.conv2d_wgrad_padded(dpad, x, _grad(conv.kernel), 1)
+        else:
+            K.conv2d_wgrad(dpre, x, _grad(conv.kernel), 1, rt.use_tc(K.OP_WGRAD, N, H, W, A, B, 1))
     g = torch.empty_like(x)
-    K.conv2d_fprop(dpre, conv.kernel, None, g, None, 1, conv.wpack, rt.use_tc(K.OP_FPROP, N, H, W, A, B, 1))
+    if dpad is not None:
+        K.conv2d_fprop(dpad, conv.kernel, None, g, None, 1, conv.wpack, True)
+    else:
+        K.conv2d_fprop(dpre, conv.kernel, None, g, None, 1, conv.wpack, rt.use_tc(K.OP_FPROP, N, H, W, A, B, 1))
     return g
 
 

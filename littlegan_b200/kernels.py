@@ -91,6 +91,22 @@ def conv2d_wgrad(big, small, dW, stride, use_tc=False):
                                       _st()), "lg_conv2d_wgrad")
 
 
+def conv2d_wgrad_padded(big_padded, small, dW, stride):
+    """tcgen05 wgrad with a channel-padded `big` ([N,Hb,Wb,A_big], A_big >= dW.shape[2])."""
+    _cuda(big_padded, small, dW)
+    N, Hb, Wb, A_big = big_padded.shape
+    A, B = dW.shape[2], dW.shape[3]
+    check(_lib.load().lg_conv2d_wgrad_padded(_p(big_padded), _p(small), _p(dW), N, Hb, Wb, A_big, A, B, stride,
+                                             _st()), "lg_conv2d_wgrad_padded")
+
+
+def pad_channels(src, dst):
+    _cuda(src, dst)
+    C, Cp = src.shape[-1], dst.shape[-1]
+    check(_lib.load().lg_pad_channels(_p(src), _p(dst), src.numel() // C, C, Cp, dt(src), _st()), "lg_pad_channels")
+    return dst
+
+
 def pack_conv_weights_bytes(A, B):
     return int(_lib.check(_lib.load().lg_pack_conv_weights(None, None, A, B, None)))
 
