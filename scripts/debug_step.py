@@ -5,9 +5,11 @@ from tests.util import *
 from tests.test_train_step_gpu import _setup, _ListIterator
 batch_no = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 oargs = small_args(use_partition=True)
+if len(sys.argv) > 2 and sys.argv[2] == "full":
+    oargs = O.make_args(cond_dim=40, batch_size=2, use_partition=False)
 pargs, gen, disc, adj, trainer, W = _setup(oargs, "fp32")
 ot = O.OracleTrainer(oargs, W, dtype=torch.float64)
-i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=5)
+i1, c1, i2, c2, noise = O.synthetic_batch(oargs, oargs.batch_size, seed=5)
 ref = ot.train_step(batch_no, i1, c1, i2, c2, noise, return_grads=True)
 res = trainer._train_step(batch_no, _ListIterator([(i1, c1), (i2, c2)]), noise=noise)
 names = {"D": disc.weights, "G": gen.weights, "A": adj.weights[16:20]}
