@@ -268,7 +268,13 @@ def run_product(a):
                               "PyTorch-CPU fp32 (TF 1.15 not installable)"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured graphs hold NCCL work; tearing the communicator down underneath them can block.
+        # Everything is measured and printed: synchronise, then leave without the destructor chain.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
