@@ -67,7 +67,11 @@ extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wp
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc) {
     LG_REQUIRE(dtype == LG_BF16 && wpack, "tcgen05 path needs LG_BF16 activations and packed weights");
-    int e = lg_tc_dgrad(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
+    int e;
+    if (W && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, stride))      // RGB layers: GEMM + col2im
+      e = lg_tc_deconv_small(small, W, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
+    else
+      e = lg_tc_dgrad(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
     if (e) return e;
   } else {
     LG_REQUIRE(W, "NULL weights");

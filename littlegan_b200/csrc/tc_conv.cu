@@ -349,6 +349,7 @@ int lg_tc_wgrad_supported(int Nimg, int Hb, int Wb, int A, int B, int s);   // t
 
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N) {
   if (op == LG_OP_WGRAD) return lg_tc_wgrad_supported(N, Hb, Wb, A, B, s);
+  if (op == LG_OP_DGRAD && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, s)) return 1;
   TcParams p;
   return plan(op == LG_OP_FPROP ? OP_F : OP_T, N, Hb, Wb, A, B, s, &p) ? 1 : 0;
 }
