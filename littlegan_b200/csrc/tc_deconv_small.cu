@@ -44,6 +44,7 @@ struct DsParams {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+template <int S, int A>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -133,7 +134,6 @@ tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p
     const int et = q * 32 + lane;        // 0..127: TMEM lane of this thread / epilogue thread id
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t tphase = 0;
-    const int OT = p.out_t;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int n = t / per_img, r = t - n * per_img;
       const int ti = r / p.tilesW, tj = r - ti * p.tilesW;
@@ -156,37 +156,53 @@ tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p
       epi_bar_sync();                                               // staging complete
 
       // col2im gather: output pixel (Y0+oy, X0+ox); input row/col of tap k: (Y + pad - k)/s, local = - origin
-      const int Y0 = p.s * ti * in_t, X0 = p.s * tj * in_t;
-      const int iy0 = ti * in_t - p.halo, ix0 = tj * in_t - p.halo;
+      const int Y0 = S * ti * in_t, X0 = S * tj * in_t;
       float s1 = 0.f, s2 = 0.f;
-      for (int o = et; o < OT * OT; o += 128) {
-        const int oy = o / OT, ox = o - oy * OT;
-        const int Y = Y0 + oy, X = X0 + ox;
-        if (Y >= p.Hb || X >= p.Wb) continue;
-        float acc[5];
+      float bia[A];
 #pragma unroll
-        for (int a = 0; a < 5; ++a) acc[a] = (a < p.A && p.bias) ? p.bias[a] : 0.f;
-        for (int ky = 0; ky < 5; ++ky) {
-          const int dy = Y + p.pad - ky;
-          if (dy % p.s != 0) continue;
-          const int li = dy / p.s - iy0;
-          for (int kx = 0; kx < 5; ++kx) {
-            const int dx = X + p.pad - kx;
-            if (dx % p.s != 0) continue;
-            const int lj = dx / p.s - ix0;
-            const float* z = Zs + (li * TILE + lj) * ZP + (ky * 5 + kx) * p.A;
+      for (int a = 0; a < A; ++a) bia[a] = p.bias ? p.bias[a] : 0.f;
+      // Outputs are walked per phase (py,px) = (Y,X) mod S so that the tap set is a compile-time
+      // list: tap ky_m = pad_ - py + S*m reads tile row oy2 + HALO + (py >= pad_ ...) - m (see below).
+      constexpr int IN_T = TILE - 2 * (S == 2 ? 1 : 2);            // 14 (s=2) / 12 (s=1) interior pixels
 #pragma unroll
-            for (int a = 0; a < 5; ++a) if (a < p.A) acc[a] += z[a];
-          }
-        }
-        bf16* dst = p.out + (((int64_t)n * p.Hb + Y) * p.Wb + X) * p.A;
+      for (int py = 0; py < S; ++py) {
 #pragma unroll
-        for (int a = 0; a < 5; ++a) {
-          if (a < p.A) {
-            float v = acc[a];
-            s1 += v; s2 += v * v;
-            if (p.act == LG_ACT_TANH) v = tanhf(v);
-            dst[a] = __float2bfloat16_rn(v);
+        for (int px = 0; px < S; ++px) {
+          // S == 1: ky = 0..4, tile row = oy + 4 - ky.   S == 2: ky = 1 - py + 2m, tile row = oy2 + 1 + py - m
+          constexpr int NTY = 5, NTX = 5;
+          const int nty = (S == 1) ? NTY : 2 + py, ntx = (S == 1) ? NTX : 2 + px;
+          for (int o = et; o < IN_T * IN_T; o += 128) {
+            const int oy2 = o / IN_T, ox2 = o - oy2 * IN_T;
+            const int Y = Y0 + S * oy2 + py, X = X0 + S * ox2 + px;
+            if (Y >= p.Hb || X >= p.Wb) continue;
+            float acc[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) acc[a] = bia[a];
+#pragma unroll
+            for (int my = 0; my < NTY; ++my) {
+              if (my < nty) {
+                const int ky = (S == 1) ? my : 1 - py + 2 * my;
+                const int li = (S == 1) ? oy2 + 4 - my : oy2 + 1 + py - my;
+#pragma unroll
+                for (int mx = 0; mx < NTX; ++mx) {
+                  if (mx < ntx) {
+                    const int kx = (S == 1) ? mx : 1 - px + 2 * mx;
+                    const int lj = (S == 1) ? ox2 + 4 - mx : ox2 + 1 + px - mx;
+                    const float* z = Zs + (li * TILE + lj) * ZP + (ky * 5 + kx) * A;
+#pragma unroll
+                    for (int a = 0; a < A; ++a) acc[a] += z[a];
+                  }
+                }
+              }
+            }
+            bf16* dst = p.out + (((int64_t)n * p.Hb + Y) * p.Wb + X) * A;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+              float v = acc[a];
+              s1 += v; s2 += v * v;
+              if (p.act == LG_ACT_TANH) v = tanhf(v);
+              dst[a] = __float2bfloat16_rn(v);
+            }
           }
         }
       }
@@ -208,7 +224,7 @@ tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p
 
 bool plan_ds(int Nimg, int Hb, int Wb, int A, int B, int s, DsParams* p) {
   if (s != 1 && s != 2) return false;
-  if (A < 1 || A > 5 || (B != 32 && B != 64)) return false;
+  if (A != 3 || (B != 32 && B != 64)) return false;      // instantiated for the RGB layers
   const int Hs = Hb / s, Ws = Wb / s;
   if (Hs < TILE || Ws < TILE) return false;
   p->Nimg = Nimg; p->Hs = Hs; p->Ws = Ws; p->Hb = Hb; p->Wb = Wb; p->s = s;
@@ -245,11 +261,13 @@ int lg_tc_deconv_small(const void* small, const float* W, const float* bias, voi
   if (e) return e;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_deconv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_deconv_small_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_deconv_small_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const size_t shm = (size_t)STAGES * p.a_bytes + ((p.NZ * B * 2 + 1023) & ~1023) + 256 * ZP * 4 + 1024 + 256;
   const int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
-  tc_deconv_small_kernel<<<grid, NUM_THREADS, shm, st>>>(tmA, p);
+  if (s == 1) tc_deconv_small_kernel<1, 3><<<grid, NUM_THREADS, shm, st>>>(tmA, p);
+  else tc_deconv_small_kernel<2, 3><<<grid, NUM_THREADS, shm, st>>>(tmA, p);
   return LG_OK;
 }
