@@ -48,7 +48,11 @@ extern "C" int lg_conv2d_fprop(const void* big, const float* W, const void* wpac
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc) {
     LG_REQUIRE(dtype == LG_BF16 && wpack, "tcgen05 path needs LG_BF16 activations and packed weights");
-    int e = lg_tc_fprop(big, wpack, bias, small_out, stats, N, Hb, Wb, A, B, stride, st);
+    int e;
+    if (W && lg_tc_cin3_supported(N, Hb, Wb, A, B, stride))              // RGB input: in-smem im2col
+      e = lg_tc_cin3_fprop(big, W, bias, small_out, stats, N, Hb, Wb, B, stride, st);
+    else
+      e = lg_tc_fprop(big, wpack, bias, small_out, stats, N, Hb, Wb, A, B, stride, st);
     if (e) return e;
   } else {
     LG_REQUIRE(W, "NULL weights");
@@ -88,7 +92,11 @@ extern "C" int lg_conv2d_wgrad(const void* big, const void* small, float* dW, in
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc) {
     LG_REQUIRE(dtype == LG_BF16, "tcgen05 path needs LG_BF16 activations");
-    int e = lg_tc_wgrad(big, small, dW, N, Hb, Wb, A, B, stride, st);
+    int e;
+    if (lg_tc_cin3_supported(N, Hb, Wb, A, B, stride))
+      e = lg_tc_cin3_wgrad(big, small, dW, N, Hb, Wb, B, stride, st);
+    else
+      e = lg_tc_wgrad(big, small, dW, N, Hb, Wb, A, B, stride, st);
     if (e) return e;
   } else {
     lg_simt_wgrad(big, small, dW, N, Hb, Wb, A, B, stride, dtype, st);

@@ -348,6 +348,7 @@ int launch_tc(const void* act_in, const void* wpack, const float* bias, void* ou
 int lg_tc_wgrad_supported(int Nimg, int Hb, int Wb, int A, int B, int s);   // tc_wgrad.cu
 
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N) {
+  if (op != LG_OP_DGRAD && lg_tc_cin3_supported(N, Hb, Wb, A, B, s)) return 1;
   if (op == LG_OP_WGRAD) return lg_tc_wgrad_supported(N, Hb, Wb, A, B, s);
   if (op == LG_OP_DGRAD && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, s)) return 1;
   TcParams p;

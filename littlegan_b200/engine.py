@@ -47,7 +47,9 @@ def _padded_for_tc(rt, x, op, B, s):
     """3-channel maps cannot be fetched by TMA (6-byte pixels): give the tcgen05 path a copy padded
     to 16 channels (one cheap pass over a tensor that is 1/20th of the layer's output)."""
     N, Hb, Wb, A = x.shape
-    if A >= 16 or not rt.want_tc or not rt.use_tc(op, N, Hb, Wb, 16, B, s):
+    if A >= 16 or not rt.want_tc or rt.use_tc(op, N, Hb, Wb, A, B, s):   # the RGB kernels take the image as is
+        return None
+    if not rt.use_tc(op, N, Hb, Wb, 16, B, s):
         return None
     return K.pad_channels(x, rt.empty(N, Hb, Wb, 16))
 

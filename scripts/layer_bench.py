@@ -41,6 +41,8 @@ for name, Hb, A, B, s in LAYERS:
         runs.append(("fprop", lambda: K.conv2d_fprop(big, W, bB, small, stats, s, wp, True)))
         runs.append(("wgrad", lambda: K.conv2d_wgrad(big, small, dW, s, True)))
     else:
+        runs.append(("fprop(cin3)", lambda: K.conv2d_fprop(big, W, bB, small, stats, s, wp, True)))
+        runs.append(("wgrad(cin3)", lambda: K.conv2d_wgrad(big, small, dW, s, True)))
         runs.append(("fprop(pad16)", lambda: K.conv2d_fprop(big16, W, bB, small, stats, s, wp, True)))
         runs.append(("wgrad(pad16)", lambda: K.conv2d_wgrad_padded(big16, small, dW, s)))
     runs.append(("dgrad", lambda: K.conv2d_dgrad(small, W, bA, big, stats, s, K.ACT_NONE, wp, True)))

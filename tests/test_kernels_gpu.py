@@ -323,6 +323,33 @@ def test_tc_three_channel_layers_via_padding(geom):
     assert rel_err(dW, dW_ref) < 1e-4
 
 
+@pytest.mark.parametrize("geom", [(3, 128, 128, 3, 64, 2), (2, 128, 128, 3, 32, 1), (5, 64, 64, 3, 64, 2)])
+def test_tc_cin3_fprop_wgrad(geom):
+    """RGB-input layers on the in-shared-memory im2col kernels (image NOT padded)."""
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = geom
+    assert K.tc_supported(K.OP_FPROP, N, Hb, Wb, A, B, s) and K.tc_supported(K.OP_WGRAD, N, Hb, Wb, A, B, s)
+    x = _rand((N, Hb, Wb, A), 1, torch.bfloat16)
+    W = _rand((5, 5, A, B), 2, torch.bfloat16, 0.1).float()
+    b = _rand((B,), 3, torch.float32)
+    small = _rand((N, Hb // s, Wb // s, B), 8, torch.bfloat16)
+    Wr = W.double().requires_grad_(True)
+    ref = O.conv2d_same(x.double(), Wr, b.double(), s)
+    (dW_ref,) = torch.autograd.grad((ref * small.double()).sum(), Wr)
+    out = torch.zeros(N, Hb // s, Wb // s, B, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    Wc = W.cuda()
+    K.conv2d_fprop(x.cuda(), Wc, b.cuda(), out, stats, s, wpack=_pack(Wc), use_tc=True)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2
+    ref_stats = torch.stack([ref.reshape(N, -1).sum(1), (ref.reshape(N, -1) ** 2).sum(1)], 1).detach()
+    assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
+    dW = torch.zeros(5, 5, A, B, dtype=torch.float32, device="cuda")
+    K.conv2d_wgrad(x.cuda(), small.cuda(), dW, s, use_tc=True)
+    torch.cuda.synchronize()
+    assert rel_err(dW, dW_ref) < 1e-4
+
+
 TC_W = [
     (4, 64, 64, 64, 128, 2),     # enc2 / dec3: 2 taps per 128-row tile
     (6, 32, 32, 128, 256, 2),    # enc3 / dec2
