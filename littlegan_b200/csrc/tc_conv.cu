@@ -110,6 +110,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int kc_per_tap = p.Kch / p.KC;
+  const uint32_t smem_u32 = tc::smem_u32(smem);
+  const uint32_t full_u32 = tc::smem_u32(full), empty_u32 = tc::smem_u32(empty);
+  const uint32_t stage_bytes_u = (uint32_t)p.stage_bytes, a_bytes_u = (uint32_t)p.a_bytes;
+  const int nstages = p.stages, KCc = p.KC;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -126,14 +130,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // start coordinates of the activation box (W, H) for this tap
             const int cw = (OP == OP_F) ? p.s * c.j0 + tx.d[ix] : c.j0 + tx.d[ix];
             const int chh = (OP == OP_F) ? p.s * c.i0 + ty.d[iy] : c.i0 + ty.d[iy];
+            const int n_off = c.nt * p.NT;
             for (int kc = 0; kc < kc_per_tap; ++kc) {
-              tc::mbar_wait(&empty[stage], phase ^ 1);
-              uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-              uint8_t* sb = sa + p.a_bytes;
-              tc::mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
-              tc::tma_load_4d(sa, &tmA, &full[stage], kc * p.KC, cw, chh, c.n0);
-              tc::tma_load_3d(sb, &tmB, &full[stage], kc * p.KC, c.nt * p.NT, tap);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              // hot single-thread loop: 32-bit shared addresses only, nothing recomputed per k-block
+              const uint32_t fb = full_u32 + (uint32_t)stage * 8u;
+              const uint32_t sa = smem_u32 + (uint32_t)stage * stage_bytes_u;
+              tc::mbar_wait_addr(empty_u32 + (uint32_t)stage * 8u, phase ^ 1);
+              tc::mbar_expect_tx_addr(fb, stage_bytes_u);
+              tc::tma_load_4d_addr(sa, &tmA, fb, kc * KCc, cw, chh, c.n0);
+              tc::tma_load_3d_addr(sa + a_bytes_u, &tmB, fb, kc * KCc, n_off, tap);
+              if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -143,8 +149,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(TILE_M, p.NT, 0, 0);
-      const uint32_t layout = (p.KC == 64) ? 2u : (p.KC == 32) ? 4u : 6u;   // SWIZZLE_128B / 64B / 32B
-      const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;            // 8 rows of KC bf16
+      const uint32_t layout = (KCc == 64) ? 2u : (KCc == 32) ? 4u : 6u;     // SWIZZLE_128B / 64B / 32B
+      const uint32_t sbo = 8u * (uint32_t)KCc * 2u;                        // 8 rows of KC bf16
+      // K-major swizzled descriptor: lo = start>>4 | LBO(16 B)<<16 ; hi = SBO>>4 | version<<14 | layout<<29
+      const uint32_t desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+      const uint32_t desc_lo0 = ((smem_u32 & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t stage_units = stage_bytes_u >> 4, a_units = a_bytes_u >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -155,19 +165,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
+        uint32_t accum = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
+          // hot single-thread loop: descriptor = (lo, hi); hi is invariant, lo = (smem address >> 4)
+          tc::mbar_wait_addr(full_u32 + (uint32_t)stage * 8u, phase);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + (uint32_t)p.a_bytes;
-          const int ksteps = p.KC / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = tc::make_sdesc(sa + k * 32, 16, sbo, layout);
-            const uint64_t db = tc::make_sdesc(sb + k * 32, 16, sbo, layout);
-            tc::mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+          const uint32_t a_lo = desc_lo0 + (uint32_t)stage * stage_units;
+          const uint32_t b_lo = a_lo + a_units;
+          if (KCc == 64) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
+          } else if (KCc == 32) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
+          } else {
+            tc::mma_bf16_lohi(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, accum); accum = 1;
           }
-          tc::mma_commit(&empty[stage]);                 // frees the smem slot when the MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          tc::mma_commit_addr(empty_u32 + (uint32_t)stage * 8u);   // frees the smem slot when the MMAs retire
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         tc::mma_commit(&tfull[acc]);                     // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

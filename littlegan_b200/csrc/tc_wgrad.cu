@@ -92,29 +92,39 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0 && num_kb > 0) {
+      // per-box constants (tap offset, channel) do not depend on the k-block: hoist them
+      int box_ch[8], box_dx[8], box_dy[8];
+#pragma unroll
+      for (int bi = 0; bi < 8; ++bi) {
+        const int row0 = bi * p.a_blk;
+        int tap = grp * p.taps_per_tile + row0 / p.rows_per_tap;
+        if (tap > 24) tap = 24;                                     // padding rows: computed, never stored
+        box_ch[bi] = at * 128 + row0 % p.rows_per_tap;
+        const int ky = tap / 5;
+        box_dy[bi] = ky - p.pad; box_dx[bi] = (tap - 5 * ky) - p.pad;
+      }
+      const uint32_t smem_u = tc::smem_u32(smem), full_u = tc::smem_u32(full), empty_u = tc::smem_u32(empty);
+      const uint32_t stage_bytes_u = (uint32_t)p.stage_bytes, a_bytes_u = (uint32_t)p.a_bytes;
+      const int nstages = p.stages, b_ch0 = nt * p.NT;
+      int pw = kb0 % p.pbW, ph = (kb0 / p.pbW) % p.pbH, pn = kb0 / (p.pbW * p.pbH);
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        int r = kb;
-        const int pw = r % p.pbW; r /= p.pbW;
-        const int ph = r % p.pbH;
-        const int pn = r / p.pbH;
         const int j0 = pw * p.BW, i0 = ph * p.BH, n0 = pn * p.BN;
-        tc::mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-        uint8_t* sb = sa + p.a_bytes;
-        tc::mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
-        for (int bi = 0; bi < nbox_a; ++bi) {
-          const int row0 = bi * p.a_blk;
-          int tap = grp * p.taps_per_tile + row0 / p.rows_per_tap;
-          if (tap > 24) tap = 24;                                   // padding rows: computed, never stored
-          const int ch = at * 128 + row0 % p.rows_per_tap;
-          const int ky = tap / 5, kx = tap - 5 * ky;
-          tc::tma_load_4d(sa + bi * a_box_bytes, &tmBig, &full[stage], ch, p.s * j0 + kx - p.pad,
-                          p.s * i0 + ky - p.pad, n0);
-        }
-        for (int bi = 0; bi < nbox_b; ++bi)
-          tc::tma_load_4d(sb + bi * b_box_bytes, &tmSmall, &full[stage], nt * p.NT + bi * p.b_blk, j0, i0, n0);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        const uint32_t fb = full_u + (uint32_t)stage * 8u;
+        const uint32_t sa = smem_u + (uint32_t)stage * stage_bytes_u;
+        tc::mbar_wait_addr(empty_u + (uint32_t)stage * 8u, phase ^ 1);
+        tc::mbar_expect_tx_addr(fb, stage_bytes_u);
+        const int bx = p.s * j0, by = p.s * i0;
+#pragma unroll
+        for (int bi = 0; bi < 8; ++bi)
+          if (bi < nbox_a)
+            tc::tma_load_4d_addr(sa + bi * a_box_bytes, &tmBig, fb, box_ch[bi], bx + box_dx[bi], by + box_dy[bi], n0);
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi)
+          if (bi < nbox_b)
+            tc::tma_load_4d_addr(sa + a_bytes_u + bi * b_box_bytes, &tmSmall, fb, b_ch0 + bi * p.b_blk, j0, i0, n0);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        if (++pw == p.pbW) { pw = 0; if (++ph == p.pbH) { ph = 0; ++pn; } }
       }
     }
   } else if (warp == 1) {
@@ -125,20 +135,28 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
       const uint32_t lbo_a = (uint32_t)a_box_bytes;                  // next block of a_blk channels
       const uint32_t layout_b = (p.b_blk == 64) ? 2u : 4u;
       const uint32_t sbo_b = 8u * (uint32_t)p.b_blk * 2u, lbo_b = (uint32_t)b_box_bytes;
-      int stage = 0; uint32_t phase = 0;
+      // descriptors as (lo, hi): hi = SBO>>4 | version<<14 | layout<<29 (invariant); lo = start>>4 | LBO>>4<<16
+      const uint32_t a_hi = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (layout_a << 29);
+      const uint32_t b_hi = ((sbo_b >> 4) & 0x3FFFu) | (1u << 14) | (layout_b << 29);
+      const uint32_t smem_u = tc::smem_u32(smem);
+      const uint32_t a_lo0 = ((smem_u & 0x3FFFFu) >> 4) | (((lbo_a >> 4) & 0x3FFFu) << 16);
+      const uint32_t b_lo0 = (((smem_u + (uint32_t)p.a_bytes) & 0x3FFFFu) >> 4) | (((lbo_b >> 4) & 0x3FFFu) << 16);
+      const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t a_step = (2 * sbo_a) >> 4, b_step = (2 * sbo_b) >> 4;   // 16 positions further along K
+      const uint32_t full_u = tc::smem_u32(full), empty_u = tc::smem_u32(empty);
+      const int nstages = p.stages;
+      int stage = 0; uint32_t phase = 0, accum = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        tc::mbar_wait(&full[stage], phase);
+        tc::mbar_wait_addr(full_u + (uint32_t)stage * 8u, phase);
         tc::fence_after_sync();
-        const uint32_t sa = tc::smem_u32(smem + (size_t)stage * p.stage_bytes);
-        const uint32_t sb = sa + (uint32_t)p.a_bytes;
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_units, b_lo = b_lo0 + (uint32_t)stage * stage_units;
 #pragma unroll
         for (int k = 0; k < KP / 16; ++k) {
-          const uint64_t da = tc::make_sdesc(sa + k * 2 * sbo_a, lbo_a, sbo_a, layout_a);
-          const uint64_t db = tc::make_sdesc(sb + k * 2 * sbo_b, lbo_b, sbo_b, layout_b);
-          tc::mma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+          tc::mma_bf16_lohi(tmem_base, a_lo + k * a_step, a_hi, b_lo + k * b_step, b_hi, idesc, accum);
+          accum = 1;
         }
-        tc::mma_commit(&empty[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        tc::mma_commit_addr(empty_u + (uint32_t)stage * 8u);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
       tc::mma_commit(tfull);
     }
