@@ -9,12 +9,14 @@
 // k-block straight from the NHWC tensor: element strides (s,s) implement the conv stride, negative
 // / overflowing start coordinates are zero-filled by TMA and implement the SAME padding - there is
 // no im2col buffer and no zero insertion.  The B operand (weights) is a 3-D TMA box of the packed
-// bf16 kernel.  Both land in 128B/64B-swizzled K-major tiles that tcgen05.mma consumes directly;
+// bf16 kernel.  Both land in 128B/64B/32B-swizzled K-major tiles that tcgen05.mma consumes directly;
 // accumulators live in TMEM (double buffered) and are drained by 4 epilogue warps that add the
 // bias, accumulate the per-sample InstanceNorm statistics, apply tanh where asked and store bf16.
 //
 // Persistent: grid = min(#tiles, #SMs); warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue.
+// warps 2..5 = epilogue.  The producer and MMA-issue loops are single-thread and latency bound
+// (~450 cycles per mbarrier round trip measured), so one pipeline stage carries `nsub` k-blocks
+// (up to 64 KB) and the loops use 32-bit shared addresses and loop-invariant descriptor halves.
 #include <cuda.h>
 #include <stdio.h>
 
@@ -28,7 +30,11 @@ namespace {
 constexpr int OP_F = 0, OP_T = 1;
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 192;
+// Warp roles: the epilogue owns warps 0-3 (TMEM lane quarter = warp id); the two latency-critical
+// single-thread roles get the HIGHEST warp ids because the SM's warp arbiter favours high ids.
+constexpr int PRODUCER_WARP = 4, MMA_WARP = 5;
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_SUB = 4;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
@@ -41,46 +47,45 @@ struct TcParams {
   int BW, BH, BN; // tile box in small-map coordinates, BW*BH*BN == 128
   int tilesW, tilesH, tilesN;
   int m_tiles, total_tiles, phases;
-  int stages, stage_bytes, a_bytes;
+  int a_bytes, sub_bytes, nsub, stage_bytes, stages;
   int act;
   const float* bias;
   bf16* out;
   double* stats;
 };
 
-struct TapList { int n; int k[5]; int d[5]; };
-
-// taps of one output phase along one axis: k in the phase iff (ph + pad - k) % s == 0
-__device__ __forceinline__ TapList phase_taps(int ph, int s, int pad) {
-  TapList t; t.n = 0;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    int d = ph + pad - k;
-    if (d % s == 0) { t.k[t.n] = k; t.d[t.n] = d / s; ++t.n; }
-  }
-  return t;
+// Taps of one output phase along one axis, as arithmetic (no tables):
+//   dgrad, s=2: phase ph has 2+ph taps, k = (1-ph) + 2i, input shift d = ph - i
+//   dgrad, s=1: 5 taps, k = i, d = 2 - i           fprop: 5 taps, k = i, d = i - pad
+template <int OP, int S> __device__ __forceinline__ int taps_n(int ph) { return (OP == OP_T && S == 2) ? 2 + ph : 5; }
+template <int OP, int S> __device__ __forceinline__ int tap_k(int ph, int i) { return (OP == OP_T && S == 2) ? (1 - ph) + 2 * i : i; }
+template <int OP, int S> __device__ __forceinline__ int tap_d(int ph, int i) {
+  if (OP == OP_F) return i - (S == 2 ? 1 : 2);
+  return (S == 2) ? ph - i : 2 - i;
 }
 
 struct TileCoord { int ph_y, ph_x, nt, n0, i0, j0; };
 
-template <int OP>
+template <int OP, int S>
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   TileCoord c;
-  const int per_phase = p.m_tiles * p.n_tiles;
-  int q = t / per_phase, r = t - q * per_phase;
+  const uint32_t per_phase = (uint32_t)(p.m_tiles * p.n_tiles);
+  const uint32_t q = (uint32_t)t / per_phase;
+  uint32_t r = (uint32_t)t - q * per_phase;
   // heavier phases (more taps) first: q = 0 -> (1,1), 1 -> (1,0), 2 -> (0,1), 3 -> (0,0)
-  if (OP == OP_T && p.s == 2) { c.ph_y = (q < 2) ? 1 : 0; c.ph_x = (q & 1) ? 0 : 1; }
+  if (OP == OP_T && S == 2) { c.ph_y = (q < 2) ? 1 : 0; c.ph_x = (q & 1) ? 0 : 1; }
   else { c.ph_y = 0; c.ph_x = 0; }
-  c.nt = r % p.n_tiles;
-  int mt = r / p.n_tiles;
-  int tw = mt % p.tilesW; mt /= p.tilesW;
-  int th = mt % p.tilesH;
-  int tn = mt / p.tilesH;
-  c.n0 = tn * p.BN; c.i0 = th * p.BH; c.j0 = tw * p.BW;
+  const uint32_t mt0 = r / (uint32_t)p.n_tiles;
+  c.nt = (int)(r - mt0 * (uint32_t)p.n_tiles);
+  const uint32_t mt1 = mt0 / (uint32_t)p.tilesW;
+  const uint32_t tw = mt0 - mt1 * (uint32_t)p.tilesW;
+  const uint32_t tn = mt1 / (uint32_t)p.tilesH;
+  const uint32_t th = mt1 - tn * (uint32_t)p.tilesH;
+  c.n0 = (int)tn * p.BN; c.i0 = (int)th * p.BH; c.j0 = (int)tw * p.BW;
   return c;
 }
 
-template <int OP>
+template <int OP, int S>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -96,14 +101,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_cols = (2 * p.NT <= 32) ? 32 : (2 * p.NT <= 64) ? 64 : (2 * p.NT <= 128) ? 128
                              : (2 * p.NT <= 256) ? 256 : 512;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
     for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -112,74 +117,81 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kc_per_tap = p.Kch / p.KC;
   const uint32_t smem_u32 = tc::smem_u32(smem);
   const uint32_t full_u32 = tc::smem_u32(full), empty_u32 = tc::smem_u32(empty);
-  const uint32_t stage_bytes_u = (uint32_t)p.stage_bytes, a_bytes_u = (uint32_t)p.a_bytes;
-  const int nstages = p.stages, KCc = p.KC;
+  const uint32_t stage_bytes_u = (uint32_t)p.stage_bytes, sub_bytes_u = (uint32_t)p.sub_bytes;
+  const uint32_t a_bytes_u = (uint32_t)p.a_bytes;
+  const int nstages = p.stages, KCc = p.KC, nsub = p.nsub;
 
-  if (warp == 0) {
+  if (warp == PRODUCER_WARP) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile<OP>(p, t);
-        TapList ty, tx;
-        if (OP == OP_T) { ty = phase_taps(c.ph_y, p.s, p.pad); tx = phase_taps(c.ph_x, p.s, p.pad); }
-        else { ty.n = tx.n = 5; for (int k = 0; k < 5; ++k) { ty.k[k] = tx.k[k] = k; ty.d[k] = tx.d[k] = k - p.pad; } }
-        for (int iy = 0; iy < ty.n; ++iy) {
-          for (int ix = 0; ix < tx.n; ++ix) {
-            const int tap = ty.k[iy] * 5 + tx.k[ix];
-            // start coordinates of the activation box (W, H) for this tap
-            const int cw = (OP == OP_F) ? p.s * c.j0 + tx.d[ix] : c.j0 + tx.d[ix];
-            const int chh = (OP == OP_F) ? p.s * c.i0 + ty.d[iy] : c.i0 + ty.d[iy];
-            const int n_off = c.nt * p.NT;
-            for (int kc = 0; kc < kc_per_tap; ++kc) {
-              // hot single-thread loop: 32-bit shared addresses only, nothing recomputed per k-block
-              const uint32_t fb = full_u32 + (uint32_t)stage * 8u;
-              const uint32_t sa = smem_u32 + (uint32_t)stage * stage_bytes_u;
-              tc::mbar_wait_addr(empty_u32 + (uint32_t)stage * 8u, phase ^ 1);
-              tc::mbar_expect_tx_addr(fb, stage_bytes_u);
-              tc::tma_load_4d_addr(sa, &tmA, fb, kc * KCc, cw, chh, c.n0);
+        const TileCoord c = decode_tile<OP, S>(p, t);
+        const int nty = taps_n<OP, S>(c.ph_y), ntx = taps_n<OP, S>(c.ph_x);
+        const int num_kb = nty * ntx * kc_per_tap;
+        const int bx = (OP == OP_F) ? S * c.j0 : c.j0, by = (OP == OP_F) ? S * c.i0 : c.i0;
+        const int n_off = c.nt * p.NT;
+        int iy = 0, ix = 0, kc = 0;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += nsub) {
+          const int nvalid = min(nsub, num_kb - kb0);
+          const uint32_t fb = full_u32 + (uint32_t)stage * 8u;
+          uint32_t sa = smem_u32 + (uint32_t)stage * stage_bytes_u;
+          tc::mbar_wait_addr(empty_u32 + (uint32_t)stage * 8u, phase ^ 1);
+          tc::mbar_expect_tx_addr(fb, (uint32_t)nvalid * sub_bytes_u);
+#pragma unroll
+          for (int j = 0; j < MAX_SUB; ++j) {
+            if (j < nvalid) {
+              const int tap = tap_k<OP, S>(c.ph_y, iy) * 5 + tap_k<OP, S>(c.ph_x, ix);
+              tc::tma_load_4d_addr(sa, &tmA, fb, kc * KCc, bx + tap_d<OP, S>(c.ph_x, ix), by + tap_d<OP, S>(c.ph_y, iy),
+                                   c.n0);
               tc::tma_load_3d_addr(sa + a_bytes_u, &tmB, fb, kc * KCc, n_off, tap);
-              if (++stage == nstages) { stage = 0; phase ^= 1; }
+              sa += sub_bytes_u;
+              if (++kc == kc_per_tap) { kc = 0; if (++ix == ntx) { ix = 0; ++iy; } }
             }
           }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(TILE_M, p.NT, 0, 0);
       const uint32_t layout = (KCc == 64) ? 2u : (KCc == 32) ? 4u : 6u;     // SWIZZLE_128B / 64B / 32B
       const uint32_t sbo = 8u * (uint32_t)KCc * 2u;                        // 8 rows of KC bf16
       // K-major swizzled descriptor: lo = start>>4 | LBO(16 B)<<16 ; hi = SBO>>4 | version<<14 | layout<<29
       const uint32_t desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
       const uint32_t desc_lo0 = ((smem_u32 & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t stage_units = stage_bytes_u >> 4, a_units = a_bytes_u >> 4;
+      const uint32_t stage_units = stage_bytes_u >> 4, sub_units = sub_bytes_u >> 4, a_units = a_bytes_u >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile<OP>(p, t);
-        int ntaps = 25;
-        if (OP == OP_T) ntaps = phase_taps(c.ph_y, p.s, p.pad).n * phase_taps(c.ph_x, p.s, p.pad).n;
-        const int num_kb = ntaps * kc_per_tap;
-        tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        const TileCoord c = decode_tile<OP, S>(p, t);
+        const int num_kb = taps_n<OP, S>(c.ph_y) * taps_n<OP, S>(c.ph_x) * kc_per_tap;
+        tc::mbar_wait_addr(tc::smem_u32(&tempty[acc]), acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
         uint32_t accum = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          // hot single-thread loop: descriptor = (lo, hi); hi is invariant, lo = (smem address >> 4)
+        for (int kb0 = 0; kb0 < num_kb; kb0 += nsub) {
+          const int nvalid = min(nsub, num_kb - kb0);
           tc::mbar_wait_addr(full_u32 + (uint32_t)stage * 8u, phase);
           tc::fence_after_sync();
-          const uint32_t a_lo = desc_lo0 + (uint32_t)stage * stage_units;
-          const uint32_t b_lo = a_lo + a_units;
-          if (KCc == 64) {
+          uint32_t a_lo = desc_lo0 + (uint32_t)stage * stage_units;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
-          } else if (KCc == 32) {
+          for (int j = 0; j < MAX_SUB; ++j) {
+            if (j < nvalid) {
+              const uint32_t b_lo = a_lo + a_units;
+              if (KCc == 64) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) { tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
-          } else {
-            tc::mma_bf16_lohi(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, accum); accum = 1;
+                for (int k = 0; k < 4; ++k) { tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
+              } else if (KCc == 32) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) { tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
+              } else {
+                tc::mma_bf16_lohi(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, accum); accum = 1;
+              }
+              a_lo += sub_units;
+            }
           }
           tc::mma_commit_addr(empty_u32 + (uint32_t)stage * 8u);   // frees the smem slot when the MMAs retire
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -192,15 +204,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== epilogue ==========================================
     const int q = warp & 3;                              // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                       // row of the tile == TMEM lane
+    const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+    const bool vec_ok = (p.Nch & 7) == 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord c = decode_tile<OP>(p, t);
-      const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+      const TileCoord c = decode_tile<OP, S>(p, t);
       const int n = c.n0 + bn, i = c.i0 + bh, j = c.j0 + bw;
       const bool valid = n < p.Nimg;
       int64_t off;
       if (OP == OP_F) off = (((int64_t)n * p.Hs + i) * p.Ws + j) * p.Nch;
-      else off = (((int64_t)n * p.Hb + (p.s * i + c.ph_y)) * p.Wb + (p.s * j + c.ph_x)) * p.Nch;
+      else off = (((int64_t)n * p.Hb + (S * i + c.ph_y)) * p.Wb + (S * j + c.ph_x)) * p.Nch;
       bf16* orow = p.out + off;
       const int ch0 = c.nt * p.NT;
 
@@ -213,7 +226,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::tmem_ld16(taddr + cb, v);
         const int chb = ch0 + cb;
         if (chb >= p.Nch) continue;                       // channel padding (uniform over the CTA)
-        if (chb + 16 <= p.Nch && (p.Nch & 7) == 0) {
+        if (chb + 16 <= p.Nch && vec_ok) {
           uint32_t pk[8];
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
@@ -258,7 +271,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -295,7 +308,14 @@ bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
   p->phases = (op == OP_T) ? s * s : 1;
   p->total_tiles = p->m_tiles * p->n_tiles * p->phases;
   p->a_bytes = TILE_M * p->KC * 2;
-  p->stage_bytes = p->a_bytes + p->NT * p->KC * 2;
+  p->sub_bytes = p->a_bytes + p->NT * p->KC * 2;
+  // k-blocks per pipeline stage: amortise the ~450-cycle mbarrier round trip over >= ~512 MMA cycles
+  int nsub = 65536 / p->sub_bytes;
+  if (nsub > MAX_SUB) nsub = MAX_SUB;
+  if (nsub < 1) nsub = 1;
+  while (nsub > 1 && SMEM_BUDGET / (nsub * p->sub_bytes) < 3) --nsub;
+  p->nsub = nsub;
+  p->stage_bytes = nsub * p->sub_bytes;
   int st = SMEM_BUDGET / p->stage_bytes;
   p->stages = st > MAX_STAGES ? MAX_STAGES : st;
   if (p->stages < 2) return false;
@@ -319,6 +339,17 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, int cols, int boxCo
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { lg_set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LG_ERR_CUDA; }
   return LG_OK;
+}
+
+template <int OP, int S>
+void launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_conv_kernel<OP, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
+  tc_conv_kernel<OP, S><<<grid, NUM_THREADS, smem_bytes(p), st>>>(tmA, tmB, p);
 }
 
 template <int OP>
@@ -347,14 +378,8 @@ int launch_tc(const void* act_in, const void* wpack, const float* bias, void* ou
     e = encode_w_map(&tmB, wt, Ap, Bp, p.KC, p.NT, sw);
   }
   if (e) return e;
-  const size_t shm = smem_bytes(p);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[OP]) {
-    cudaFuncSetAttribute(tc_conv_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set[OP] = true;
-  }
-  int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
-  tc_conv_kernel<OP><<<grid, NUM_THREADS, shm, st>>>(tmA, tmB, p);
+  if (s == 1) launch_kernel<OP, 1>(tmA, tmB, p, st);
+  else launch_kernel<OP, 2>(tmA, tmB, p, st);
   return LG_OK;
 }
 

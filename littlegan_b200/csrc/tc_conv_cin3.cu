@@ -144,7 +144,7 @@ cin3_fprop_kernel(const C3Params p) {
     }
   } else if (warp == 4) {
     // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(128, p.B, 0, 0);
       const uint32_t sw_addr = tc::smem_u32(sW);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t aphase = 0;
@@ -275,7 +275,7 @@ cin3_wgrad_kernel(const __grid_constant__ CUtensorMap tmSmall, const C3Params p)
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       const int nbox = p.B / p.b_blk;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -289,7 +289,7 @@ cin3_wgrad_kernel(const __grid_constant__ CUtensorMap tmSmall, const C3Params p)
       }
     }
   } else if (warp == 4) {
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(128, p.B, 1, 1);     // both operands MN-major
       const uint32_t layout_b = p.b_blk == 64 ? 2u : 4u;
       const uint32_t sbo_b = 8u * (uint32_t)p.b_blk * 2u, lbo_b = 128u * (uint32_t)p.b_blk * 2u;

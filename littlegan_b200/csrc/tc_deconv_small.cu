@@ -25,7 +25,8 @@
 namespace {
 
 constexpr int NUM_THREADS = 192;
-constexpr int TILE = 16;                 // input tile is TILE x TILE pixels = 256 GEMM rows (2 MMA blocks)
+constexpr int PRODUCER_WARP = 4, MMA_WARP = 5;   // epilogue = warps 0-3; single-thread roles get the high warp ids
+constexpr int TILE = 16;                // input tile is TILE x TILE pixels = 256 GEMM rows (2 MMA blocks)
 constexpr int STAGES = 2;
 constexpr int ZP = 81;                   // fp32 pitch of the Z staging rows (odd -> conflict-free)
 
@@ -73,14 +74,14 @@ tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p
       *reinterpret_cast<bf16*>(sW + off) = __float2bfloat16_rn(v);
     }
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(tfull, 1);
     tc::mbar_init(tempty, 4);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, 256);
   tc::fence_proxy_async();               // generic-proxy smem writes (weights) -> visible to the tensor core
   tc::fence_before_sync();
   __syncthreads();
@@ -90,8 +91,8 @@ tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p
   const int in_t = TILE - 2 * p.halo;    // interior input pixels per tile edge
   const int per_img = p.tilesH * p.tilesW;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp == PRODUCER_WARP) {
+    if (tc::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int n = t / per_img, r = t - n * per_img;
@@ -102,8 +103,8 @@ tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == MMA_WARP) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(128, p.NZ, 0, 0);
       const uint32_t layout_a = (p.B == 64) ? 2u : 4u;              // SWIZZLE_128B / SWIZZLE_64B rows
       const uint32_t row_bytes = (uint32_t)p.B * 2u;
@@ -208,7 +209,7 @@ tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p
       }
       if (p.stats != nullptr) {
         s1 = warp_sum(s1); s2 = warp_sum(s2);
-        if (lane == 0) { atomicAdd(&p.stats[2 * n], (double)s1); atomicAdd(&p.stats[2 * n + 1], (double)s2); }
+        if (tc::elect_one()) { atomicAdd(&p.stats[2 * n], (double)s1); atomicAdd(&p.stats[2 * n + 1], (double)s2); }
       }
       epi_bar_sync();                                               // Zs free for the next tile
     }
@@ -216,7 +217,7 @@ tc_deconv_small_kernel(const __grid_constant__ CUtensorMap tmA, const DsParams p
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 256);
   }

@@ -9,6 +9,19 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a converged warp.  Unlike `lane == 0`, ptxas knows that exactly one thread is
+// active under this predicate, so register operands of UTCHMMA / UTMALDG become plain R2UR moves instead
+// of an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop around every instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -24,6 +24,7 @@
 namespace {
 
 constexpr int NUM_THREADS = 192;
+constexpr int PRODUCER_WARP = 4, MMA_WARP = 5;   // epilogue = warps 0-3; single-thread roles get the high warp ids
 constexpr int MAX_STAGES = 8;
 constexpr int KP = 64;                   // positions per k-block
 constexpr int SMEM_BUDGET = 200 * 1024;
@@ -72,14 +73,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
   const int kb1 = min(p.total_kb, kb0 + p.kb_per_slice);
   const int num_kb = kb1 - kb0;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     tc::tma_prefetch_desc(&tmBig);
     tc::tma_prefetch_desc(&tmSmall);
     for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(tfull, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -90,8 +91,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
   const int a_box_bytes = KP * p.a_blk * 2;
   const int b_box_bytes = KP * p.b_blk * 2;
 
-  if (warp == 0) {
-    if (lane == 0 && num_kb > 0) {
+  if (warp == PRODUCER_WARP) {
+    if (num_kb > 0 && tc::elect_one()) {
       // per-box constants (tap offset, channel) do not depend on the k-block: hoist them
       int box_ch[8], box_dx[8], box_dy[8];
 #pragma unroll
@@ -127,8 +128,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
         if (++pw == p.pbW) { pw = 0; if (++ph == p.pbH) { ph = 0; ++pn; } }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && num_kb > 0) {
+  } else if (warp == MMA_WARP) {
+    if (num_kb > 0 && tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(128, p.NT, 1, 1);        // both operands MN-major
       const uint32_t layout_a = (p.a_blk == 64) ? 2u : (p.a_blk == 32) ? 4u : 6u;
       const uint32_t sbo_a = 8u * (uint32_t)p.a_blk * 2u;            // 8 positions x a_blk channels
@@ -182,7 +183,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, tmem_cols);
   }
