@@ -125,16 +125,27 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const T* __rest
   const int64_t beg = (int64_t)blockIdx.x * per_cta, end = min(M, beg + per_cta);
   const int64_t base = (int64_t)n * M;
   float s1 = 0.f, s2 = 0.f;
-  for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
-    float v[V], g[V];
-    ldv<TZ, V>(z + base + i, v);
-    ldv<T, V>(gp + base + i, g);
+  // xhat = fma(u, k1, k0), y = fma(u, y1, y0): 6 flops per element; two vectors in flight per thread
+  const float k1 = np.inv, k0 = -np.mu * np.inv, y1 = ga * k1, y0 = fmaf(ga, k0, be);
+  const bool pre = alpha_pre != 1.f;
+  const int64_t step = (int64_t)NT * V;
+  for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += 2 * step) {
+    float v[2][V], g[2][V];
+    const bool two = i + step < end;
+    ldv<TZ, V>(z + base + i, v[0]);
+    ldv<T, V>(gp + base + i, g[0]);
+    if (two) { ldv<TZ, V>(z + base + i + step, v[1]); ldv<T, V>(gp + base + i + step, g[1]); }
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float xh = (leaky_f(v[k], alpha_pre) - np.mu) * np.inv;
-      float y = fmaf(ga, xh, be);
-      float dy = g[k] * leaky_d(y, alpha_post);
-      s1 += dy; s2 += dy * xh;
+    for (int h = 0; h < 2; ++h) {
+      if (h == 0 || two) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float u = pre ? leaky_f(v[h][k], alpha_pre) : v[h][k];
+          const float xh = fmaf(u, k1, k0);
+          const float dy = g[h][k] * leaky_d(fmaf(u, y1, y0), alpha_post);
+          s1 += dy; s2 = fmaf(dy, xh, s2);
+        }
+      }
     }
   }
   double a = s1, b = s2;
@@ -168,18 +179,31 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restr
   const float scale = ga * np.inv;
   const int64_t beg = (int64_t)blockIdx.x * per_cta, end = min(M, beg + per_cta);
   const int64_t base = (int64_t)n * M;
-  for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += (int64_t)NT * V) {
-    float v[V], g[V], o[V];
-    ldv<TZ, V>(z + base + i, v);
-    ldv<T, V>(gp + base + i, g);
+  // dz = pre'(z) * (c1*dy - c3 - c2*xhat) with xhat = fma(u,k1,k0), y = fma(u,y1,y0)
+  const float k1 = np.inv, k0 = -np.mu * np.inv, y1 = ga * k1, y0 = fmaf(ga, k0, be);
+  const float c1 = scale, c2 = mdyx * scale, c3 = mdy * scale;
+  const bool pre = alpha_pre != 1.f;
+  const int64_t step = (int64_t)NT * V;
+  for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += 2 * step) {
+    float v[2][V], g[2][V], o[V];
+    const bool two = i + step < end;
+    ldv<TZ, V>(z + base + i, v[0]);
+    ldv<T, V>(gp + base + i, g[0]);
+    if (two) { ldv<TZ, V>(z + base + i + step, v[1]); ldv<T, V>(gp + base + i + step, g[1]); }
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float xh = (leaky_f(v[k], alpha_pre) - np.mu) * np.inv;
-      float y = fmaf(ga, xh, be);
-      float dy = g[k] * leaky_d(y, alpha_post);
-      o[k] = scale * (dy - mdy - xh * mdyx) * leaky_d(v[k], alpha_pre);
+    for (int h = 0; h < 2; ++h) {
+      if (h == 0 || two) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float u = pre ? leaky_f(v[h][k], alpha_pre) : v[h][k];
+          const float xh = fmaf(u, k1, k0);
+          const float dy = g[h][k] * leaky_d(fmaf(u, y1, y0), alpha_post);
+          const float r = fmaf(-xh, c2, fmaf(dy, c1, -c3));
+          o[k] = pre ? r * leaky_d(v[h][k], alpha_pre) : r;
+        }
+        stv<TZ, V>(dz + base + i + h * step, o);
+      }
     }
-    stv<TZ, V>(dz + base + i, o);
   }
 }
 
@@ -213,6 +237,37 @@ __global__ void __launch_bounds__(NT) bias_grad_kernel(const T* __restrict__ g, 
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += NT) atomicAdd(&db[c], shc[c]);
+}
+
+// C == 3 (the RGB bias gradients): a thread walks groups of 3 vectors = 3V elements, so element e of a
+// group always belongs to channel e % 3 - register accumulation, one block reduction, 3 atomics per CTA.
+template <typename T, int V>
+__global__ void __launch_bounds__(NT) bias_grad_c3_kernel(const T* __restrict__ g, float* db, int64_t total) {
+  __shared__ float sh[3][NT / 32];
+  float acc[3] = {0.f, 0.f, 0.f};
+  const int64_t ngroups = total / (3 * V);
+  for (int64_t gi = (int64_t)blockIdx.x * NT + threadIdx.x; gi < ngroups; gi += (int64_t)gridDim.x * NT) {
+    float v[3][V];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ldv<T, V>(g + gi * 3 * V + j * V, v[j]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[(j * V + k) % 3] += v[j][k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t e = ngroups * 3 * V; e < total; ++e) acc[e % 3] += to_f(g[e]);      // tail (< 3V elements)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s = warp_sum(acc[c]);
+    if ((threadIdx.x & 31) == 0) sh[c][threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int w = 0; w < NT / 32; ++w) s += sh[threadIdx.x][w];
+    atomicAdd(&db[threadIdx.x], s);
+  }
 }
 
 template <typename T>
@@ -454,6 +509,16 @@ extern "C" int lg_bias_grad(const void* g, float* db, int64_t rows, int C, int d
   LG_REQUIRE(g && db && rows > 0 && C > 0, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = rows * C;
+  if (C == 3 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    const int V = dtype == LG_BF16 ? 8 : 4;
+    int64_t need = (total / (3 * V) + NT - 1) / NT;
+    int64_t cap = (int64_t)lg_num_sms() * 8;
+    int gsz = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+    if (dtype == LG_BF16) bias_grad_c3_kernel<bf16, 8><<<gsz, NT, 0, st>>>((const bf16*)g, db, total);
+    else bias_grad_c3_kernel<float, 4><<<gsz, NT, 0, st>>>((const float*)g, db, total);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+  }
   if (C > 4096) {   // wide, short matrices (the dense heads): one thread per column, coalesced over columns
     int64_t rows_per = (rows + 7) / 8;
     dim3 grid((C + NT - 1) / NT, (unsigned)((rows + rows_per - 1) / rows_per));
