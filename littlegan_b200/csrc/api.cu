@@ -74,6 +74,8 @@ extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wp
     int e;
     if (W && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, stride))      // RGB layers: GEMM + col2im
       e = lg_tc_deconv_small(small, W, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
+    else if (lg_tc_dgrad4_supported(N, Hb, Wb, A, B, stride))            // <= 128 channels: 4 phases per pass
+      e = lg_tc_dgrad4(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, act, st);
     else
       e = lg_tc_dgrad(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
     if (e) return e;

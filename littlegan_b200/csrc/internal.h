@@ -23,6 +23,9 @@ int lg_tc_wgrad_padded(const void* big, const void* small, float* dW, int N, int
 int lg_tc_deconv_small_supported(int N, int Hb, int Wb, int A, int B, int s);
 int lg_tc_deconv_small(const void* small, const float* W, const float* bias, void* out, double* stats, int N,
                        int Hb, int Wb, int A, int B, int s, int act, cudaStream_t st);
+int lg_tc_dgrad4_supported(int N, int Hb, int Wb, int A, int B, int s);
+int lg_tc_dgrad4(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
+                 int Wb, int A, int B, int act, cudaStream_t st);
 int lg_tc_cin3_supported(int N, int Hb, int Wb, int A, int B, int s);
 int lg_tc_cin3_fprop(const void* img, const float* W, const float* bias, void* out, double* stats, int N, int Hb,
                      int Wb, int B, int s, cudaStream_t st);

@@ -47,6 +47,7 @@ struct TcParams {
   int BW, BH, BN; // tile box in small-map coordinates, BW*BH*BN == 128
   int tilesW, tilesH, tilesN;
   int m_tiles, total_tiles, phases;
+  int per_phase, lg_nt, lg_tw, lg_th;   // division-free tile decode (all tile counts are powers of two)
   int a_bytes, sub_bytes, nsub, stage_bytes, stages;
   int act;
   const float* bias;
@@ -69,19 +70,19 @@ struct TileCoord { int ph_y, ph_x, nt, n0, i0, j0; };
 template <int OP, int S>
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   TileCoord c;
-  const uint32_t per_phase = (uint32_t)(p.m_tiles * p.n_tiles);
-  const uint32_t q = (uint32_t)t / per_phase;
-  uint32_t r = (uint32_t)t - q * per_phase;
   // heavier phases (more taps) first: q = 0 -> (1,1), 1 -> (1,0), 2 -> (0,1), 3 -> (0,0)
+  int q = 0;
+  if (OP == OP_T && S == 2) q = (t >= p.per_phase) + (t >= 2 * p.per_phase) + (t >= 3 * p.per_phase);
+  const int r = t - q * p.per_phase;
   if (OP == OP_T && S == 2) { c.ph_y = (q < 2) ? 1 : 0; c.ph_x = (q & 1) ? 0 : 1; }
   else { c.ph_y = 0; c.ph_x = 0; }
-  const uint32_t mt0 = r / (uint32_t)p.n_tiles;
-  c.nt = (int)(r - mt0 * (uint32_t)p.n_tiles);
-  const uint32_t mt1 = mt0 / (uint32_t)p.tilesW;
-  const uint32_t tw = mt0 - mt1 * (uint32_t)p.tilesW;
-  const uint32_t tn = mt1 / (uint32_t)p.tilesH;
-  const uint32_t th = mt1 - tn * (uint32_t)p.tilesH;
-  c.n0 = (int)tn * p.BN; c.i0 = (int)th * p.BH; c.j0 = (int)tw * p.BW;
+  c.nt = r & ((1 << p.lg_nt) - 1);
+  const int mt0 = r >> p.lg_nt;
+  const int tw = mt0 & ((1 << p.lg_tw) - 1);
+  const int mt1 = mt0 >> p.lg_tw;
+  const int th = mt1 & ((1 << p.lg_th) - 1);
+  const int tn = mt1 >> p.lg_th;
+  c.n0 = tn * p.BN; c.i0 = th * p.BH; c.j0 = tw * p.BW;
   return c;
 }
 
@@ -96,6 +97,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * MAX_STAGES;     // [2]        MMA -> epilogue
   uint64_t* tempty = bars + 2 * MAX_STAGES + 2;// [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  float* sbias = reinterpret_cast<float*>(bars + 32);     // n_tiles * NT floats (<= 512)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (2 * p.NT <= 32) ? 32 : (2 * p.NT <= 64) ? 64 : (2 * p.NT <= 128) ? 128
@@ -109,6 +111,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::fence_barrier_init();
   }
   if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, tmem_cols);
+  for (int i = threadIdx.x; i < p.n_tiles * p.NT; i += NUM_THREADS) sbias[i] = (p.bias && i < p.Nch) ? p.bias[i] : 0.f;
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -230,8 +233,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t pk[8];
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
-            float a = v[e] + (p.bias ? __ldg(p.bias + chb + e) : 0.f);
-            float b = v[e + 1] + (p.bias ? __ldg(p.bias + chb + e + 1) : 0.f);
+            float a = v[e] + sbias[chb + e];
+            float b = v[e + 1] + sbias[chb + e + 1];
             s1 += a + b; s2 += a * a + b * b;
             if (p.act == LG_ACT_TANH) { a = tanhf(a); b = tanhf(b); }
             __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -244,7 +247,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {
           for (int e = 0; e < 16 && chb + e < p.Nch; ++e) {
-            float a = v[e] + (p.bias ? __ldg(p.bias + chb + e) : 0.f);
+            float a = v[e] + sbias[chb + e];
             s1 += a; s2 += a * a;
             if (p.act == LG_ACT_TANH) a = tanhf(a);
             if (valid) orow[chb + e] = __float2bfloat16_rn(a);
@@ -307,6 +310,10 @@ bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
   p->m_tiles = p->tilesW * p->tilesH * p->tilesN;
   p->phases = (op == OP_T) ? s * s : 1;
   p->total_tiles = p->m_tiles * p->n_tiles * p->phases;
+  p->per_phase = p->m_tiles * p->n_tiles;
+  auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  if (!is_pow2(p->n_tiles) || !is_pow2(p->tilesW) || !is_pow2(p->tilesH)) return false;
+  p->lg_nt = lg2(p->n_tiles); p->lg_tw = lg2(p->tilesW); p->lg_th = lg2(p->tilesH);
   p->a_bytes = TILE_M * p->KC * 2;
   p->sub_bytes = p->a_bytes + p->NT * p->KC * 2;
   // k-blocks per pipeline stage: amortise the ~450-cycle mbarrier round trip over >= ~512 MMA cycles
@@ -323,7 +330,7 @@ bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
   return true;
 }
 
-size_t smem_bytes(const TcParams& p) { return (size_t)p.stages * p.stage_bytes + 1024 + 256; }
+size_t smem_bytes(const TcParams& p) { return (size_t)p.stages * p.stage_bytes + 1024 + 256 + 2048; }
 
 // packed weights [25][rows][cols] bf16, cols contiguous (the contraction channels)
 int encode_w_map(CUtensorMap* m, const void* base, int rows, int cols, int boxCols, int boxRows,
@@ -391,6 +398,7 @@ int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N) {
   if (op != LG_OP_DGRAD && lg_tc_cin3_supported(N, Hb, Wb, A, B, s)) return 1;
   if (op == LG_OP_WGRAD) return lg_tc_wgrad_supported(N, Hb, Wb, A, B, s);
   if (op == LG_OP_DGRAD && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, s)) return 1;
+  if (op == LG_OP_DGRAD && lg_tc_dgrad4_supported(N, Hb, Wb, A, B, s)) return 1;
   TcParams p;
   return plan(op == LG_OP_FPROP ? OP_F : OP_T, N, Hb, Wb, A, B, s, &p) ? 1 : 0;
 }
