@@ -248,7 +248,9 @@ bool plan_d4(int Nimg, int Hb, int Wb, int A, int B, D4Params* p) {
   if (!tc_host::is_pow2(Hs) || !tc_host::is_pow2(Ws) || Ws > 128 || Hs * Ws < 32) return false;
   if (B % 32 != 0) return false;
   const int Npad = (A + 15) / 16 * 16;
-  if (Npad > 128 || A < 16) return false;              // tiny A: tc_deconv_small; large A: tc_conv
+  // tiny A: tc_deconv_small.  A > 64 would need all 512 TMEM columns for one accumulator set (no double
+  // buffering, 2 pipeline stages) and measured slower than the per-phase kernel (87 vs 66 us, dec2 shape).
+  if (Npad > 64 || A < 16) return false;
   p->Nimg = Nimg; p->Hs = Hs; p->Ws = Ws; p->Hb = Hb; p->Wb = Wb;
   p->Kch = B; p->Nch = A; p->KC = (B % 64 == 0) ? 64 : 32; p->NT = Npad;
   p->BW = Ws < 128 ? Ws : 128;
