@@ -75,6 +75,7 @@ class EagerTrainer:
         self._seen = set()
         self._pool = None
         self._noise_gen = None
+        self._comm_stream = None
         if getattr(args, "result_dir", None) and getattr(args, "init_dirs", False):
             self._init_dir()
 
@@ -228,6 +229,7 @@ class EagerTrainer:
         # ---- disc_tape.gradient(disc_loss, D weights): both halves, no input gradient (:145)
         g4 = E.disc_heads_backward(rt, D, outs[3], dl_pr_d, dl_c_d, wgrad=True)
         E.encoder_backward(rt, D.encoder, ectx, g4, wgrad=True, input_grad=False)
+        self._reduce_async("Discriminator", batch_no)        # overlaps with the G backward + adjuster step
 
         # ---- gen_tape.gradient(gen_loss, G weights): dgrad-only through D(fake), then G (:149)
         ectx_f = [(x[B:], z[B:], st[B:], None) for (x, z, st, _) in ectx]
@@ -238,6 +240,7 @@ class EagerTrainer:
         g = E.final_conv_backward(rt, G.conv, g_x4, dpre, wgrad=True)
         g = E.decoder_backward(rt, G.decoder, g_dctx, g, wgrad=True)
         E.head_backward(rt, G.dense, G.norm, g_hctx, g)
+        self._reduce_async("Generator", batch_no)             # overlaps with the adjuster step
 
         # ---- adjuster sub-step on 2B samples (eager_trainer.py:152-164)
         if adj_on:
@@ -259,17 +262,32 @@ class EagerTrainer:
             S["adj"] = adj
 
         # ---- apply: A (if trained), D, G (eager_trainer.py:164-168); D grads value-clipped (:146-148)
-        dist = _dist()
+        if adj_on:
+            self._reduce_async("Adjuster", batch_no)
+        if _dist() is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)   # join the gradient all-reduces
         for name in (["Adjuster"] if adj_on else []) + ["Discriminator", "Generator"]:
             lo, hi = self._range(name, batch_no)
             grad = self.Gd[lo:hi]
-            if dist is not None:
-                dist.all_reduce(grad, op=dist.ReduceOp.AVG)
             lr, b1, b2 = self._hyper[name]
             K.adam_advance(self.adam_state[name], lr, b1, b2)
             clip = a.clip_range if (name == "Discriminator" and a.use_clip) else 0.0
             K.adam_apply(self.P[lo:hi], grad, self.M[lo:hi], self.V[lo:hi], self.adam_state[name], b1, b2, 1e-8,
                          clip)
+
+    def _reduce_async(self, name, batch_no):
+        """Data parallel: average this optimiser's (active range of the) flat gradient arena over the
+        ranks on a side stream, so that NCCL runs under the remaining backward work; the ranges of
+        the three optimisers are disjoint and the main stream joins before the first Adam."""
+        dist = _dist()
+        if dist is None:
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        lo, hi = self._range(name, batch_no)
+        self._comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_reduce(self.Gd[lo:hi], op=dist.ReduceOp.AVG)
 
     def _variant(self, batch_no):
         a = self.args
