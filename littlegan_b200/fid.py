@@ -32,8 +32,32 @@ class FeatureStatistics:
         self.S1 = torch.zeros(d, dtype=torch.float64, device=dev)
         self.S2 = torch.zeros(d, d, dtype=torch.float64, device=dev)
         self.shift = None if shift is None else shift.to(dev, torch.float64).contiguous()
+        self._stage = None            # batches are pooled to >= 4096 rows per kernel launch
+        self._fill = 0
 
     def update(self, X):
+        """Queue a feature batch [b, d]; the outer-product kernel runs once per ~4096 rows (a launch per
+        100-row Inception batch, `evaluate.py:54`, would leave the GPU mostly idle)."""
+        if X.dim() != 2 or X.shape[1] != self.d:
+            raise ValueError("expected features of shape [b, %d]" % self.d)
+        X = X.to(torch.float32)
+        if X.shape[0] >= 4096 and self._fill == 0:
+            return self._accumulate(X.contiguous())
+        if self._stage is None:
+            self._stage = torch.empty(8192, self.d, dtype=torch.float32, device=self.S1.device)
+        if self._fill + X.shape[0] > self._stage.shape[0]:
+            self.flush()
+        self._stage[self._fill:self._fill + X.shape[0]].copy_(X)
+        self._fill += X.shape[0]
+        if self._fill >= 4096:
+            self.flush()
+
+    def flush(self):
+        if self._fill:
+            self._accumulate(self._stage[:self._fill])
+            self._fill = 0
+
+    def _accumulate(self, X):
         if X.dim() != 2 or X.shape[1] != self.d:
             raise ValueError("expected features of shape [b, %d]" % self.d)
         X = X.to(torch.float32).contiguous()
@@ -48,6 +72,7 @@ class FeatureStatistics:
 
     def finalize(self):
         import torch.distributed as dist
+        self.flush()
         n = self.n
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             cnt = torch.tensor([n], dtype=torch.float64, device=self.S1.device)

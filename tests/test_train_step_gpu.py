@@ -193,3 +193,41 @@ def test_trajectory_full_size_golden():
         med = float(np.median(devs))
         print("trajectory %s: median deviation %.4f (oracle fp32-vs-fp64 floor %.4f)" % (dtype, med, floor))
         assert med < factor * max(floor, 0.005), (dtype, med, floor)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_predict_matches_oracle(dtype):
+    """predict (eager_trainer.py:265-298): 1 G + 2 D + 2 A forwards and the four MSE scalars."""
+    oargs = small_args()
+    pargs, gen, disc, adj, trainer, W = _setup(oargs, dtype)
+    i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=7)
+    ot = O.OracleTrainer(oargs, W, dtype=torch.float64)
+    ref_img, ref_save, ref_ar, ref_af = ot.predict(noise, c1, i1)
+    img, save, ar, af = trainer.predict(noise, c1, i1)
+    t = tol(torch.float32 if dtype == "fp32" else torch.bfloat16) * 3
+    assert rel_err(img, ref_img) < t and rel_err(ar, ref_ar) < t and rel_err(af, ref_af) < t
+    for key in ("real_pr_mse", "real_c_mse", "fake_pr_mse", "fake_c_mse"):
+        assert abs(save[key] - ref_save[key]) < max(t * abs(ref_save[key]), 1e-6), key
+    # the x100-rounded integer lists of the reference's JSON dump
+    want = torch.round(ref_save["real_c"] * 100).to(torch.int64)
+    got = torch.tensor(save["real_c"])
+    assert int((got - want).abs().max()) <= (0 if dtype == "fp32" else 2)
+    assert save["real_cond"] == torch.round(c1 * 100).to(torch.int64).tolist()
+
+
+def test_public_loss_functions():
+    """discriminator_loss / generator_loss / adjuster_loss keep the reference's signatures."""
+    from littlegan_b200.eager_trainer import EagerTrainer
+    oargs = small_args()
+    pargs, gen, disc, adj, trainer, W = _setup(oargs, "fp32")
+    g = torch.Generator().manual_seed(0)
+    c_true = O.soft((torch.rand(4, oargs.cond_dim, generator=g) < 0.5).float() * 2 - 1)
+    c_pred, pr_r, pr_f = (torch.rand(4, oargs.cond_dim, generator=g), torch.rand(4, 1, generator=g),
+                          torch.rand(4, 1, generator=g))
+    img_a, img_b = torch.rand(4, 32, 32, 3, generator=g) * 2 - 1, torch.rand(4, 32, 32, 3, generator=g) * 2 - 1
+    d = EagerTrainer.discriminator_loss(c_true.cuda(), c_pred.cuda(), pr_r.cuda(), pr_f.cuda())
+    assert abs(float(d) - float(O.discriminator_loss(c_true, c_pred, pr_r, pr_f))) < 1e-5
+    gl = trainer.generator_loss(c_true.cuda(), c_pred.cuda(), pr_f.cuda(), img_a.cuda(), img_b.cuda())
+    assert abs(float(gl) - float(O.generator_loss(oargs, c_true, c_pred, pr_f, img_a, img_b))) < 1e-5
+    al = trainer.adjuster_loss(c_true.cuda(), c_pred.cuda(), pr_f.cuda(), img_a.cuda(), img_b.cuda())
+    assert abs(float(al) - float(gl)) < 1e-7
