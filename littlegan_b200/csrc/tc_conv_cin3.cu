@@ -38,18 +38,34 @@ struct C3Params {
 };
 
 // ---- im2col builder: 128 threads, thread m owns tile position m -------------------------------------
+// Image halo rows s*i0 - pad ... (+rows_in), interior pixels only (margins stay zero), 16-byte vectors,
+// at most 3 per thread.  Split into global->register and register->shared halves so that the loads of
+// the NEXT tile are in flight while the patches of the current one are built.
+constexpr int ROW_VECS = 3;
 template <int S>
-__device__ __forceinline__ void stage_image_rows(const C3Params& p, uint8_t* simg, int n, int i0, int bt) {
-  // rows s*i0 - pad ... (+rows_in), interior pixels only (margins stay zero); 16-byte vectors
+__device__ __forceinline__ void load_image_rows(const C3Params& p, int n, int i0, int bt, uint4 (&v)[ROW_VECS]) {
   const int vec_per_row = p.Wb * 6 / 16;
-  const int y_first = S * i0 - p.pad;
-  for (int e = bt; e < p.rows_in * vec_per_row; e += 128) {
-    const int r = e / vec_per_row, v = e - r * vec_per_row;
-    const int y = y_first + r;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < p.Hb)
-      val = __ldg(reinterpret_cast<const uint4*>(p.img + ((int64_t)n * p.Hb + y) * p.Wb * 3) + v);
-    *reinterpret_cast<uint4*>(simg + r * p.pitch + MARGIN * 6 + v * 16) = val;
+  const int y_first = S * i0 - p.pad, total = p.rows_in * vec_per_row;
+#pragma unroll
+  for (int q = 0; q < ROW_VECS; ++q) {
+    const int e = bt + q * 128;
+    v[q] = make_uint4(0, 0, 0, 0);
+    if (e < total) {
+      const int r = e / vec_per_row, c = e - r * vec_per_row;
+      const int y = y_first + r;
+      if (y >= 0 && y < p.Hb) v[q] = __ldg(reinterpret_cast<const uint4*>(p.img + ((int64_t)n * p.Hb + y) * p.Wb * 3) + c);
+    }
+  }
+}
+__device__ __forceinline__ void store_image_rows(const C3Params& p, uint8_t* simg, int bt, const uint4 (&v)[ROW_VECS]) {
+  const int vec_per_row = p.Wb * 6 / 16, total = p.rows_in * vec_per_row;
+#pragma unroll
+  for (int q = 0; q < ROW_VECS; ++q) {
+    const int e = bt + q * 128;
+    if (e < total) {
+      const int r = e / vec_per_row, c = e - r * vec_per_row;
+      *reinterpret_cast<uint4*>(simg + r * p.pitch + MARGIN * 6 + c * 16) = v[q];
+    }
   }
 }
 
@@ -130,12 +146,15 @@ cin3_fprop_kernel(const C3Params p) {
     // ------------------------------------------------ builders
     const int bt = threadIdx.x;
     int stage = 0; uint32_t phase = 0;
+    uint4 pre[ROW_VECS];
+    if ((int)blockIdx.x < p.total_tiles)
+      load_image_rows<S>(p, blockIdx.x / p.tiles_per_img, (blockIdx.x % p.tiles_per_img) * p.BH, bt, pre);
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int n = t / p.tiles_per_img, r = t - n * p.tiles_per_img;
-      const int i0 = r * p.BH;
       bar_sync_builders();                                       // previous tile's patch reads of simg are done
-      stage_image_rows<S>(p, simg, n, i0, bt);
+      store_image_rows(p, simg, bt, pre);
       bar_sync_builders();
+      const int tn = t + gridDim.x;                              // next tile's rows: in flight during the build
+      if (tn < p.total_tiles) load_image_rows<S>(p, tn / p.tiles_per_img, (tn % p.tiles_per_img) * p.BH, bt, pre);
       tc::mbar_wait(&empty[stage], phase ^ 1);
       build_patches<S>(p, simg, sA + stage * (KPAD / 8) * PLANE, bt);
       tc::fence_proxy_async();                                   // generic writes -> async (tensor core) proxy
@@ -263,11 +282,15 @@ cin3_wgrad_kernel(const __grid_constant__ CUtensorMap tmSmall, const C3Params p)
   if (warp < 4) {
     const int bt = threadIdx.x;
     int stage = 0; uint32_t phase = 0;
+    uint4 pre[ROW_VECS];
+    if ((int)blockIdx.x < p.total_tiles)
+      load_image_rows<S>(p, blockIdx.x / p.tiles_per_img, (blockIdx.x % p.tiles_per_img) * p.BH, bt, pre);
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int n = t / p.tiles_per_img, r = t - n * p.tiles_per_img;
       bar_sync_builders();
-      stage_image_rows<S>(p, simg, n, r * p.BH, bt);
+      store_image_rows(p, simg, bt, pre);
       bar_sync_builders();
+      const int tn = t + gridDim.x;
+      if (tn < p.total_tiles) load_image_rows<S>(p, tn / p.tiles_per_img, (tn % p.tiles_per_img) * p.BH, bt, pre);
       tc::mbar_wait(&empty[stage], phase ^ 1);
       build_patches<S>(p, simg, sStage + (size_t)stage * p.stage_bytes, bt);
       tc::fence_proxy_async();
@@ -347,7 +370,7 @@ bool plan_c3(int Nimg, int Hb, int Wb, int B, int s, C3Params* p) {
   p->BW = Ws; p->BH = 128 / Ws;
   p->rows_in = s * (p->BH - 1) + 5;
   p->pitch = (Wb + 2 * MARGIN) * 6;
-  if (p->pitch % 16 != 0) return false;
+  if (p->pitch % 16 != 0 || p->rows_in * (Wb * 6 / 16) > ROW_VECS * 128) return false;
   p->tiles_per_img = Hs * Ws / 128;
   p->total_tiles = Nimg * p->tiles_per_img;
   p->b_blk = (B % 64 == 0) ? 64 : 32;
