@@ -57,18 +57,38 @@ int lg_conv2d_tc_supported(int op, int N, int Hb, int Wb, int A, int B, int stri
 /* ---- convolution family (replaces TF Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter,
  *      model.py:15,39,86 and their autodiff from eager_trainer.py:145,149,163) -------------- */
 
+/* Optional fused epilogue of a BACKWARD conv launch (tensor-core path): the launch produces g = dL/da for
+ * the layer below, a = LeakyReLU(InstanceNorm(z)) (instance.py:105-128).  With this descriptor the kernel
+ * reads the matching element of z, stores dy = g * LeakyReLU'(gamma*xhat + beta) instead of g, and adds
+ * (sum dy, sum dy*xhat) per sample into `red` - pass 1 of the norm backward without a separate kernel.
+ * Follow with lg_instnorm_act_bwd_apply(..., dy_ready = 1).  lg_conv2d_norm_bwd_supported says whether a
+ * geometry accepts it. */
+typedef struct lg_norm_bwd {
+  const void* z;        /* pre-norm output of the layer below (LG_BF16), shape of this launch's output */
+  const double* stats;  /* [N][2] sum / sum of squares of z per sample */
+  const float* gamma;   /* [1] */
+  const float* beta;    /* [1] */
+  double* red;          /* [N][2], ACCUMULATED (caller zeroes) */
+  float eps;            /* added to the standard deviation */
+  float alpha;          /* LeakyReLU slope */
+} lg_norm_bwd_t;
+int lg_conv2d_norm_bwd_supported(int op, int N, int Hb, int Wb, int A, int B, int stride);
+
 /* fprop.  bias: [B] or NULL.  stats: double[N][2] (sum, sum of squares of the written values,
  * per sample, ACCUMULATED - caller zeroes) or NULL.  use_tc: 1 = tcgen05 path (requires LG_BF16,
- * wpack from lg_pack_conv_weights), 0 = fp32-accumulate SIMT path reading W fp32. */
+ * wpack from lg_pack_conv_weights), 0 = fp32-accumulate SIMT path reading W fp32.  norm_bwd: NULL or
+ * the fused epilogue above (excludes stats). */
 int lg_conv2d_fprop(const void* big, const float* W, const void* wpack, const float* bias,
                     void* small_out, double* stats, int N, int Hb, int Wb, int A, int B,
-                    int stride, int dtype, int use_tc, void* stream);
+                    int stride, int dtype, int use_tc, const lg_norm_bwd_t* norm_bwd, void* stream);
 
 /* dgrad (== Conv2DTranspose forward).  bias: [A] or NULL; act: LG_ACT_NONE / LG_ACT_TANH applied
- * after the bias; stats as above, taken on the pre-activation values. */
+ * after the bias; stats as above, taken on the pre-activation values; norm_bwd as above (excludes
+ * stats and act). */
 int lg_conv2d_dgrad(const void* small, const float* W, const void* wpack, const float* bias,
                     void* big_out, double* stats, int N, int Hb, int Wb, int A, int B,
-                    int stride, int act, int dtype, int use_tc, void* stream);
+                    int stride, int act, int dtype, int use_tc, const lg_norm_bwd_t* norm_bwd,
+                    void* stream);
 
 /* wgrad.  dW [5,5,A,B] fp32 is ACCUMULATED into (caller zeroes). */
 int lg_conv2d_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb,
@@ -124,11 +144,16 @@ int lg_instnorm_act_bwd_reduce(const void* g, const void* z, const double* stats
                                int dtype, void* stream);
 /* Backward, pass 2: dz = pre'(z) * (gamma/s) * (dy - mean(dy) - xhat*(s/sigma)*mean(dy*xhat));
  * dgamma += sum_n red[n][1], dbeta += sum_n red[n][0] (added once, by block 0), either may be
- * NULL. */
+ * NULL.  dy_ready: `g` already holds dy (written by a conv launch with a lg_norm_bwd_t epilogue).
+ * dbias (or NULL): float[C] += per-channel sums of dz (the bias gradient of the conv that produced z,
+ * channels innermost); fused only when lg_instnorm_bias_grad_fusable(M, C, z_dtype), else
+ * LG_ERR_UNSUPPORTED (use lg_bias_grad). */
+int lg_instnorm_bias_grad_fusable(int64_t M, int C, int z_dtype);
 int lg_instnorm_act_bwd_apply(const void* g, const void* z, const double* stats, const double* red,
                               const float* gamma, const float* beta, void* dz, float* dgamma,
-                              float* dbeta, int N, int64_t M, float eps, float alpha_pre,
-                              float alpha_post, int z_dtype, int dtype, void* stream);
+                              float* dbeta, float* dbias, int C, int dy_ready, int N, int64_t M,
+                              float eps, float alpha_pre, float alpha_post, int z_dtype, int dtype,
+                              void* stream);
 
 /* ---- Dense (tf.layers.Dense, model.py:62,63,83,120): C[M,N] (+)= op(A)[M,K] * op(B)[K,N] ----
  * A is activation-typed (a_dtype), B fp32, C c_dtype.  transA: A stored [K,M]; transB: B stored
@@ -136,6 +161,21 @@ int lg_instnorm_act_bwd_apply(const void* g, const void* z, const double* stats,
  * is added in the epilogue when accumulate == 0. */
 int lg_gemm(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K,
             int transA, int transB, int accumulate, int a_dtype, int c_dtype, void* stream);
+/* Two Dense layers sharing one input - the discriminator heads (model.py:62-63,70-72):
+ *   out_h[N,U_h] = act(feat[N,F] @ W_h[F,U_h] + b_h),  h = 0,1;  feat is `dtype`, everything else fp32.
+ * One pass over feat.  Needs U0 + U1 <= 48 and F % 64 == 0 (else LG_ERR_UNSUPPORTED: use lg_gemm).
+ * `workspace`: lg_dense_heads_workspace_bytes(N) bytes, zero-filled ONCE by the caller; every call leaves it
+ * zeroed again (calls sharing a workspace must be stream-ordered). */
+int64_t lg_dense_heads_workspace_bytes(int N);
+int lg_dense_heads_fwd(const void* feat, const float* W0, const float* b0, int U0, const float* W1,
+                       const float* b1, int U1, float* out0, float* out1, int N, int F, int act, int dtype,
+                       void* workspace, void* stream);
+/* Backward of the pair given dl_h = d loss / d(pre-activation) [N,U_h] fp32 (one of them may be NULL = 0):
+ *   dfeat[N,F] (`dtype`, written; may be NULL) = dl0 @ W0^T + dl1 @ W1^T
+ *   dW_h[F,U_h] += feat^T @ dl_h ; db_h[U_h] += column sums of dl_h      (each may be NULL = skip) */
+int lg_dense_heads_bwd(const void* feat, const float* dl0, const float* dl1, const float* W0, int U0,
+                       const float* W1, int U1, void* dfeat, float* dW0, float* dW1, float* db0, float* db1,
+                       int N, int F, int dtype, void* stream);
 /* x[r,c] = act(x[r,c] + bias[c]) in place, fp32. */
 int lg_bias_act(float* x, const float* bias, int rows, int cols, int act, void* stream);
 
@@ -168,11 +208,12 @@ int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype,
 
 /* ---- FID statistics (fid.py:169-188: np.mean / np.cov in fp64) ----------------------------- */
 
-/* X [n,d] fp32 features.  S1 double[d] += sum_r (x_r - shift); S2 double[d,d] (upper AND lower
- * triangles) += sum_r (x_r - shift)(x_r - shift)^T.  shift double[d] (may be NULL = 0). */
+/* X [n,d] fp32 features.  S1 double[d] += sum_r (x_r - shift); S2 double[d,d], UPPER triangle
+ * only (j >= i) += sum_r (x_r - shift)(x_r - shift)^T.  shift double[d] (may be NULL = 0). */
 int lg_fid_accumulate(const float* X, const double* shift, double* S1, double* S2, int64_t n,
                       int d, void* stream);
-/* mu = shift + S1/n ; sigma = (S2 - S1 S1^T / n) / (n-1)  (unbiased, np.cov default). */
+/* mu = shift + S1/n ; sigma = (S2 - S1 S1^T / n) / (n-1)  (unbiased, np.cov default); reads the upper
+ * triangle of S2 and writes the full, exactly symmetric sigma. */
 int lg_fid_finalize(const double* S1, const double* S2, const double* shift, double* mu,
                     double* sigma, int64_t n, int d, void* stream);
 

@@ -22,8 +22,9 @@ SIGNATURES = {
     "lg_last_error": (C.c_char_p, []),
     "lg_tensor_core_path_available": (_i, []),
     "lg_conv2d_tc_supported": (_i, [_i] * 7),
-    "lg_conv2d_fprop": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "lg_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lg_conv2d_norm_bwd_supported": (_i, [_i] * 7),
+    "lg_conv2d_fprop": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lg_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lg_conv2d_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_conv2d_wgrad_padded": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_pad_channels": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
@@ -34,8 +35,13 @@ SIGNATURES = {
     "lg_rowstats": (_i, [_vp, _vp, _i, _i64, _f, _i, _vp]),
     "lg_instnorm_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _i, _i, _vp]),
     "lg_instnorm_act_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _i, _i, _vp]),
-    "lg_instnorm_act_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _i, _i, _vp]),
+    "lg_instnorm_bias_grad_fusable": (_i, [_i64, _i, _i]),
+    "lg_instnorm_act_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _f, _f, _f, _i,
+                                       _i, _vp]),
     "lg_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lg_dense_heads_workspace_bytes": (_i64, [_i]),
+    "lg_dense_heads_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "lg_dense_heads_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lg_bias_act": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "lg_bce_sigmoid": (_i, [_vp, _vp, _f, _i, _i, _f, _vp, _vp, _vp]),
     "lg_l1_tanh_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _vp, _i, _vp]),
@@ -45,6 +51,14 @@ SIGNATURES = {
     "lg_fid_accumulate": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lg_fid_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
 }
+
+
+
+class NormBwd(C.Structure):
+    """lg_norm_bwd_t: fused InstanceNorm-backward epilogue descriptor of a backward conv launch."""
+    _fields_ = [("z", _vp), ("stats", _vp), ("gamma", _vp), ("beta", _vp), ("red", _vp), ("eps", _f),
+                ("alpha", _f)]
+
 
 _lib = None
 

@@ -40,9 +40,17 @@ static int check_geom(const char* fn, int N, int Hb, int Wb, int A, int B, int s
   return LG_OK;
 }
 
+// Would lg_conv2d_fprop / lg_conv2d_dgrad (tensor-core path) accept a fused norm-backward epilogue here?
+extern "C" int lg_conv2d_norm_bwd_supported(int op, int N, int Hb, int Wb, int A, int B, int stride) {
+  if (!lg_tc_supported(op, Hb, Wb, A, B, stride, N)) return 0;
+  if (op == LG_OP_FPROP) return B % 16 == 0 ? 1 : 0;                      // output channels = B
+  if (op == LG_OP_DGRAD) return (A % 16 == 0 && !lg_tc_deconv_small_supported(N, Hb, Wb, A, B, stride)) ? 1 : 0;
+  return 0;
+}
+
 extern "C" int lg_conv2d_fprop(const void* big, const float* W, const void* wpack, const float* bias,
                                void* small_out, double* stats, int N, int Hb, int Wb, int A, int B, int stride,
-                               int dtype, int use_tc, void* stream) {
+                               int dtype, int use_tc, const lg_norm_bwd_t* norm_bwd, void* stream) {
   if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, dtype)) return e;
   LG_REQUIRE(big && small_out, "NULL tensor");
   cudaStream_t st = (cudaStream_t)stream;
@@ -50,12 +58,13 @@ extern "C" int lg_conv2d_fprop(const void* big, const float* W, const void* wpac
     LG_REQUIRE(dtype == LG_BF16 && wpack, "tcgen05 path needs LG_BF16 activations and packed weights");
     int e;
     if (W && lg_tc_cin3_supported(N, Hb, Wb, A, B, stride))              // RGB input: in-smem im2col
-      e = lg_tc_cin3_fprop(big, W, bias, small_out, stats, N, Hb, Wb, B, stride, st);
+      e = lg_tc_cin3_fprop(big, W, bias, small_out, stats, N, Hb, Wb, B, stride, norm_bwd, st);
     else
-      e = lg_tc_fprop(big, wpack, bias, small_out, stats, N, Hb, Wb, A, B, stride, st);
+      e = lg_tc_fprop(big, wpack, bias, small_out, stats, N, Hb, Wb, A, B, stride, norm_bwd, st);
     if (e) return e;
   } else {
     LG_REQUIRE(W, "NULL weights");
+    LG_REQUIRE(!norm_bwd, "the fused norm-backward epilogue exists on the tensor-core path only");
     lg_simt_fprop(big, W, bias, small_out, stats, N, Hb, Wb, A, B, stride, dtype, st);
   }
   LG_LAUNCH_CHECK();
@@ -64,7 +73,7 @@ extern "C" int lg_conv2d_fprop(const void* big, const float* W, const void* wpac
 
 extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wpack, const float* bias,
                                void* big_out, double* stats, int N, int Hb, int Wb, int A, int B, int stride,
-                               int act, int dtype, int use_tc, void* stream) {
+                               int act, int dtype, int use_tc, const lg_norm_bwd_t* norm_bwd, void* stream) {
   if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, dtype)) return e;
   LG_REQUIRE(small && big_out, "NULL tensor");
   LG_REQUIRE(act == LG_ACT_NONE || act == LG_ACT_TANH, "unsupported activation");
@@ -72,15 +81,17 @@ extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wp
   if (use_tc) {
     LG_REQUIRE(dtype == LG_BF16 && wpack, "tcgen05 path needs LG_BF16 activations and packed weights");
     int e;
-    if (W && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, stride))      // RGB layers: GEMM + col2im
+    if (W && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, stride)) {    // RGB layers: GEMM + col2im
+      LG_REQUIRE(!norm_bwd, "no fused norm-backward epilogue on the RGB transposed-conv kernel");
       e = lg_tc_deconv_small(small, W, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
-    else if (lg_tc_dgrad4_supported(N, Hb, Wb, A, B, stride))            // <= 128 channels: 4 phases per pass
-      e = lg_tc_dgrad4(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, act, st);
+    } else if (lg_tc_dgrad4_supported(N, Hb, Wb, A, B, stride))          // <= 128 channels: 4 phases per pass
+      e = lg_tc_dgrad4(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, act, norm_bwd, st);
     else
-      e = lg_tc_dgrad(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
+      e = lg_tc_dgrad(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, norm_bwd, st);
     if (e) return e;
   } else {
     LG_REQUIRE(W, "NULL weights");
+    LG_REQUIRE(!norm_bwd, "the fused norm-backward epilogue exists on the tensor-core path only");
     lg_simt_dgrad(small, W, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, dtype, st);
   }
   LG_LAUNCH_CHECK();
@@ -122,14 +133,14 @@ extern "C" int lg_conv2d_transpose_fprop(const void* x_small, const float* W, co
                                          int A_out, int B_in, int stride, int act, int dtype, int use_tc,
                                          void* stream) {
   return lg_conv2d_dgrad(x_small, W, wpack, bias, y_big, stats, N, Hb, Wb, A_out, B_in, stride, act, dtype, use_tc,
-                         stream);
+                         nullptr, stream);
 }
 
 extern "C" int lg_conv2d_transpose_dgrad(const void* dy_big, const float* W, const void* wpack, void* dx_small,
                                          int N, int Hb, int Wb, int A_out, int B_in, int stride, int dtype,
                                          int use_tc, void* stream) {
   return lg_conv2d_fprop(dy_big, W, wpack, nullptr, dx_small, nullptr, N, Hb, Wb, A_out, B_in, stride, dtype, use_tc,
-                         stream);
+                         nullptr, stream);
 }
 
 extern "C" int lg_gemm(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K,

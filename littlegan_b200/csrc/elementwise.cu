@@ -156,12 +156,17 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_reduce_kernel(const T* __rest
 // ------------------------------------------------------------------------------------------------
 // backward pass 2
 // ------------------------------------------------------------------------------------------------
-template <typename TZ, typename T, int V>
+// DB: also accumulate the per-channel sums of dz (the producing conv's bias gradient; channels innermost,
+// C divides NT*V so a thread sees the same V channels in every iteration).  dy_ready: `gp` already holds
+// dy = g * leaky_post'(y) (written by a conv epilogue, norm_bwd.cuh).
+template <typename TZ, typename T, int V, bool DB>
 __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restrict__ gp, const TZ* __restrict__ z,
                                                                 const double* __restrict__ stats, const double* __restrict__ red,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                TZ* __restrict__ dz, float* dgamma, float* dbeta, int N, int64_t M,
-                                                                int64_t per_cta, float eps, float alpha_pre, float alpha_post) {
+                                                                TZ* __restrict__ dz, float* dgamma, float* dbeta, float* dbias,
+                                                                int C, int dy_ready, int N, int64_t M, int64_t per_cta,
+                                                                float eps, float alpha_pre, float alpha_post) {
+  __shared__ float shc[DB ? NT * V : 1];
   const int n = blockIdx.y;
   if (blockIdx.x == 0 && n == 0 && threadIdx.x < 32) {
     double a = 0.0, b = 0.0;
@@ -171,6 +176,10 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restr
       if (dbeta) atomicAdd(dbeta, (float)a);
       if (dgamma) atomicAdd(dgamma, (float)b);
     }
+  }
+  if constexpr (DB) {
+    for (int c = threadIdx.x; c < C; c += NT) shc[c] = 0.f;
+    __syncthreads();
   }
   const NormParams np = norm_params(stats, n, M, eps);
   const float ga = gamma[0], be = beta[0];
@@ -183,7 +192,11 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restr
   const float k1 = np.inv, k0 = -np.mu * np.inv, y1 = ga * k1, y0 = fmaf(ga, k0, be);
   const float c1 = scale, c2 = mdyx * scale, c3 = mdy * scale;
   const bool pre = alpha_pre != 1.f;
+  const float a_post = dy_ready ? 1.f : alpha_post;            // leaky_d(., 1) == 1: dy is taken as is
   const int64_t step = (int64_t)NT * V;
+  float bsum[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) bsum[k] = 0.f;
   for (int64_t i = beg + (int64_t)threadIdx.x * V; i < end; i += 2 * step) {
     float v[2][V], g[2][V], o[V];
     const bool two = i + step < end;
@@ -197,13 +210,23 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restr
         for (int k = 0; k < V; ++k) {
           const float u = pre ? leaky_f(v[h][k], alpha_pre) : v[h][k];
           const float xh = fmaf(u, k1, k0);
-          const float dy = g[h][k] * leaky_d(fmaf(u, y1, y0), alpha_post);
+          const float dy = g[h][k] * leaky_d(fmaf(u, y1, y0), a_post);
           const float r = fmaf(-xh, c2, fmaf(dy, c1, -c3));
           o[k] = pre ? r * leaky_d(v[h][k], alpha_pre) : r;
+          if constexpr (DB) bsum[k] += o[k];
         }
         stv<TZ, V>(dz + base + i + h * step, o);
       }
     }
+  }
+  if constexpr (DB) {
+    const int c0 = (int)((beg + (int64_t)threadIdx.x * V) % C);
+    if (beg + (int64_t)threadIdx.x * V < end) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) atomicAdd(&shc[c0 + k], bsum[k]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += NT) atomicAdd(&dbias[c], shc[c]);
   }
 }
 
@@ -385,17 +408,30 @@ __global__ void pad_channels_kernel(const T* __restrict__ src, T* __restrict__ d
   }
 }
 
-// W[25][A][B] fp32 -> Wt[25][Ap][Bp] bf16 (b contiguous), Wf[25][Bp][Ap] bf16 (a contiguous)
-__global__ void pack_weights_kernel(const float* __restrict__ W, bf16* __restrict__ Wt, bf16* __restrict__ Wf, int A,
-                                    int B, int Ap, int Bp) {
-  const int64_t total = (int64_t)25 * Ap * Bp;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int b = (int)(i % Bp); int64_t t = i / Bp; int a = (int)(t % Ap); int tap = (int)(t / Ap);
-    float v = (a < A && b < B) ? W[((int64_t)tap * A + a) * B + b] : 0.f;
-    bf16 h = __float2bfloat16_rn(v);
-    Wt[i] = h;
-    Wf[((int64_t)tap * Bp + b) * Ap + a] = h;
+// W[25][A][B] fp32 -> Wt[25][Ap][Bp] bf16 (b contiguous), Wf[25][Bp][Ap] bf16 (a contiguous).
+// One 64x64 (a, b) tile of one tap per CTA: W is read and Wt written along b, the tile is transposed in
+// shared memory and Wf written along a, so all three streams are coalesced (the weights are re-packed
+// after every optimiser step, ~20 MB of traffic per step).
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ W, bf16* __restrict__ Wt,
+                                                           bf16* __restrict__ Wf, int A, int B, int Ap, int Bp) {
+  __shared__ float tile[64][65];
+  const int tap = blockIdx.z, a0 = blockIdx.y * 64, b0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* Wp = W + (int64_t)tap * A * B;
+  for (int r = ty; r < 64; r += 8) {
+    const int a = a0 + r, b = b0 + 2 * tx;
+    const float v0 = (a < A && b < B) ? Wp[(int64_t)a * B + b] : 0.f;
+    const float v1 = (a < A && b + 1 < B) ? Wp[(int64_t)a * B + b + 1] : 0.f;
+    tile[r][2 * tx] = v0; tile[r][2 * tx + 1] = v1;
+    if (a < Ap && b < Bp)
+      *reinterpret_cast<__nv_bfloat162*>(Wt + ((int64_t)tap * Ap + a) * Bp + b) = __floats2bfloat162_rn(v0, v1);
+  }
+  __syncthreads();
+  for (int r = ty; r < 64; r += 8) {
+    const int b = b0 + r, a = a0 + 2 * tx;
+    if (a < Ap && b < Bp)
+      *reinterpret_cast<__nv_bfloat162*>(Wf + ((int64_t)tap * Bp + b) * Ap + a) =
+          __floats2bfloat162_rn(tile[2 * tx][r], tile[2 * tx + 1][r]);
   }
 }
 
@@ -485,19 +521,38 @@ extern "C" int lg_instnorm_act_bwd_reduce(const void* g, const void* z, const do
   return LG_OK;
 }
 
+static int apply_vec(int64_t M, int z_dtype) {
+  if (z_dtype == LG_BF16) return M % 8 == 0 ? 8 : 1;
+  return M % 4 == 0 ? 4 : 1;
+}
+
+extern "C" int lg_instnorm_bias_grad_fusable(int64_t M, int C, int z_dtype) {
+  const int V = apply_vec(M, z_dtype);
+  return (V > 1 && C > 0 && C <= NT * V && (NT * V) % C == 0 && C % V == 0 && M % C == 0) ? 1 : 0;
+}
+
 extern "C" int lg_instnorm_act_bwd_apply(const void* g, const void* z, const double* stats, const double* red,
                                          const float* gamma, const float* beta, void* dz, float* dgamma,
-                                         float* dbeta, int N, int64_t M, float eps, float alpha_pre,
-                                         float alpha_post, int z_dtype, int dtype, void* stream) {
+                                         float* dbeta, float* dbias, int C, int dy_ready, int N, int64_t M, float eps,
+                                         float alpha_pre, float alpha_post, int z_dtype, int dtype, void* stream) {
   LG_REQUIRE(g && z && stats && red && gamma && beta && dz && N > 0 && M > 0, "bad arguments");
   LG_REQUIRE(!(z_dtype == LG_BF16 && dtype == LG_F32), "bf16 z with fp32 g is not supported");
+  if (dbias != nullptr && !lg_instnorm_bias_grad_fusable(M, C, z_dtype)) {
+    lg_set_error("lg_instnorm_act_bwd_apply: bias gradient not fusable for M=%lld C=%d", (long long)M, C);
+    return LG_ERR_UNSUPPORTED;
+  }
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(TZ, T, V)                                                                                          \
-  {                                                                                                             \
-    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                          \
-    instnorm_bwd_apply_kernel<TZ, T, V><<<dim3(ch, N), NT, 0, st>>>((const T*)g, (const TZ*)z, stats, red,      \
-                                                                    gamma, beta, (TZ*)dz, dgamma, dbeta, N, M,  \
-                                                                    per, eps, alpha_pre, alpha_post);           \
+#define CALL(TZ, T, V)                                                                                           \
+  {                                                                                                              \
+    int64_t per; int ch; chunking(M, V, N, &per, &ch);                                                           \
+    if (dbias != nullptr)                                                                                        \
+      instnorm_bwd_apply_kernel<TZ, T, V, (V > 1)><<<dim3(ch, N), NT, 0, st>>>(                                  \
+          (const T*)g, (const TZ*)z, stats, red, gamma, beta, (TZ*)dz, dgamma, dbeta, dbias, C, dy_ready, N, M,  \
+          per, eps, alpha_pre, alpha_post);                                                                      \
+    else                                                                                                         \
+      instnorm_bwd_apply_kernel<TZ, T, V, false><<<dim3(ch, N), NT, 0, st>>>(                                    \
+          (const T*)g, (const TZ*)z, stats, red, gamma, beta, (TZ*)dz, dgamma, dbeta, nullptr, C, dy_ready, N,   \
+          M, per, eps, alpha_pre, alpha_post);                                                                   \
   }
   DISPATCH_ZT(z_dtype, dtype, M, CALL);
 #undef CALL
@@ -635,9 +690,8 @@ extern "C" int64_t lg_pack_conv_weights(const float* W, void* wpack, int A, int 
   if (W == nullptr) { lg_set_error("lg_pack_conv_weights: W is NULL"); return LG_ERR_INVALID; }
   bf16* wt = (bf16*)wpack;
   bf16* wf = wt + half;
-  int gsz = (int)((half + 255) / 256);
-  if (gsz > lg_num_sms() * 16) gsz = lg_num_sms() * 16;
-  pack_weights_kernel<<<gsz, 256, 0, (cudaStream_t)stream>>>(W, wt, wf, A, B, Ap, Bp);
+  pack_weights_kernel<<<dim3((Bp + 63) / 64, (Ap + 63) / 64, 25), 256, 0, (cudaStream_t)stream>>>(W, wt, wf, A, B, Ap,
+                                                                                                  Bp);
   LG_LAUNCH_CHECK();
   return 2 * half * (int64_t)sizeof(bf16);
 }

@@ -1,6 +1,7 @@
 // FID feature statistics (fid.py:169-188): streaming fp64 accumulation of sum(x) and sum(x x^T)
 // over fp32 feature rows, so that mean / unbiased covariance match np.mean / np.cov (fp64).
-// S2 is a rank-n symmetric update: only tiles with bx <= by are computed and mirrored.
+// S2 is a rank-n symmetric update: only its upper triangle (tiles with bx <= by) is accumulated;
+// lg_fid_finalize mirrors it.
 #include "common.cuh"
 
 namespace {
@@ -65,8 +66,7 @@ __global__ void __launch_bounds__(FNT) fid_accumulate_kernel(const float* __rest
     for (int q = 0; q < 4; ++q) {
       int j = j0 + tx * 4 + q;
       if (j >= d) continue;
-      atomicAdd(&S2[(int64_t)i * d + j], acc[p][q]);
-      if (!diag) atomicAdd(&S2[(int64_t)j * d + i], acc[p][q]);
+      if (j >= i) atomicAdd(&S2[(int64_t)i * d + j], acc[p][q]);       // upper triangle only (finalize mirrors)
     }
   }
   if (diag && S1 != nullptr) {
@@ -84,7 +84,10 @@ __global__ void fid_finalize_kernel(const double* __restrict__ S1, const double*
   const double inv_n = 1.0 / (double)n, inv_nm1 = 1.0 / (double)(n - 1);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int i = (int)(e / d), j = (int)(e % d);
-    sigma[e] = (S2[e] - S1[i] * S1[j] * inv_n) * inv_nm1;
+    // only the upper triangle of S2 is accumulated (atomics arrive in any order, so a mirrored copy would
+    // differ in the last bit): reading (min, max) makes sigma exactly symmetric, like np.cov's
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    sigma[e] = (S2[(int64_t)lo * d + hi] - S1[lo] * S1[hi] * inv_n) * inv_nm1;
     if (e < d) mu[e] = (shift ? shift[e] : 0.0) + S1[e] * inv_n;
   }
 }

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "littlegan_b200.h"
+
 int lg_simt_fprop(const void* big, const float* W, const float* bias, void* out, double* stats, int N,
                   int Hb, int Wb, int A, int B, int s, int dtype, cudaStream_t st);
 int lg_simt_dgrad(const void* small, const float* W, const float* bias, void* out, double* stats, int N,
@@ -12,10 +14,11 @@ int lg_simt_dense(const void* A, const float* Bm, const float* bias, void* C, in
                   int tB, int acc, int a_dtype, int c_dtype, cudaStream_t st);
 
 // tcgen05 / TMA path (tc_conv.cu).  Return LG_ERR_UNSUPPORTED when the geometry is not covered.
+// `nb` (may be NULL): fuse the InstanceNorm-backward reduction of the layer below into the epilogue.
 int lg_tc_fprop(const void* big, const void* wpack, const float* bias, void* out, double* stats, int N,
-                int Hb, int Wb, int A, int B, int s, cudaStream_t st);
+                int Hb, int Wb, int A, int B, int s, const lg_norm_bwd_t* nb, cudaStream_t st);
 int lg_tc_dgrad(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N,
-                int Hb, int Wb, int A, int B, int s, int act, cudaStream_t st);
+                int Hb, int Wb, int A, int B, int s, int act, const lg_norm_bwd_t* nb, cudaStream_t st);
 int lg_tc_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A, int B,
                 int s, cudaStream_t st);
 int lg_tc_wgrad_padded(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A, int A_real,
@@ -25,10 +28,10 @@ int lg_tc_deconv_small(const void* small, const float* W, const float* bias, voi
                        int Hb, int Wb, int A, int B, int s, int act, cudaStream_t st);
 int lg_tc_dgrad4_supported(int N, int Hb, int Wb, int A, int B, int s);
 int lg_tc_dgrad4(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
-                 int Wb, int A, int B, int act, cudaStream_t st);
+                 int Wb, int A, int B, int act, const lg_norm_bwd_t* nb, cudaStream_t st);
 int lg_tc_cin3_supported(int N, int Hb, int Wb, int A, int B, int s);
 int lg_tc_cin3_fprop(const void* img, const float* W, const float* bias, void* out, double* stats, int N, int Hb,
-                     int Wb, int B, int s, cudaStream_t st);
+                     int Wb, int B, int s, const lg_norm_bwd_t* nb, cudaStream_t st);
 int lg_tc_cin3_wgrad(const void* img, const void* small, float* dW, int N, int Hb, int Wb, int B, int s,
                      cudaStream_t st);
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N);

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "norm_bwd.cuh"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
 
@@ -86,9 +87,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   return c;
 }
 
-template <int OP, int S>
+// NB: fuse the InstanceNorm-backward reduction of the layer below into the epilogue (norm_bwd.cuh).
+template <int OP, int S, bool NB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+               const NormBwdDev nb) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -220,10 +223,46 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bf16* orow = p.out + off;
       const int ch0 = c.nt * p.NT;
 
+      NormBwdCoef coef = {0.f, 0.f, 0.f, 0.f};
+      NormBwdZ zc;
+      const bf16* zrow = nullptr;
+      if constexpr (NB) {
+        // z row of this output position: first 64 channels into registers, the rest of the row towards L2,
+        // all in flight while the MMAs of this tile still run
+        zrow = nb.z + off + ch0;
+        if (valid) coef = nb_coef(nb, n);
+        nb_load(zc, zrow, p.NT >> 4, valid);
+        if (p.NT > 64) nb_prefetch_l2(zrow + 64, (p.NT - 64) * 2, valid);
+      }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
       float s1 = 0.f, s2 = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+      if constexpr (NB) {
+        // s1 / s2 carry (sum dy, sum dy*xhat); the host guarantees Nch % 16 == 0, no activation
+        for (int sc = 0; sc < p.NT; sc += 64) {
+          NormBwdZ zn;
+          if (sc + 64 < p.NT) nb_load(zn, zrow + sc + 64, (p.NT - sc - 64) >> 4, valid);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int cb = sc + 16 * c;
+            if (cb < p.NT) {
+              float v[16];
+              tc::tmem_ld16(taddr + cb, v);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] += sbias[ch0 + cb + e];
+              uint32_t pk[8];
+              nb_chunk(v, zc.v[2 * c], zc.v[2 * c + 1], coef, nb.alpha, s1, s2, pk);
+              if (valid) {
+                uint4* dst = reinterpret_cast<uint4*>(orow + ch0 + cb);
+                dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
+            }
+          }
+          if (sc + 64 < p.NT) zc = zn;
+        }
+      } else {
       for (int cb = 0; cb < p.NT; cb += 16) {
         float v[16];
         tc::tmem_ld16(taddr + cb, v);
@@ -254,19 +293,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-      if (p.stats != nullptr) {
+      double* sums = NB ? nb.red : p.stats;
+      if (sums != nullptr) {
         // rows of one warp belong to one sample whenever BW*BH >= 32 (checked on the host)
         if (!valid) { s1 = 0.f; s2 = 0.f; }
         s1 = warp_sum(s1); s2 = warp_sum(s2);
         if (lane == 0 && valid) {
-          atomicAdd(&p.stats[2 * n], (double)s1);
-          atomicAdd(&p.stats[2 * n + 1], (double)s2);
+          atomicAdd(&sums[2 * n], (double)s1);
+          atomicAdd(&sums[2 * n + 1], (double)s2);
         }
       }
     }
@@ -348,24 +389,33 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, int cols, int boxCo
   return LG_OK;
 }
 
-template <int OP, int S>
-void launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+template <int OP, int S, bool NB>
+void launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, const NormBwdDev& nb,
+                   cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_conv_kernel<OP, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_conv_kernel<OP, S, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
-  tc_conv_kernel<OP, S><<<grid, NUM_THREADS, smem_bytes(p), st>>>(tmA, tmB, p);
+  tc_conv_kernel<OP, S, NB><<<grid, NUM_THREADS, smem_bytes(p), st>>>(tmA, tmB, p, nb);
 }
 
 template <int OP>
 int launch_tc(const void* act_in, const void* wpack, const float* bias, void* out, double* stats, int Nimg, int Hb,
-              int Wb, int A, int B, int s, int act, cudaStream_t st) {
+              int Wb, int A, int B, int s, int act, const lg_norm_bwd_t* nbh, cudaStream_t st) {
   TcParams p;
   if (!plan(OP, Nimg, Hb, Wb, A, B, s, &p)) {
     lg_set_error("tcgen05 path: unsupported geometry");
     return LG_ERR_UNSUPPORTED;
+  }
+  NormBwdDev nb = {};
+  if (nbh != nullptr) {
+    if (p.Nch % 16 != 0 || act != LG_ACT_NONE || stats != nullptr) {
+      lg_set_error("tcgen05 path: fused norm-backward needs Nch %% 16 == 0, no activation, no forward statistics");
+      return LG_ERR_UNSUPPORTED;
+    }
+    nb = lg_make_norm_bwd(nbh, OP == OP_F ? (int64_t)p.Hs * p.Ws * p.Nch : (int64_t)p.Hb * p.Wb * p.Nch);
   }
   p.act = act; p.bias = bias; p.out = (bf16*)out; p.stats = stats;
   const int Ap = (A + 15) / 16 * 16, Bp = (B + 15) / 16 * 16;
@@ -385,8 +435,13 @@ int launch_tc(const void* act_in, const void* wpack, const float* bias, void* ou
     e = encode_w_map(&tmB, wt, Ap, Bp, p.KC, p.NT, sw);
   }
   if (e) return e;
-  if (s == 1) launch_kernel<OP, 1>(tmA, tmB, p, st);
-  else launch_kernel<OP, 2>(tmA, tmB, p, st);
+  if (nbh != nullptr) {
+    if (s == 1) launch_kernel<OP, 1, true>(tmA, tmB, p, nb, st);
+    else launch_kernel<OP, 2, true>(tmA, tmB, p, nb, st);
+  } else {
+    if (s == 1) launch_kernel<OP, 1, false>(tmA, tmB, p, nb, st);
+    else launch_kernel<OP, 2, false>(tmA, tmB, p, nb, st);
+  }
   return LG_OK;
 }
 
@@ -404,11 +459,11 @@ int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N) {
 }
 
 int lg_tc_fprop(const void* big, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
-                int Wb, int A, int B, int s, cudaStream_t st) {
-  return launch_tc<OP_F>(big, wpack, bias, out, stats, N, Hb, Wb, A, B, s, LG_ACT_NONE, st);
+                int Wb, int A, int B, int s, const lg_norm_bwd_t* nb, cudaStream_t st) {
+  return launch_tc<OP_F>(big, wpack, bias, out, stats, N, Hb, Wb, A, B, s, LG_ACT_NONE, nb, st);
 }
 
 int lg_tc_dgrad(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
-                int Wb, int A, int B, int s, int act, cudaStream_t st) {
-  return launch_tc<OP_T>(small, wpack, bias, out, stats, N, Hb, Wb, A, B, s, act, st);
+                int Wb, int A, int B, int s, int act, const lg_norm_bwd_t* nb, cudaStream_t st) {
+  return launch_tc<OP_T>(small, wpack, bias, out, stats, N, Hb, Wb, A, B, s, act, nb, st);
 }

@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "norm_bwd.cuh"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
 
@@ -99,9 +100,9 @@ __device__ __forceinline__ void bar_sync_builders() { asm volatile("bar.sync 1, 
 constexpr int F_THREADS = 288;
 constexpr int F_STAGES = 2;
 
-template <int S>
+template <int S, bool NB>
 __global__ void __launch_bounds__(F_THREADS)
-cin3_fprop_kernel(const C3Params p) {
+cin3_fprop_kernel(const C3Params p, const NormBwdDev nb) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                           // F_STAGES x 10 planes
@@ -115,6 +116,7 @@ cin3_fprop_kernel(const C3Params p) {
   uint64_t* tfull = bars + 4;            // [2] MMA -> epilogue
   uint64_t* tempty = bars + 6;           // [2] epilogue -> MMA        (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sbias = reinterpret_cast<float*>(bars + 10);           // B floats (<= 128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = 2 * p.B <= 32 ? 32 : 2 * p.B <= 64 ? 64 : 2 * p.B <= 128 ? 128 : 256;
@@ -128,6 +130,7 @@ cin3_fprop_kernel(const C3Params p) {
   }
   for (int e = threadIdx.x * 16; e < img_bytes; e += F_THREADS * 16)
     *reinterpret_cast<uint4*>(simg + e) = make_uint4(0, 0, 0, 0);     // margins (and everything else) start at zero
+  for (int e = threadIdx.x; e < p.B; e += F_THREADS) sbias[e] = p.bias ? p.bias[e] : 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&full[i], 128); tc::mbar_init(&empty[i], 1);
@@ -193,18 +196,49 @@ cin3_fprop_kernel(const C3Params p) {
       const int n = t / p.tiles_per_img, r = t - n * p.tiles_per_img;
       const int64_t pos = (int64_t)n * p.Hs * p.Ws + (int64_t)r * 128 + row;
       bf16* orow = p.out + pos * p.B;
+      NormBwdCoef coef = {0.f, 0.f, 0.f, 0.f};
+      NormBwdZ zc;
+      const bf16* zrow = nullptr;
+      if constexpr (NB) {                                        // fused InstanceNorm-backward reduction (norm_bwd.cuh)
+        zrow = nb.z + pos * p.B;
+        coef = nb_coef(nb, n);
+        nb_load(zc, zrow, p.B >> 4, true);
+        if (p.B > 64) nb_prefetch_l2(zrow + 64, (p.B - 64) * 2, true);
+      }
       tc::mbar_wait(&tfull[acc], aphase);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.B);
       float s1 = 0.f, s2 = 0.f;
+      if constexpr (NB) {
+        for (int sc = 0; sc < p.B; sc += 64) {
+          NormBwdZ zn;
+          if (sc + 64 < p.B) nb_load(zn, zrow + sc + 64, (p.B - sc - 64) >> 4, true);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int cb = sc + 16 * c;
+            if (cb < p.B) {
+              float v[16];
+              tc::tmem_ld16(taddr + cb, v);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] += sbias[cb + e];
+              uint32_t pk[8];
+              nb_chunk(v, zc.v[2 * c], zc.v[2 * c + 1], coef, nb.alpha, s1, s2, pk);
+              uint4* dst = reinterpret_cast<uint4*>(orow + cb);
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+          if (sc + 64 < p.B) zc = zn;
+        }
+      } else {
       for (int cb = 0; cb < p.B; cb += 16) {
         float v[16];
         tc::tmem_ld16(taddr + cb, v);
         uint32_t pk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-          float a = v[e] + (p.bias ? __ldg(p.bias + cb + e) : 0.f);
-          float b = v[e + 1] + (p.bias ? __ldg(p.bias + cb + e + 1) : 0.f);
+          float a = v[e] + sbias[cb + e];
+          float b = v[e + 1] + sbias[cb + e + 1];
           s1 += a + b; s2 += a * a + b * b;
           __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
           pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
@@ -213,13 +247,15 @@ cin3_fprop_kernel(const C3Params p) {
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
+      }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; aphase ^= 1; }
-      if (p.stats != nullptr) {
+      double* sums = NB ? nb.red : p.stats;
+      if (sums != nullptr) {
         s1 = warp_sum(s1); s2 = warp_sum(s2);
-        if (lane == 0) { atomicAdd(&p.stats[2 * n], (double)s1); atomicAdd(&p.stats[2 * n + 1], (double)s2); }
+        if (lane == 0) { atomicAdd(&sums[2 * n], (double)s1); atomicAdd(&sums[2 * n + 1], (double)s2); }
       }
     }
   }
@@ -387,22 +423,34 @@ int lg_tc_cin3_supported(int Nimg, int Hb, int Wb, int A, int B, int s) {
 }
 
 int lg_tc_cin3_fprop(const void* img, const float* W, const float* bias, void* out, double* stats, int Nimg, int Hb,
-                     int Wb, int B, int s, cudaStream_t st) {
+                     int Wb, int B, int s, const lg_norm_bwd_t* nbh, cudaStream_t st) {
   C3Params p;
   if (!plan_c3(Nimg, Hb, Wb, B, s, &p) || !W) { lg_set_error("cin3 fprop: unsupported geometry"); return LG_ERR_UNSUPPORTED; }
+  NormBwdDev nb = {};
+  if (nbh != nullptr) {
+    if (stats != nullptr) { lg_set_error("cin3 fprop: fused norm-backward excludes forward statistics"); return LG_ERR_UNSUPPORTED; }
+    nb = lg_make_norm_bwd(nbh, (int64_t)p.Hs * p.Ws * B);
+  }
   p.img = (const bf16*)img; p.W = W; p.bias = bias; p.out = (bf16*)out; p.stats = stats; p.dW = nullptr;
   const size_t shm = (size_t)F_STAGES * (KPAD / 8) * PLANE + ((B * KPAD * 2 + 1023) & ~1023) +
-                     (size_t)p.rows_in * p.pitch + 2048;
+                     (size_t)p.rows_in * p.pitch + 2048 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(cin3_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(cin3_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(cin3_fprop_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(cin3_fprop_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(cin3_fprop_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(cin3_fprop_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
   int grid = 3 * lg_num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  if (s == 1) cin3_fprop_kernel<1><<<grid, F_THREADS, shm, st>>>(p);
-  else cin3_fprop_kernel<2><<<grid, F_THREADS, shm, st>>>(p);
+  if (nbh != nullptr) {
+    if (s == 1) cin3_fprop_kernel<1, true><<<grid, F_THREADS, shm, st>>>(p, nb);
+    else cin3_fprop_kernel<2, true><<<grid, F_THREADS, shm, st>>>(p, nb);
+  } else {
+    if (s == 1) cin3_fprop_kernel<1, false><<<grid, F_THREADS, shm, st>>>(p, nb);
+    else cin3_fprop_kernel<2, false><<<grid, F_THREADS, shm, st>>>(p, nb);
+  }
   return LG_OK;
 }
 

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "norm_bwd.cuh"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
 
@@ -44,8 +45,10 @@ __device__ __forceinline__ int shift_d(int u) { return 1 - u; }
 __device__ __forceinline__ int shift_ntaps(int u) { return u == 0 ? 1 : 2; }
 __device__ __forceinline__ int shift_tap(int u, int i) { return u == 0 ? 0 : 2 * u - 1 + i; }
 
+template <bool NB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const D4Params p) {
+tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const D4Params p,
+                 const NormBwdDev nb) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -182,10 +185,48 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool valid = n < p.Nimg;
       bf16* obase = p.out + (((int64_t)n * p.Hb + 2 * i) * p.Wb + 2 * j) * p.Nch;
 
+      NormBwdCoef coef = {0.f, 0.f, 0.f, 0.f};
+      NormBwdZ zc;
+      const bf16* zbase = nullptr;
+      if constexpr (NB) {
+        // fused InstanceNorm-backward reduction (norm_bwd.cuh): z rows of the four output phases, one phase ahead
+        zbase = nb.z + (obase - p.out);
+        if (valid) coef = nb_coef(nb, n);
+        nb_load(zc, zbase, p.NT >> 4, valid);
+      }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();
       float s1 = 0.f, s2 = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * set_cols);
+      if constexpr (NB) {
+        for (int ph = 0; ph < 4; ++ph) {
+          const int64_t poff = ((int64_t)(ph >> 1) * p.Wb + (ph & 1)) * p.Nch;
+          bf16* orow = obase + poff;
+          NormBwdZ zn;
+          if (ph < 3) {
+            const int pn = ph + 1;
+            nb_load(zn, zbase + ((int64_t)(pn >> 1) * p.Wb + (pn & 1)) * p.Nch, p.NT >> 4, valid);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int cb = 16 * c;
+            if (cb < p.NT) {
+              float v[16];
+              tc::tmem_ld16(taddr + ph * p.NT + cb, v);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] += sbias[cb + e];
+              uint32_t pk[8];
+              nb_chunk(v, zc.v[2 * c], zc.v[2 * c + 1], coef, nb.alpha, s1, s2, pk);
+              if (valid) {
+                uint4* dst = reinterpret_cast<uint4*>(orow + cb);
+                dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
+            }
+          }
+          if (ph < 3) zc = zn;
+        }
+      } else {
       for (int ph = 0; ph < 4; ++ph) {
         bf16* orow = obase + ((int64_t)(ph >> 1) * p.Wb + (ph & 1)) * p.Nch;
         for (int cb = 0; cb < p.NT; cb += 16) {
@@ -218,18 +259,20 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
       if (nacc == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
       else acc_phase ^= 1;
 
-      if (p.stats != nullptr) {
+      double* sums = NB ? nb.red : p.stats;
+      if (sums != nullptr) {
         if (!valid) { s1 = 0.f; s2 = 0.f; }
         s1 = warp_sum(s1); s2 = warp_sum(s2);
         if (lane == 0 && valid) {
-          atomicAdd(&p.stats[2 * n], (double)s1);
-          atomicAdd(&p.stats[2 * n + 1], (double)s2);
+          atomicAdd(&sums[2 * n], (double)s1);
+          atomicAdd(&sums[2 * n + 1], (double)s2);
         }
       }
     }
@@ -294,9 +337,17 @@ int lg_tc_dgrad4_supported(int Nimg, int Hb, int Wb, int A, int B, int s) {
 }
 
 int lg_tc_dgrad4(const void* small, const void* wpack, const float* bias, void* out, double* stats, int Nimg, int Hb,
-                 int Wb, int A, int B, int act, cudaStream_t st) {
+                 int Wb, int A, int B, int act, const lg_norm_bwd_t* nbh, cudaStream_t st) {
   D4Params p;
   if (!plan_d4(Nimg, Hb, Wb, A, B, &p)) { lg_set_error("tcgen05 dgrad4: unsupported geometry"); return LG_ERR_UNSUPPORTED; }
+  NormBwdDev nb = {};
+  if (nbh != nullptr) {
+    if (A % 16 != 0 || act != LG_ACT_NONE || stats != nullptr) {
+      lg_set_error("tcgen05 dgrad4: fused norm-backward needs A %% 16 == 0, no activation, no forward statistics");
+      return LG_ERR_UNSUPPORTED;
+    }
+    nb = lg_make_norm_bwd(nbh, (int64_t)Hb * Wb * A);
+  }
   p.act = act; p.bias = bias; p.out = (bf16*)out; p.stats = stats;
   const int Ap = (A + 15) / 16 * 16, Bp = (B + 15) / 16 * 16;
   const CUtensorMapSwizzle sw = p.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -307,11 +358,13 @@ int lg_tc_dgrad4(const void* small, const void* wpack, const float* bias, void* 
   if (e) return e;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_dgrad4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_dgrad4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_dgrad4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const size_t shm = (size_t)p.stages * p.stage_bytes + 1024 + 256 + 2048;
   const int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
-  tc_dgrad4_kernel<<<grid, NUM_THREADS, shm, st>>>(tmA, tmB, p);
+  if (nbh != nullptr) tc_dgrad4_kernel<true><<<grid, NUM_THREADS, shm, st>>>(tmA, tmB, p, nb);
+  else tc_dgrad4_kernel<false><<<grid, NUM_THREADS, shm, st>>>(tmA, tmB, p, nb);
   return LG_OK;
 }

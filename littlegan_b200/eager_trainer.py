@@ -237,8 +237,7 @@ class EagerTrainer:
         g_img = E.encoder_backward(rt, D.encoder, ectx_f, g4, wgrad=False, input_grad=True)
         dpre = torch.empty_like(fake)
         K.l1_tanh_bwd(fake, S["img2"], g_img, dpre, a.l1_lambda, l_gen)
-        g = E.final_conv_backward(rt, G.conv, g_x4, dpre, wgrad=True)
-        g = E.decoder_backward(rt, G.decoder, g_dctx, g, wgrad=True)
+        g = E.generator_tail_backward(rt, G.decoder, G.conv, g_dctx, g_x4, dpre, wgrad=True)
         E.head_backward(rt, G.dense, G.norm, g_hctx, g)
         self._reduce_async("Generator", batch_no)             # overlaps with the adjuster step
 
@@ -256,8 +255,7 @@ class EagerTrainer:
             g_img = E.encoder_backward(rt, D.encoder, ectx2, g4, wgrad=False, input_grad=True)
             dpre = torch.empty_like(adj)
             K.l1_tanh_bwd(adj, S["aimg_t"], g_img, dpre, a.l1_lambda, l_adj)
-            g = E.final_conv_backward(rt, A.conv, a_x4, dpre, wgrad=False)
-            g = E.decoder_backward(rt, A.decoder, a_dctx, g, wgrad=False)
+            g = E.generator_tail_backward(rt, A.decoder, A.conv, a_dctx, a_x4, dpre, wgrad=False)
             E.head_backward(rt, A.dense, A.norm, a_hctx, g)
             S["adj"] = adj
 

@@ -25,6 +25,7 @@ class Runtime:
         self.device = torch.device("cuda")
         self.want_tc = mode == "bf16" and getattr(args, "tensor_cores", True)
         self._tc_cache = {}
+        self._heads_ws = None
 
     def use_tc(self, op, N, Hb, Wb, A, B, s):
         if not self.want_tc:
@@ -35,6 +36,25 @@ class Runtime:
             r = K.tc_available() and K.tc_supported(op, N, Hb, Wb, A, B, s)
             self._tc_cache[key] = r
         return r
+
+    def fuse_norm_bwd(self, op, N, Hb, Wb, A, B, s):
+        """May the backward conv launch (op, geometry) carry the fused InstanceNorm-backward epilogue?"""
+        if not self.use_tc(op, N, Hb, Wb, A, B, s):
+            return False
+        key = ("nb", op, N, Hb, Wb, A, B, s)
+        r = self._tc_cache.get(key)
+        if r is None:
+            r = self._tc_cache[key] = K.norm_bwd_supported(op, N, Hb, Wb, A, B, s)
+        return r
+
+    def heads_workspace(self, N):
+        """Scratch of the fused discriminator-heads forward (self-cleaning, allocated once per size)."""
+        if self._heads_ws is None:
+            self._heads_ws = {}                 # never freed: captured CUDA graphs hold the pointers
+        ws = self._heads_ws.get(N)
+        if ws is None:
+            ws = self._heads_ws[N] = K.dense_heads_workspace(N, self.device)
+        return ws
 
     def empty(self, *shape, dtype=None):
         return torch.empty(*shape, dtype=dtype or self.act_dtype, device=self.device)
@@ -99,30 +119,50 @@ def encoder_forward(rt, enc, x):
     return outs, ctx
 
 
+def _norm_act_bwd(rt, g, z, stats, norm, red, conv, wgrad, dy_ready):
+    """IN + LeakyReLU backward of one conv layer -> dz; with `wgrad` also d(gamma), d(beta), d(bias)."""
+    dz = torch.empty_like(z)
+    fuse_db = wgrad and K.bias_grad_fusable(z)
+    K.instnorm_act_bwd(g.view_as(z), z, stats, norm.gamma, norm.beta, red, dz,
+                       _grad(norm.gamma) if wgrad else None, _grad(norm.beta) if wgrad else None,
+                       norm.epsilon, 1.0, rt.alpha, dy_ready=dy_ready,
+                       dbias=_grad(conv.bias) if fuse_db else None)
+    if wgrad and not fuse_db:
+        K.bias_grad(dz, _grad(conv.bias))
+    return dz
+
+
 def encoder_backward(rt, enc, ctx, g, wgrad, input_grad):
     """g: gradient w.r.t. the last encoder output.  wgrad: accumulate kernel/bias/gamma/beta
-    gradients.  Returns the gradient w.r.t. the encoder input if `input_grad`."""
+    gradients.  Returns the gradient w.r.t. the encoder input if `input_grad`.
+    The dgrad launch of layer i produces the gradient w.r.t. layer i-1's activation: where the
+    tensor-core kernel supports it, that launch also does pass 1 of layer i-1's norm backward
+    (csrc/norm_bwd.cuh) and hands over dy instead of g."""
     N = g.shape[0]
     red = rt.zeros(4, N, 2)
+    dy_ready = False
     for i in (3, 2, 1, 0):
         conv, norm = enc.convs[i], enc.norms[i]
         x, z, stats, xpad = ctx[i]
-        dz = torch.empty_like(z)
-        K.instnorm_act_bwd(g.view_as(z), z, stats, norm.gamma, norm.beta, red[i], dz,
-                           _grad(norm.gamma) if wgrad else None, _grad(norm.beta) if wgrad else None,
-                           norm.epsilon, 1.0, rt.alpha)
+        dz = _norm_act_bwd(rt, g, z, stats, norm, red[i], conv, wgrad, dy_ready)
         _, Hb, Wb, A = x.shape
         B = conv.filters
         if wgrad:
-            K.bias_grad(dz, _grad(conv.bias))
             if xpad is not None and rt.use_tc(K.OP_WGRAD, N, Hb, Wb, 16, B, 2):
                 K.conv2d_wgrad_padded(xpad, dz, _grad(conv.kernel), 2)
             else:
                 K.conv2d_wgrad(x, dz, _grad(conv.kernel), 2, rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2))
+        dy_ready = False
         if i > 0 or input_grad:
             g = torch.empty_like(x)
+            nb = None
+            if i > 0 and rt.fuse_norm_bwd(K.OP_DGRAD, N, Hb, Wb, A, B, 2):
+                _, zp, sp, _ = ctx[i - 1]
+                nb = K.norm_bwd_desc(zp, sp, enc.norms[i - 1].gamma, enc.norms[i - 1].beta, red[i - 1],
+                                     enc.norms[i - 1].epsilon, rt.alpha)
+                dy_ready = True
             K.conv2d_dgrad(dz, conv.kernel, None, g, None, 2, K.ACT_NONE, conv.wpack,
-                           rt.use_tc(K.OP_DGRAD, N, Hb, Wb, A, B, 2))
+                           rt.use_tc(K.OP_DGRAD, N, Hb, Wb, A, B, 2), norm_bwd=nb)
         else:
             g = None
     return g
@@ -152,24 +192,32 @@ def decoder_forward(rt, dec, x, skips_after=(None, None, None)):
     return x, ctx
 
 
-def decoder_backward(rt, dec, ctx, g, wgrad):
-    """Returns the gradient w.r.t. the decoder input (always needed: the heads sit below)."""
+def decoder_backward(rt, dec, ctx, g, wgrad, red=None, dy_ready=False):
+    """Returns the gradient w.r.t. the decoder input (always needed: the heads sit below).
+    `red` / `dy_ready`: the producer of `g` (final_conv_backward) already ran pass 1 of the last layer's
+    norm backward into red[3]."""
     N = g.shape[0]
-    red = rt.zeros(4, N, 2)
+    if red is None:
+        red = rt.zeros(4, N, 2)
+        dy_ready = False
     for i in (3, 2, 1, 0):
         conv, norm = dec.convs[i], dec.norms[i]
         x, z, stats = ctx[i]
-        dz = torch.empty_like(z)
-        K.instnorm_act_bwd(g, z, stats, norm.gamma, norm.beta, red[i], dz,
-                           _grad(norm.gamma) if wgrad else None, _grad(norm.beta) if wgrad else None,
-                           norm.epsilon, 1.0, rt.alpha)
+        dz = _norm_act_bwd(rt, g, z, stats, norm, red[i], conv, wgrad, dy_ready)
         _, Hb, Wb, A = z.shape
         B = x.shape[3]
         if wgrad:
-            K.bias_grad(dz, _grad(conv.bias))
             K.conv2d_wgrad(dz, x, _grad(conv.kernel), 2, rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2))
         g = torch.empty_like(x)
-        K.conv2d_fprop(dz, conv.kernel, None, g, None, 2, conv.wpack, rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, 2))
+        nb = None
+        dy_ready = False
+        if i > 0 and rt.fuse_norm_bwd(K.OP_FPROP, N, Hb, Wb, A, B, 2):
+            _, zp, sp = ctx[i - 1]
+            nb = K.norm_bwd_desc(zp, sp, dec.norms[i - 1].gamma, dec.norms[i - 1].beta, red[i - 1],
+                                 dec.norms[i - 1].epsilon, rt.alpha)
+            dy_ready = True
+        K.conv2d_fprop(dz, conv.kernel, None, g, None, 2, conv.wpack, rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, 2),
+                       norm_bwd=nb)
     return g
 
 
@@ -186,8 +234,9 @@ def final_conv_forward(rt, conv, x, out=None):
     return out
 
 
-def final_conv_backward(rt, conv, x, dpre, wgrad):
-    """dpre: gradient w.r.t. the pre-tanh output.  Returns the gradient w.r.t. x."""
+def final_conv_backward(rt, conv, x, dpre, wgrad, nb=None):
+    """dpre: gradient w.r.t. the pre-tanh output.  Returns the gradient w.r.t. x (with `nb`, a
+    lg_norm_bwd_t of the decoder's last layer: dy of that layer, pass 1 of its norm backward done)."""
     N, H, W, B = x.shape
     A = conv.filters
     dpad = _padded_for_tc(rt, dpre, K.OP_FPROP, B, 1)
@@ -199,10 +248,33 @@ def final_conv_backward(rt, conv, x, dpre, wgrad):
             K.conv2d_wgrad(dpre, x, _grad(conv.kernel), 1, rt.use_tc(K.OP_WGRAD, N, H, W, A, B, 1))
     g = torch.empty_like(x)
     if dpad is not None:
-        K.conv2d_fprop(dpad, conv.kernel, None, g, None, 1, conv.wpack, True)
+        K.conv2d_fprop(dpad, conv.kernel, None, g, None, 1, conv.wpack, True, norm_bwd=nb)
     else:
-        K.conv2d_fprop(dpre, conv.kernel, None, g, None, 1, conv.wpack, rt.use_tc(K.OP_FPROP, N, H, W, A, B, 1))
+        K.conv2d_fprop(dpre, conv.kernel, None, g, None, 1, conv.wpack, rt.use_tc(K.OP_FPROP, N, H, W, A, B, 1),
+                       norm_bwd=nb)
     return g
+
+
+def generator_tail_backward(rt, dec, conv, dctx, x4, dpre, wgrad):
+    """final conv backward + decoder backward (Generator / Adjuster share the tail, model.py:103-104,
+    135-136); the final conv's input-gradient launch carries pass 1 of the last decoder norm backward."""
+    N, H, W, B = x4.shape
+    A = conv.filters
+    red, nb = None, None
+    Ain = 16 if (_would_pad(rt, N, H, W, A, B)) else A
+    if rt.fuse_norm_bwd(K.OP_FPROP, N, H, W, Ain, B, 1):
+        red = rt.zeros(4, N, 2)
+        _, z3, s3 = dctx[3]
+        nb = K.norm_bwd_desc(z3, s3, dec.norms[3].gamma, dec.norms[3].beta, red[3], dec.norms[3].epsilon, rt.alpha)
+    g = final_conv_backward(rt, conv, x4, dpre, wgrad, nb)
+    return decoder_backward(rt, dec, dctx, g, wgrad, red, nb is not None)
+
+
+def _would_pad(rt, N, H, W, A, B):
+    """Mirrors _padded_for_tc's decision for a [N,H,W,A] gradient feeding the stride-1 fprop."""
+    if A >= 16 or not rt.want_tc or rt.use_tc(K.OP_FPROP, N, H, W, A, B, 1):
+        return False
+    return rt.use_tc(K.OP_FPROP, N, H, W, 16, B, 1)
 
 
 # --------------------------------------------------------------------------------------------
@@ -239,6 +311,13 @@ def disc_heads_forward(rt, disc, feat):
     N = feat.shape[0]
     f = feat.view(N, -1)
     F = f.shape[1]
+    U0, U1 = disc.dense_pr.units, disc.dense_cond.units
+    if K.dense_heads_supported(F, U0, U1):
+        pr = rt.empty(N, U0, dtype=torch.float32)
+        c = rt.empty(N, U1, dtype=torch.float32)
+        K.dense_heads_fwd(f, disc.dense_pr.kernel, disc.dense_pr.bias, disc.dense_cond.kernel, disc.dense_cond.bias,
+                          pr, c, K.ACT_SIGMOID, rt.heads_workspace(N))
+        return pr, c
     outs = []
     for dense in (disc.dense_pr, disc.dense_cond):
         o = rt.zeros(N, dense.units, dtype=torch.float32)
@@ -253,8 +332,17 @@ def disc_heads_backward(rt, disc, feat, dl_pr, dl_c, wgrad):
     N = feat.shape[0]
     f = feat.view(N, -1)
     F = f.shape[1]
+    dp, dc = disc.dense_pr, disc.dense_cond
+    if K.dense_heads_supported(F, dp.units, dc.units):
+        df = torch.empty_like(f)
+        if wgrad:
+            K.dense_heads_bwd(f, dl_pr, dl_c, dp.kernel, dc.kernel, df, _grad(dp.kernel), _grad(dc.kernel),
+                              _grad(dp.bias), _grad(dc.bias))
+        else:
+            K.dense_heads_bwd(None, dl_pr, dl_c, dp.kernel, dc.kernel, df, None, None, None, None)
+        return df.view_as(feat)
     df = rt.zeros(N, F, dtype=torch.float32)
-    for dense, dl in ((disc.dense_pr, dl_pr), (disc.dense_cond, dl_c)):
+    for dense, dl in ((dp, dl_pr), (dc, dl_c)):
         if dl is None:
             continue
         U = dense.units

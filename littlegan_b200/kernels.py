@@ -62,23 +62,40 @@ def tc_available():
 
 
 # ------------------------------------------------------------------------------------------- conv
-def conv2d_fprop(big, W, bias, out, stats, stride, wpack=None, use_tc=False):
+def norm_bwd_supported(op, N, Hb, Wb, A, B, stride):
+    return bool(_lib.load().lg_conv2d_norm_bwd_supported(op, N, Hb, Wb, A, B, stride))
+
+
+def norm_bwd_desc(z, stats, gamma, beta, red, eps, alpha):
+    """lg_norm_bwd_t for a backward conv launch whose output is dL/d(LeakyReLU(IN(z)))."""
+    _cuda(z, stats, gamma, beta, red)
+    if z.dtype != torch.bfloat16:
+        raise _lib.LittleGANError("the fused norm-backward epilogue needs bf16 activations")
+    return _lib.NormBwd(_p(z), _p(stats), _p(gamma), _p(beta), _p(red), eps, alpha)
+
+
+def _nb(desc):
+    import ctypes
+    return None if desc is None else ctypes.byref(desc)
+
+
+def conv2d_fprop(big, W, bias, out, stats, stride, wpack=None, use_tc=False, norm_bwd=None):
     """small = conv(big): big [N,Hb,Wb,A], W [5,5,A,B] fp32, out [N,Hb/s,Wb/s,B]."""
     _cuda(big, W, bias, out, stats, wpack)
     N, Hb, Wb, A = big.shape
     B = out.shape[3]
     check(_lib.load().lg_conv2d_fprop(_p(big), _p(W), _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
-                                      stride, dt(big), int(use_tc), _st()), "lg_conv2d_fprop")
+                                      stride, dt(big), int(use_tc), _nb(norm_bwd), _st()), "lg_conv2d_fprop")
     return out
 
 
-def conv2d_dgrad(small, W, bias, out, stats, stride, act=ACT_NONE, wpack=None, use_tc=False):
+def conv2d_dgrad(small, W, bias, out, stats, stride, act=ACT_NONE, wpack=None, use_tc=False, norm_bwd=None):
     """big = conv_transpose(small): small [N,Hs,Ws,B], W [5,5,A,B] fp32, out [N,s*Hs,s*Ws,A]."""
     _cuda(small, W, bias, out, stats, wpack)
     N, Hb, Wb, A = out.shape
     B = small.shape[3]
     check(_lib.load().lg_conv2d_dgrad(_p(small), _p(W), _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
-                                      stride, act, dt(small), int(use_tc), _st()), "lg_conv2d_dgrad")
+                                      stride, act, dt(small), int(use_tc), _nb(norm_bwd), _st()), "lg_conv2d_dgrad")
     return out
 
 
@@ -139,17 +156,28 @@ def instnorm_act_fwd(z, stats, gamma, beta, skip, out, eps, alpha_pre, alpha_pos
     return out
 
 
-def instnorm_act_bwd(g, z, stats, gamma, beta, red, dz, dgamma, dbeta, eps, alpha_pre, alpha_post):
-    """Two passes: per-sample reductions into `red` (zeroed by the caller), then dz."""
-    _cuda(g, z, stats, gamma, beta, red, dz, dgamma, dbeta)
+def bias_grad_fusable(z):
+    """Can lg_instnorm_act_bwd_apply also produce the bias gradient of the conv that wrote z [N,...,C]?"""
+    N = z.shape[0]
+    return bool(_lib.load().lg_instnorm_bias_grad_fusable(z.numel() // N, z.shape[-1], dt(z)))
+
+
+def instnorm_act_bwd(g, z, stats, gamma, beta, red, dz, dgamma, dbeta, eps, alpha_pre, alpha_post, dy_ready=False,
+                     dbias=None):
+    """Two passes: per-sample reductions into `red` (zeroed by the caller), then dz.  dy_ready: pass 1 was
+    done by the conv launch that produced `g` (norm_bwd epilogue).  dbias: also accumulate the per-channel
+    sums of dz (needs bias_grad_fusable(z))."""
+    _cuda(g, z, stats, gamma, beta, red, dz, dgamma, dbeta, dbias)
     N = z.shape[0]
     M = z.numel() // N
     lib = _lib.load()
-    check(lib.lg_instnorm_act_bwd_reduce(_p(g), _p(z), _p(stats), _p(gamma), _p(beta), _p(red), N, M, eps,
-                                         alpha_pre, alpha_post, dt(z), dt(g), _st()), "lg_instnorm_act_bwd_reduce")
+    if not dy_ready:
+        check(lib.lg_instnorm_act_bwd_reduce(_p(g), _p(z), _p(stats), _p(gamma), _p(beta), _p(red), N, M, eps,
+                                             alpha_pre, alpha_post, dt(z), dt(g), _st()),
+              "lg_instnorm_act_bwd_reduce")
     check(lib.lg_instnorm_act_bwd_apply(_p(g), _p(z), _p(stats), _p(red), _p(gamma), _p(beta), _p(dz), _p(dgamma),
-                                        _p(dbeta), N, M, eps, alpha_pre, alpha_post, dt(z), dt(g), _st()),
-          "lg_instnorm_act_bwd_apply")
+                                        _p(dbeta), _p(dbias), z.shape[-1], int(dy_ready), N, M, eps, alpha_pre,
+                                        alpha_post, dt(z), dt(g), _st()), "lg_instnorm_act_bwd_apply")
     return dz
 
 
@@ -159,6 +187,34 @@ def gemm(A, Bm, C, M, N, K, bias=None, transA=False, transB=False, accumulate=Fa
     check(_lib.load().lg_gemm(_p(A), _p(Bm), _p(bias), _p(C), M, N, K, int(transA), int(transB), int(accumulate),
                               dt(A), dt(C), _st()), "lg_gemm")
     return C
+
+
+def dense_heads_supported(F, U0, U1):
+    return U0 + U1 <= 48 and F % 64 == 0
+
+
+def dense_heads_workspace(N, device):
+    """Zero-filled scratch of the fused heads forward (the kernel leaves it zeroed after every call)."""
+    nbytes = int(_lib.check(_lib.load().lg_dense_heads_workspace_bytes(N)))
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+
+def dense_heads_fwd(feat, W0, b0, W1, b1, out0, out1, act, workspace):
+    """out_h = act(feat @ W_h + b_h) for two Dense layers sharing `feat` [N,F] (model.py:62-63,70-72)."""
+    _cuda(feat, W0, b0, W1, b1, out0, out1, workspace)
+    N, F = feat.shape
+    check(_lib.load().lg_dense_heads_fwd(_p(feat), _p(W0), _p(b0), W0.shape[1], _p(W1), _p(b1), W1.shape[1],
+                                         _p(out0), _p(out1), N, F, act, dt(feat), _p(workspace), _st()),
+          "lg_dense_heads_fwd")
+
+
+def dense_heads_bwd(feat, dl0, dl1, W0, W1, dfeat, dW0, dW1, db0, db1):
+    _cuda(feat, dl0, dl1, W0, W1, dfeat, dW0, dW1, db0, db1)
+    ref = feat if feat is not None else dfeat
+    N, F = ref.shape
+    check(_lib.load().lg_dense_heads_bwd(_p(feat), _p(dl0), _p(dl1), _p(W0), W0.shape[1], _p(W1), W1.shape[1],
+                                         _p(dfeat), _p(dW0), _p(dW1), _p(db0), _p(db1), N, F, dt(ref), _st()),
+          "lg_dense_heads_bwd")
 
 
 def bias_act(x, bias, act):

@@ -159,6 +159,46 @@ def test_gemm(tA, tB, acc, adt):
     assert rel_err(C, ref) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,F,U1", [(5, 128, 7), (128, 1536, 40), (200, 512, 47), (64, 24576, 40)])
+def test_dense_heads_fwd_bwd(N, F, U1, dtype):
+    """Discriminator heads (model.py:62-63,70-72) as one fused pass; repeated calls share a workspace."""
+    from littlegan_b200 import kernels as K
+    f = _rand((N, F), 50, dtype, 0.5)
+    W0 = _rand((F, 1), 51, torch.float32, 0.05)
+    W1 = _rand((F, U1), 52, torch.float32, 0.05)
+    b0 = _rand((1,), 53, torch.float32)
+    b1 = _rand((U1,), 54, torch.float32)
+    dl0 = _rand((N, 1), 55, torch.float32)
+    dl1 = _rand((N, U1), 56, torch.float32)
+    fd = f.double()
+    ref0 = torch.sigmoid(fd @ W0.double() + b0.double())
+    ref1 = torch.sigmoid(fd @ W1.double() + b1.double())
+    ws = K.dense_heads_workspace(N, "cuda")
+    fc, W0c, W1c = f.cuda(), W0.cuda(), W1.cuda()
+    for _ in range(3):                                   # the kernel must leave the workspace zeroed
+        o0 = torch.full((N, 1), 7.0, device="cuda")
+        o1 = torch.full((N, U1), 7.0, device="cuda")
+        K.dense_heads_fwd(fc, W0c, b0.cuda(), W1c, b1.cuda(), o0, o1, K.ACT_SIGMOID, ws)
+        assert rel_err(o0, ref0) < 1e-4 and rel_err(o1, ref1) < 1e-4
+    assert int(ws.to(torch.int32).abs().sum()) == 0
+
+    ref_df = dl0.double() @ W0.double().T + dl1.double() @ W1.double().T
+    df = torch.empty(N, F, dtype=dtype, device="cuda")
+    dW0 = torch.ones(F, 1, device="cuda"); dW1 = torch.ones(F, U1, device="cuda")
+    db0 = torch.ones(1, device="cuda"); db1 = torch.ones(U1, device="cuda")
+    K.dense_heads_bwd(fc, dl0.cuda(), dl1.cuda(), W0c, W1c, df, dW0, dW1, db0, db1)
+    assert rel_err(df, ref_df) < tol(dtype)
+    assert rel_err(dW0, 1 + fd.T @ dl0.double()) < 1e-4
+    assert rel_err(dW1, 1 + fd.T @ dl1.double()) < 1e-4
+    assert rel_err(db0, 1 + dl0.double().sum(0)) < 1e-4
+    assert rel_err(db1, 1 + dl1.double().sum(0)) < 1e-4
+    # input-gradient only (generator / adjuster steps), one head's gradient absent
+    df2 = torch.empty(N, F, dtype=dtype, device="cuda")
+    K.dense_heads_bwd(None, None, dl1.cuda(), W0c, W1c, df2, None, None, None, None)
+    assert rel_err(df2, dl1.double() @ W1.double().T) < tol(dtype)
+
+
 def test_bce_and_l1():
     from littlegan_b200 import kernels as K
     rows, cols = 6, 5
@@ -348,6 +388,107 @@ def test_tc_cin3_fprop_wgrad(geom):
     K.conv2d_wgrad(x.cuda(), small.cuda(), dW, s, use_tc=True)
     torch.cuda.synchronize()
     assert rel_err(dW, dW_ref) < 1e-4
+
+
+def _norm_bwd_reference(g, z, gamma, beta, alpha, eps=1e-3):
+    """fp64: dy = g * LeakyReLU'(y) and the per-sample sums (sum dy, sum dy*xhat) of instance.py's norm."""
+    N = z.shape[0]
+    zf = z.double().reshape(N, -1)
+    mu = zf.mean(1, keepdim=True)
+    sigma = ((zf - mu) ** 2).mean(1, keepdim=True).sqrt()
+    xhat = (zf - mu) / (sigma + eps)
+    y = gamma * xhat + beta
+    dy = g.double().reshape(N, -1) * torch.where(y > 0, 1.0, alpha)
+    red = torch.stack([dy.sum(1), (dy * xhat).sum(1)], 1)
+    return dy.reshape(g.shape), red
+
+
+NB_CASES = [
+    ("fprop", (2, 64, 64, 64, 128, 2)),      # tc_conv fprop (decoder backward), N tile 128
+    ("fprop", (3, 16, 16, 256, 384, 2)),     # 2 x 192-channel tiles, a tile spans two samples
+    ("fprop", (2, 128, 128, 32, 64, 2)),     # dec4 backward
+    ("fprop", (2, 128, 128, 3, 32, 1)),      # final conv backward on the RGB im2col kernel
+    ("dgrad", (3, 16, 16, 256, 384, 2)),     # tc_conv dgrad (encoder backward), 256 output channels
+    ("dgrad", (2, 32, 32, 128, 256, 2)),
+    ("dgrad", (2, 64, 64, 64, 128, 2)),      # four-phase kernel
+    ("dgrad", (2, 128, 128, 32, 64, 2)),
+]
+
+
+@pytest.mark.parametrize("op,geom", NB_CASES)
+def test_tc_fused_norm_backward_epilogue(op, geom):
+    """A backward conv launch with the lg_norm_bwd_t epilogue == the plain launch followed by pass 1 of the
+    norm backward (and the whole IN backward agrees with autograd of the oracle's instance_norm)."""
+    from littlegan_b200 import kernels as K
+    N, Hb, Wb, A, B, s = geom
+    kop = K.OP_FPROP if op == "fprop" else K.OP_DGRAD
+    assert K.tc_supported(kop, N, Hb, Wb, A, B, s) and K.norm_bwd_supported(kop, N, Hb, Wb, A, B, s)
+    W = _rand((5, 5, A, B), 2, torch.bfloat16, 0.05).float()
+    if op == "fprop":
+        x = _rand((N, Hb, Wb, A), 1, torch.bfloat16)
+        g_ref = O.conv2d_same(x.double(), W.double(), None, s)
+        oshape = (N, Hb // s, Wb // s, B)
+    else:
+        x = _rand((N, Hb // s, Wb // s, B), 1, torch.bfloat16)
+        g_ref = O.conv2d_transpose_same(x.double(), W.double(), None, s)
+        oshape = (N, Hb, Wb, A)
+    z = (_rand(oshape, 3, torch.float32, 1.5) + 0.3).to(torch.bfloat16)
+    gamma, beta, alpha = torch.tensor([0.9]), torch.tensor([0.15]), 0.3
+    dy_ref, red_ref = _norm_bwd_reference(g_ref, z, 0.9, 0.15, alpha)
+
+    zc, Wc = z.cuda(), W.cuda()
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.rowstats(zc, stats, 1.0)
+    red = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    nb = K.norm_bwd_desc(zc, stats, gamma.cuda(), beta.cuda(), red, 1e-3, alpha)
+    out = torch.zeros(oshape, dtype=torch.bfloat16, device="cuda")
+    if op == "fprop":
+        K.conv2d_fprop(x.cuda(), Wc, None, out, None, s, wpack=_pack(Wc), use_tc=True, norm_bwd=nb)
+    else:
+        K.conv2d_dgrad(x.cuda(), Wc, None, out, None, s, K.ACT_NONE, wpack=_pack(Wc), use_tc=True, norm_bwd=nb)
+    torch.cuda.synchronize()
+    assert rel_err(out, dy_ref) < 1e-2
+    assert float(((red.cpu() - red_ref).abs() / red_ref.abs().max()).max()) < 1e-4
+
+    # pass 2 on the handed-over dy (+ fused bias gradient) against autograd through the oracle's norm
+    zr = z.double().requires_grad_(True)
+    gr = gamma.double().requires_grad_(True); br = beta.double().requires_grad_(True)
+    a = torch.nn.functional.leaky_relu(O.instance_norm(zr, gr, br), alpha)
+    dz_ref, dg_ref, db_ref = torch.autograd.grad((a * g_ref).sum(), [zr, gr, br])
+    dz = torch.empty_like(zc)
+    dgam = torch.zeros(1, device="cuda"); dbet = torch.zeros(1, device="cuda")
+    C = oshape[-1]
+    dbias = torch.zeros(C, device="cuda") if K.bias_grad_fusable(zc) else None
+    K.instnorm_act_bwd(out, zc, stats, gamma.cuda(), beta.cuda(), red, dz, dgam, dbet, 1e-3, 1.0, alpha,
+                       dy_ready=True, dbias=dbias)
+    assert rel_err(dz, dz_ref) < 2e-2
+    assert rel_err(dgam, dg_ref) < 2e-3 and rel_err(dbet, db_ref) < 2e-3
+    if dbias is not None:
+        assert rel_err(dbias, dz_ref.reshape(-1, C).sum(0)) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(3, 16, 16, 64), (2, 8, 8, 32), (2, 64, 64, 256)])
+def test_instnorm_bwd_fused_bias_grad(shape, dtype):
+    from littlegan_b200 import kernels as K
+    N, C = shape[0], shape[-1]
+    z = (_rand(shape, 20, torch.float32, 2.0) + 0.5).to(dtype)
+    gout = _rand(shape, 22, dtype)
+    gamma = torch.tensor([1.3]); beta = torch.tensor([-0.2])
+    zr = z.double().requires_grad_(True)
+    ref = torch.nn.functional.leaky_relu(O.instance_norm(zr, gamma.double(), beta.double()), 0.3)
+    (dz_ref,) = torch.autograd.grad((ref * gout.double()).sum(), [zr])
+    zc = z.cuda()
+    assert K.bias_grad_fusable(zc)
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.rowstats(zc, stats, 1.0)
+    red = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    dz = torch.empty_like(zc)
+    dbias = torch.ones(C, device="cuda")
+    K.instnorm_act_bwd(gout.cuda(), zc, stats, gamma.cuda(), beta.cuda(), red, dz, None, None, 1e-3, 1.0, 0.3,
+                       dbias=dbias)
+    assert rel_err(dz, dz_ref) < tol(dtype) * 2
+    assert rel_err(dbias - 1, dz_ref.reshape(-1, C).sum(0)) < (1e-4 if dtype == torch.float32 else 2e-3)
 
 
 TC_W = [
