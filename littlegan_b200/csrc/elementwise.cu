@@ -220,8 +220,18 @@ __global__ void __launch_bounds__(NT) instnorm_bwd_apply_kernel(const T* __restr
     }
   }
   if constexpr (DB) {
+    // lanes l and l + G (G = C/V channel groups per warp, a power of two) hold the same channels: fold them
+    // with shuffles first, so a warp issues G*V shared atomics instead of 32*V
+    const int G = C / V;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (o >= G) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], o);
+      }
+    }
     const int c0 = (int)((beg + (int64_t)threadIdx.x * V) % C);
-    if (beg + (int64_t)threadIdx.x * V < end) {
+    if ((threadIdx.x & 31) < G || G >= 32) {
 #pragma unroll
       for (int k = 0; k < V; ++k) atomicAdd(&shc[c0 + k], bsum[k]);
     }

@@ -24,33 +24,78 @@ template <typename TF> struct Pitch { static constexpr int v = KS + (sizeof(TF) 
 
 template <typename TF>
 __device__ __forceinline__ void stage_feat(const TF* __restrict__ feat, TF* fs, int n0, int N, int F, int k0) {
-  // NC x KS tile, 16-byte global loads, zero beyond N
+  // NC x KS tile, 16-byte global loads (all issued before the first store), zero beyond N
   constexpr int VE = 16 / sizeof(TF);
-  for (int e = threadIdx.x; e < NC * (KS / VE); e += HT) {
+  constexpr int FP = Pitch<TF>::v;
+  constexpr int PER = NC * (KS / VE) / HT;
+  static_assert(NC * (KS / VE) % HT == 0, "tile must divide over the CTA");
+  uint4 v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int e = threadIdx.x + i * HT;
     const int r = e / (KS / VE), c = (e - r * (KS / VE)) * VE;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (n0 + r < N) v = *reinterpret_cast<const uint4*>(feat + (int64_t)(n0 + r) * F + k0 + c);
-    constexpr int FP = Pitch<TF>::v;
+    v[i] = make_uint4(0, 0, 0, 0);
+    if (n0 + r < N) v[i] = __ldg(reinterpret_cast<const uint4*>(feat + (int64_t)(n0 + r) * F + k0 + c));
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int e = threadIdx.x + i * HT;
+    const int r = e / (KS / VE), c = (e - r * (KS / VE)) * VE;
     if constexpr (sizeof(TF) == 2) {
       uint32_t* d = reinterpret_cast<uint32_t*>(fs + r * FP + c);          // (r*66 + c) is even
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
     } else {
-      const TF* pv = reinterpret_cast<const TF*>(&v);
+      const TF* pv = reinterpret_cast<const TF*>(&v[i]);
 #pragma unroll
-      for (int i = 0; i < VE; ++i) fs[r * FP + c + i] = pv[i];
+      for (int j = 0; j < VE; ++j) fs[r * FP + c + j] = pv[j];
     }
   }
 }
 
 __device__ __forceinline__ void stage_w(const float* __restrict__ W0, int U0, const float* __restrict__ W1, int U1,
                                         float* ws, int k0) {
-  // ws[k][u]: columns [0,U0) from W0, [U0,U0+U1) from W1, zero padding up to UP
-  for (int e = threadIdx.x; e < KS * UP; e += HT) {
+  // ws[k][u]: columns [0,U0) from W0, [U0,U0+U1) from W1, zero padding up to UP.  All loads are issued
+  // before the first store (a load-store-load-store chain pays one memory round trip per element).
+  constexpr int PER = KS * UP / HT;
+  static_assert(KS * UP % HT == 0, "tile must divide over the CTA");
+  float v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int e = threadIdx.x + i * HT;
     const int k = e / UP, u = e - k * UP;
-    float v = 0.f;
-    if (u < U0) v = W0[(int64_t)(k0 + k) * U0 + u];
-    else if (u < U0 + U1) v = W1[(int64_t)(k0 + k) * U1 + (u - U0)];
-    ws[e] = v;
+    v[i] = 0.f;
+    if (u < U0) v[i] = __ldg(W0 + (int64_t)(k0 + k) * U0 + u);
+    else if (u < U0 + U1) v[i] = __ldg(W1 + (int64_t)(k0 + k) * U1 + (u - U0));
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) ws[threadIdx.x + i * HT] = v[i];
+}
+
+// dls[r][u] (pitch DP): logit gradients of samples n0 .. n0+NC-1, columns as in stage_w, zero padded
+template <int DP>
+__device__ __forceinline__ void stage_dl(const float* __restrict__ dl0, int U0, const float* __restrict__ dl1, int U1,
+                                         float* dls, int n0, int N) {
+  constexpr int PER = NC * UP / HT, HALF = PER / 2;
+  static_assert(NC * UP % (2 * HT) == 0, "tile must divide over the CTA");
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float v[HALF];
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+      const int e = threadIdx.x + (h * HALF + i) * HT;
+      const int r = e / UP, u = e - r * UP;
+      v[i] = 0.f;
+      if (n0 + r < N) {
+        if (u < U0) { if (dl0) v[i] = __ldg(dl0 + (int64_t)(n0 + r) * U0 + u); }
+        else if (u < U0 + U1) { if (dl1) v[i] = __ldg(dl1 + (int64_t)(n0 + r) * U1 + (u - U0)); }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+      const int e = threadIdx.x + (h * HALF + i) * HT;
+      const int r = e / UP, u = e - r * UP;
+      dls[r * DP + u] = v[i];
+    }
   }
 }
 
@@ -68,43 +113,58 @@ __global__ void __launch_bounds__(HT) heads_fwd_kernel(const TF* __restrict__ fe
   TF* fs = reinterpret_cast<TF*>(ws + KS * UP);              // [NC][FP]
   __shared__ bool last;
   constexpr int FP = Pitch<TF>::v;
-  const int k0 = blockIdx.x * KS;
   const int U = U0 + U1;
-  stage_w(W0, U0, W1, U1, ws, k0);
-  // thread tile: 4 samples (ns, ns+32, ns+64, ns+96) x 6 columns (warp-uniform column group)
+  const int nslices = F / KS;
+  // thread tile: 4 samples (ns, ns+32, ns+64, ns+96) x 6 columns (warp-uniform column group); a CTA walks
+  // its feature slices with the accumulators in registers and adds them to the workspace once per pass
   const int ns = threadIdx.x & 31, ug = threadIdx.x >> 5;
   for (int n0 = 0; n0 < N; n0 += NC) {
-    __syncthreads();
-    stage_feat<TF>(feat, fs, n0, N, F, k0);
-    __syncthreads();
     float acc[4][6];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < KS; ++k) {
-      float w[6];
-      const float2 w01 = *reinterpret_cast<const float2*>(ws + k * UP + ug * 6);
-      const float2 w23 = *reinterpret_cast<const float2*>(ws + k * UP + ug * 6 + 2);
-      const float2 w45 = *reinterpret_cast<const float2*>(ws + k * UP + ug * 6 + 4);
-      w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y; w[4] = w45.x; w[5] = w45.y;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+      const int k0 = sl * KS;
+      __syncthreads();
+      stage_w(W0, U0, W1, U1, ws, k0);
+      stage_feat<TF>(feat, fs, n0, N, F, k0);
+      __syncthreads();
+      constexpr int KSTEP = sizeof(TF) == 2 ? 2 : 1;
+#pragma unroll 2
+      for (int k = 0; k < KS; k += KSTEP) {
+        float w[KSTEP][6];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float f = to_f(fs[(ns + 32 * i) * FP + k]);
+        for (int kk = 0; kk < KSTEP; ++kk) {
+          const float2 w01 = *reinterpret_cast<const float2*>(ws + (k + kk) * UP + ug * 6);
+          const float2 w23 = *reinterpret_cast<const float2*>(ws + (k + kk) * UP + ug * 6 + 2);
+          const float2 w45 = *reinterpret_cast<const float2*>(ws + (k + kk) * UP + ug * 6 + 4);
+          w[kk][0] = w01.x; w[kk][1] = w01.y; w[kk][2] = w23.x; w[kk][3] = w23.y; w[kk][4] = w45.x; w[kk][5] = w45.y;
+        }
 #pragma unroll
-        for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(f, w[j], acc[i][j]);
+        for (int i = 0; i < 4; ++i) {
+          float f[KSTEP];
+          if constexpr (sizeof(TF) == 2) {
+            const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(fs + (ns + 32 * i) * FP + k));
+            f[0] = f2.x; f[1] = f2.y;
+          } else {
+            f[0] = to_f(fs[(ns + 32 * i) * FP + k]);
+          }
+#pragma unroll
+          for (int kk = 0; kk < KSTEP; ++kk)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(f[kk], w[kk][j], acc[i][j]);
+        }
       }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = n0 + ns + 32 * i;
       if (n >= N) continue;
+      float* dst = ws_acc + (int64_t)n * UP + ug * 6;          // padded columns stay zero: sums of zeros
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int u = ug * 6 + j;
-        if (u < U) atomicAdd(&ws_acc[(int64_t)n * UP + u], acc[i][j]);
-      }
+      for (int j = 0; j < 6; j += 2)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + j), "f"(acc[i][j]), "f"(acc[i][j + 1]) : "memory");
     }
   }
   // last CTA: bias + activation, write the two outputs, leave the workspace zeroed for the next call
@@ -141,20 +201,20 @@ __global__ void __launch_bounds__(HT) heads_bwd_kernel(const TF* __restrict__ fe
                                                        TF* __restrict__ dfeat, float* dW0, float* dW1, float* db0,
                                                        float* db1, int N, int F) {
   extern __shared__ __align__(16) uint8_t hsm[];
-  float* ws = reinterpret_cast<float*>(hsm);                 // [KS][UP]
-  float* dls = ws + KS * UP;                                 // [NC][UP+1]
-  TF* fs = reinterpret_cast<TF*>(dls + NC * (UP + 1));       // [NC][FP]   (weight gradient only)
-  constexpr int DP = UP + 1;
+  constexpr int DP = UP + 4;                                 // 52 floats: 16-byte rows, conflict-free LDS.128
   constexpr int FP = Pitch<TF>::v;
+  float* ws = reinterpret_cast<float*>(hsm);                 // [KS][UP]
+  float* dls = ws + KS * UP;                                 // [NC][DP]
+  TF* fs = reinterpret_cast<TF*>(dls + NC * DP);             // [NC][FP]   (weight gradient only)
   const int k0 = blockIdx.x * KS;
   const int U = U0 + U1;
   const bool wgrad = dW0 != nullptr || dW1 != nullptr;
   stage_w(W0, U0, W1, U1, ws, k0);
 
-  // d(feat) tile: 8 samples (ns + 16 i) x 4 features (kg*4 .. +3) per thread
+  // d(feat) tile: 8 samples (ns + 16 i) x 4 features (kg*4 .. +3) per thread, columns four at a time
   const int ns = threadIdx.x & 15, kg = threadIdx.x >> 4;
-  // dW tile: feature kw, columns uh*24 .. +23
-  const int kw = threadIdx.x & 63, uh = threadIdx.x >> 6;     // 4 column groups of 12
+  // dW tile: feature kw, columns uh*12 .. +11
+  const int kw = threadIdx.x & 63, uh = threadIdx.x >> 6;
   float wacc[12];
 #pragma unroll
   for (int j = 0; j < 12; ++j) wacc[j] = 0.f;
@@ -162,15 +222,7 @@ __global__ void __launch_bounds__(HT) heads_bwd_kernel(const TF* __restrict__ fe
 
   for (int n0 = 0; n0 < N; n0 += NC) {
     __syncthreads();
-    for (int e = threadIdx.x; e < NC * UP; e += HT) {
-      const int r = e / UP, u = e - r * UP;
-      float v = 0.f;
-      if (n0 + r < N) {
-        if (u < U0) v = dl0 ? dl0[(int64_t)(n0 + r) * U0 + u] : 0.f;
-        else if (u < U) v = dl1 ? dl1[(int64_t)(n0 + r) * U1 + (u - U0)] : 0.f;
-      }
-      dls[r * DP + u] = v;
-    }
+    stage_dl<DP>(dl0, U0, dl1, U1, dls, n0, N);
     if (wgrad) stage_feat<TF>(feat, fs, n0, N, F, k0);
     __syncthreads();
 
@@ -180,15 +232,16 @@ __global__ void __launch_bounds__(HT) heads_bwd_kernel(const TF* __restrict__ fe
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      for (int u = 0; u < U; ++u) {
-        float w[4];
+      for (int u = 0; u < U; u += 4) {                       // columns >= U are zero in both operands
+        float4 w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = ws[(kg * 4 + j) * UP + u];
+        for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(ws + (kg * 4 + j) * UP + u);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float d = dls[(ns + 16 * i) * DP + u];
+          const float4 d = *reinterpret_cast<const float4*>(dls + (ns + 16 * i) * DP + u);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(d, w[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j)
+            acc[i][j] = fmaf(d.x, w[j].x, fmaf(d.y, w[j].y, fmaf(d.z, w[j].z, fmaf(d.w, w[j].w, acc[i][j]))));
         }
       }
 #pragma unroll
@@ -211,8 +264,15 @@ __global__ void __launch_bounds__(HT) heads_bwd_kernel(const TF* __restrict__ fe
       const int rows = min(NC, N - n0);
       for (int r = 0; r < rows; ++r) {
         const float f = to_f(fs[r * FP + kw]);
-#pragma unroll
-        for (int j = 0; j < 12; ++j) wacc[j] = fmaf(f, dls[r * DP + uh * 12 + j], wacc[j]);
+        const float4 d0 = *reinterpret_cast<const float4*>(dls + r * DP + uh * 12);
+        const float4 d1 = *reinterpret_cast<const float4*>(dls + r * DP + uh * 12 + 4);
+        const float4 d2 = *reinterpret_cast<const float4*>(dls + r * DP + uh * 12 + 8);
+        wacc[0] = fmaf(f, d0.x, wacc[0]); wacc[1] = fmaf(f, d0.y, wacc[1]);
+        wacc[2] = fmaf(f, d0.z, wacc[2]); wacc[3] = fmaf(f, d0.w, wacc[3]);
+        wacc[4] = fmaf(f, d1.x, wacc[4]); wacc[5] = fmaf(f, d1.y, wacc[5]);
+        wacc[6] = fmaf(f, d1.z, wacc[6]); wacc[7] = fmaf(f, d1.w, wacc[7]);
+        wacc[8] = fmaf(f, d2.x, wacc[8]); wacc[9] = fmaf(f, d2.y, wacc[9]);
+        wacc[10] = fmaf(f, d2.z, wacc[10]); wacc[11] = fmaf(f, d2.w, wacc[11]);
       }
     }
     if (blockIdx.x == 0 && threadIdx.x < U) {
@@ -236,7 +296,7 @@ __global__ void __launch_bounds__(HT) heads_bwd_kernel(const TF* __restrict__ fe
 }
 
 size_t fwd_smem(int esz) { return (size_t)KS * UP * 4 + (size_t)NC * (KS + 2) * esz; }
-size_t bwd_smem(int esz) { return (size_t)KS * UP * 4 + (size_t)NC * (UP + 1) * 4 + (size_t)NC * (KS + 2) * esz; }
+size_t bwd_smem(int esz) { return (size_t)KS * UP * 4 + (size_t)NC * (UP + 4) * 4 + (size_t)NC * (KS + 2) * esz; }
 
 }  // namespace
 
@@ -254,13 +314,14 @@ extern "C" int lg_dense_heads_fwd(const void* feat, const float* W0, const float
   cudaStream_t st = (cudaStream_t)stream;
   unsigned* counter = reinterpret_cast<unsigned*>(workspace);
   float* acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 256);
+  const int grid = F / KS < 2 * lg_num_sms() ? F / KS : 2 * lg_num_sms();   // two CTAs per SM: loads overlap FMAs
   if (dtype == LG_BF16) {
-    heads_fwd_kernel<bf16><<<F / KS, HT, fwd_smem(2), st>>>((const bf16*)feat, W0, b0, U0, W1, b1, U1, out0, out1, N, F,
+    heads_fwd_kernel<bf16><<<grid, HT, fwd_smem(2), st>>>((const bf16*)feat, W0, b0, U0, W1, b1, U1, out0, out1, N, F,
                                                            act, acc, counter);
   } else {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(heads_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
-    heads_fwd_kernel<float><<<F / KS, HT, fwd_smem(4), st>>>((const float*)feat, W0, b0, U0, W1, b1, U1, out0, out1, N,
+    heads_fwd_kernel<float><<<grid, HT, fwd_smem(4), st>>>((const float*)feat, W0, b0, U0, W1, b1, U1, out0, out1, N,
                                                             F, act, acc, counter);
   }
   LG_LAUNCH_CHECK();

@@ -40,12 +40,15 @@ __device__ __forceinline__ NormBwdCoef nb_coef(const NormBwdDev& nb, int n) {
   return c;
 }
 
-// Up to four 16-channel chunks (64 channels = 8 x 16 B) of one z row, kept in registers.
-struct NormBwdZ { uint4 v[8]; };
+// Up to NCH 16-channel chunks (NCH x 32 B) of one z row, kept in registers.
+template <int NCH>
+struct NormBwdZn { uint4 v[2 * NCH]; };
+typedef NormBwdZn<4> NormBwdZ;
 
-__device__ __forceinline__ void nb_load(NormBwdZ& b, const bf16* zrow, int nchunks, bool valid) {
+template <int NCH>
+__device__ __forceinline__ void nb_load(NormBwdZn<NCH>& b, const bf16* zrow, int nchunks, bool valid) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     if (valid && c < nchunks) {
       b.v[2 * c] = __ldg(reinterpret_cast<const uint4*>(zrow + 16 * c));
       b.v[2 * c + 1] = __ldg(reinterpret_cast<const uint4*>(zrow + 16 * c + 8));

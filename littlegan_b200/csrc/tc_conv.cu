@@ -233,6 +233,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (valid) coef = nb_coef(nb, n);
         nb_load(zc, zrow, p.NT >> 4, valid);
         if (p.NT > 64) nb_prefetch_l2(zrow + 64, (p.NT - 64) * 2, valid);
+        // the NEXT tile's z row towards L2 now: a whole tile period ahead of its use (the loads above miss
+        // to HBM only for the first tile of a CTA)
+        const int tn = t + gridDim.x;
+        if (tn < p.total_tiles) {
+          const TileCoord cn = decode_tile<OP, S>(p, tn);
+          const int n2 = cn.n0 + bn, i2 = cn.i0 + bh, j2 = cn.j0 + bw;
+          int64_t off2;
+          if (OP == OP_F) off2 = (((int64_t)n2 * p.Hs + i2) * p.Ws + j2) * p.Nch;
+          else off2 = (((int64_t)n2 * p.Hb + (S * i2 + cn.ph_y)) * p.Wb + (S * j2 + cn.ph_x)) * p.Nch;
+          nb_prefetch_l2(nb.z + off2 + cn.nt * p.NT, p.NT * 2, n2 < p.Nimg);
+        }
       }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();

@@ -101,7 +101,7 @@ constexpr int F_THREADS = 288;
 constexpr int F_STAGES = 2;
 
 template <int S, bool NB>
-__global__ void __launch_bounds__(F_THREADS)
+__global__ void __launch_bounds__(F_THREADS, 3)
 cin3_fprop_kernel(const C3Params p, const NormBwdDev nb) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -197,38 +197,44 @@ cin3_fprop_kernel(const C3Params p, const NormBwdDev nb) {
       const int64_t pos = (int64_t)n * p.Hs * p.Ws + (int64_t)r * 128 + row;
       bf16* orow = p.out + pos * p.B;
       NormBwdCoef coef = {0.f, 0.f, 0.f, 0.f};
-      NormBwdZ zc;
+      NormBwdZn<2> zc;                                           // 32 channels at a time (3 CTAs/SM: few registers)
       const bf16* zrow = nullptr;
       if constexpr (NB) {                                        // fused InstanceNorm-backward reduction (norm_bwd.cuh)
         zrow = nb.z + pos * p.B;
         coef = nb_coef(nb, n);
         nb_load(zc, zrow, p.B >> 4, true);
-        if (p.B > 64) nb_prefetch_l2(zrow + 64, (p.B - 64) * 2, true);
+        // the MMA of a tile is tiny here, so the z rows of this CTA's tile after next are sent towards L2
+        // now (the first tile also sends the next one); without it every tile waits an HBM round trip
+        for (int a = (t == (int)blockIdx.x ? 1 : 2); a <= 2; ++a) {
+          const int tn = t + a * gridDim.x;
+          if (tn < p.total_tiles) {
+            const int n2 = tn / p.tiles_per_img, r2 = tn - n2 * p.tiles_per_img;
+            nb_prefetch_l2(nb.z + ((int64_t)n2 * p.Hs * p.Ws + (int64_t)r2 * 128 + row) * p.B, p.B * 2, true);
+          }
+        }
       }
       tc::mbar_wait(&tfull[acc], aphase);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.B);
       float s1 = 0.f, s2 = 0.f;
       if constexpr (NB) {
-        for (int sc = 0; sc < p.B; sc += 64) {
-          NormBwdZ zn;
-          if (sc + 64 < p.B) nb_load(zn, zrow + sc + 64, (p.B - sc - 64) >> 4, true);
+        for (int sc = 0; sc < p.B; sc += 32) {
+          NormBwdZn<2> zn;
+          if (sc + 32 < p.B) nb_load(zn, zrow + sc + 32, (p.B - sc - 32) >> 4, true);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             const int cb = sc + 16 * c;
-            if (cb < p.B) {
-              float v[16];
-              tc::tmem_ld16(taddr + cb, v);
+            float v[16];
+            tc::tmem_ld16(taddr + cb, v);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] += sbias[cb + e];
-              uint32_t pk[8];
-              nb_chunk(v, zc.v[2 * c], zc.v[2 * c + 1], coef, nb.alpha, s1, s2, pk);
-              uint4* dst = reinterpret_cast<uint4*>(orow + cb);
-              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
+            for (int e = 0; e < 16; ++e) v[e] += sbias[cb + e];
+            uint32_t pk[8];
+            nb_chunk(v, zc.v[2 * c], zc.v[2 * c + 1], coef, nb.alpha, s1, s2, pk);
+            uint4* dst = reinterpret_cast<uint4*>(orow + cb);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          if (sc + 64 < p.B) zc = zn;
+          if (sc + 32 < p.B) zc = zn;
         }
       } else {
       for (int cb = 0; cb < p.B; cb += 16) {

@@ -193,6 +193,17 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         zbase = nb.z + (obase - p.out);
         if (valid) coef = nb_coef(nb, n);
         nb_load(zc, zbase, p.NT >> 4, valid);
+        // the NEXT tile's four z rows towards L2, a whole tile period ahead of their use
+        const int tnx = t + gridDim.x;
+        if (tnx < p.total_tiles) {
+          const int tw2 = tnx & ((1 << p.lg_tw) - 1);
+          const int th2 = (tnx >> p.lg_tw) & ((1 << p.lg_th) - 1);
+          const int n2 = (tnx >> (p.lg_tw + p.lg_th)) * p.BN + bn;
+          const int i2 = th2 * p.BH + bh, j2 = tw2 * p.BW + bw;
+          const bf16* z2 = nb.z + (((int64_t)n2 * p.Hb + 2 * i2) * p.Wb + 2 * j2) * p.Nch;
+          nb_prefetch_l2(z2, 2 * p.Nch * 2, n2 < p.Nimg);                               // phases (0,0), (0,1): adjacent
+          nb_prefetch_l2(z2 + (int64_t)p.Wb * p.Nch, 2 * p.Nch * 2, n2 < p.Nimg);      // phases (1,0), (1,1)
+        }
       }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::fence_after_sync();

@@ -71,7 +71,9 @@ def norm_bwd_desc(z, stats, gamma, beta, red, eps, alpha):
     _cuda(z, stats, gamma, beta, red)
     if z.dtype != torch.bfloat16:
         raise _lib.LittleGANError("the fused norm-backward epilogue needs bf16 activations")
-    return _lib.NormBwd(_p(z), _p(stats), _p(gamma), _p(beta), _p(red), eps, alpha)
+    d = _lib.NormBwd(_p(z), _p(stats), _p(gamma), _p(beta), _p(red), eps, alpha)
+    d._keep = (z, stats, gamma, beta, red)      # the descriptor holds raw pointers: keep the tensors alive
+    return d
 
 
 def _nb(desc):

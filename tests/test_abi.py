@@ -32,7 +32,7 @@ def test_version_and_error_channel():
     assert lib.lg_abi_version() == 1
     assert isinstance(lib.lg_last_error(), bytes)
     # argument validation happens before any CUDA call, so it works without a GPU
-    r = lib.lg_conv2d_fprop(None, None, None, None, None, None, 0, 0, 0, 0, 0, 3, 0, 0, None)
+    r = lib.lg_conv2d_fprop(None, None, None, None, None, None, 0, 0, 0, 0, 0, 3, 0, 0, None, None)
     assert r == -1 and b"invalid geometry" in lib.lg_last_error()
     assert lib.lg_gemm(None, None, None, None, 1, 1, 1, 0, 0, 0, 0, 0, None) == -1
     assert lib.lg_pack_conv_weights(None, None, 64, 128, None) == 2 * 25 * 64 * 128 * 2
