@@ -99,6 +99,19 @@ int lg_conv2d_wgrad(const void* big, const void* small, float* dW, int N, int Hb
 int lg_conv2d_wgrad_padded(const void* big, const void* small, float* dW, int N, int Hb, int Wb,
                            int A_big, int A, int B, int stride, void* stream);
 
+/* fprop on the row-streaming tensor-core kernel (csrc/tc_rowconv.cu) for maps that are 128 pixels wide with
+ * few channels: every input row is fetched once into a shared-memory ring and all 25 taps read it in place.
+ * `big` is [N,Hb,Wb,A_big] LG_BF16, A_big = 8 for A <= 8 (RGB images zero-padded to 16-byte pixels, see
+ * lg_pad_channels) or A_big = A = 32.  wpack: the bf16 weight operand made by lg_pack_rowconv_weights from
+ * W[5,5,A,B] (call it with W or wpack NULL to get the size in bytes; refresh after every weight update).
+ * Same contract as lg_conv2d_fprop otherwise (bias, stats, norm_bwd).
+ * lg_conv2d_fprop_rows_supported: 1 if the geometry is covered. */
+int lg_conv2d_fprop_rows_supported(int N, int Hb, int Wb, int A_big, int A, int B, int stride);
+int lg_pack_rowconv_weights(const float* W, void* wpack, int A_big, int A, int B, int stride, void* stream);
+int lg_conv2d_fprop_rows(const void* big, int A_big, const void* wpack, const float* bias, void* small_out,
+                         double* stats, int N, int Hb, int Wb, int A, int B, int stride,
+                         const lg_norm_bwd_t* norm_bwd, void* stream);
+
 /* dst[row, 0:Cpad] = (src[row, 0:C], 0, ..., 0): channel padding of an NHWC tensor (rows = N*H*W). */
 int lg_pad_channels(const void* src, void* dst, int64_t rows, int C, int Cpad, int dtype,
                     void* stream);

@@ -24,6 +24,9 @@ SIGNATURES = {
     "lg_conv2d_tc_supported": (_i, [_i] * 7),
     "lg_conv2d_norm_bwd_supported": (_i, [_i] * 7),
     "lg_conv2d_fprop": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lg_conv2d_fprop_rows_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "lg_pack_rowconv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "lg_conv2d_fprop_rows": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lg_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lg_conv2d_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_conv2d_wgrad_padded": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -71,6 +71,31 @@ extern "C" int lg_conv2d_fprop(const void* big, const float* W, const void* wpac
   return LG_OK;
 }
 
+extern "C" int lg_conv2d_fprop_rows_supported(int N, int Hb, int Wb, int A_big, int A, int B, int stride) {
+  return lg_tc_rowconv_supported(N, Hb, Wb, A, A_big, B, stride);
+}
+
+extern "C" int lg_pack_rowconv_weights(const float* W, void* wpack, int A_big, int A, int B, int stride,
+                                       void* stream) {
+  int e = lg_tc_rowconv_pack(W, wpack, A, A_big, B, stride, (cudaStream_t)stream);
+  if (e < 0 || !W || !wpack) return e;
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_conv2d_fprop_rows(const void* big, int A_big, const void* wpack, const float* bias, void* small_out,
+                                    double* stats, int N, int Hb, int Wb, int A, int B, int stride,
+                                    const lg_norm_bwd_t* norm_bwd, void* stream) {
+  if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, LG_BF16)) return e;
+  LG_REQUIRE(big && small_out && wpack, "NULL tensor");
+  LG_REQUIRE(!(norm_bwd && stats), "norm_bwd excludes stats");
+  int e = lg_tc_rowconv_fprop(big, wpack, bias, small_out, stats, N, Hb, Wb, A, A_big, B, stride, norm_bwd,
+                              (cudaStream_t)stream);
+  if (e) return e;
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
 extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wpack, const float* bias,
                                void* big_out, double* stats, int N, int Hb, int Wb, int A, int B, int stride,
                                int act, int dtype, int use_tc, const lg_norm_bwd_t* norm_bwd, void* stream) {

@@ -34,4 +34,8 @@ int lg_tc_cin3_fprop(const void* img, const float* W, const float* bias, void* o
                      int Wb, int B, int s, const lg_norm_bwd_t* nb, cudaStream_t st);
 int lg_tc_cin3_wgrad(const void* img, const void* small, float* dW, int N, int Hb, int Wb, int B, int s,
                      cudaStream_t st);
+int lg_tc_rowconv_supported(int N, int Hb, int Wb, int A, int Cpad, int B, int s);
+int lg_tc_rowconv_pack(const float* W, void* wpack, int A, int Cpad, int B, int s, cudaStream_t st);
+int lg_tc_rowconv_fprop(const void* big, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
+                        int Wb, int A, int Cpad, int B, int s, const lg_norm_bwd_t* nb, cudaStream_t st);
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N);

@@ -91,6 +91,33 @@ def conv2d_fprop(big, W, bias, out, stats, stride, wpack=None, use_tc=False, nor
     return out
 
 
+def fprop_rows_supported(N, Hb, Wb, A_big, A, B, stride):
+    return bool(_lib.load().lg_conv2d_fprop_rows_supported(N, Hb, Wb, A_big, A, B, stride))
+
+
+def pack_rowconv_weights(W, A_big, stride, wpack=None):
+    """bf16 weight operand of the row-streaming kernel for W [5,5,A,B] (refresh after every weight update)."""
+    A, B = W.shape[2], W.shape[3]
+    lib = _lib.load()
+    if wpack is None:
+        nbytes = int(_lib.check(lib.lg_pack_rowconv_weights(None, None, A_big, A, B, stride, None)))
+        wpack = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    _cuda(W, wpack)
+    check(lib.lg_pack_rowconv_weights(_p(W), _p(wpack), A_big, A, B, stride, _st()), "lg_pack_rowconv_weights")
+    return wpack
+
+
+def conv2d_fprop_rows(big, wpack, bias, out, stats, stride, A, norm_bwd=None):
+    """Row-streaming tcgen05 fprop: big [N,Hb,128,A_big] bf16 (A_big = 8 holds a zero-padded RGB image),
+    wpack from pack_rowconv_weights(W [5,5,A,B])."""
+    _cuda(big, wpack, bias, out, stats)
+    N, Hb, Wb, A_big = big.shape
+    B = out.shape[3]
+    check(_lib.load().lg_conv2d_fprop_rows(_p(big), A_big, _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
+                                           stride, _nb(norm_bwd), _st()), "lg_conv2d_fprop_rows")
+    return out
+
+
 def conv2d_dgrad(small, W, bias, out, stats, stride, act=ACT_NONE, wpack=None, use_tc=False, norm_bwd=None):
     """big = conv_transpose(small): small [N,Hs,Ws,B], W [5,5,A,B] fp32, out [N,s*Hs,s*Ws,A]."""
     _cuda(small, W, bias, out, stats, wpack)

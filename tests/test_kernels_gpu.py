@@ -516,3 +516,52 @@ def test_tc_wgrad(geom):
     assert rel_err(dW, ref) < 1e-4          # bf16 operands are exact inputs; accumulation is fp32
     K.conv2d_wgrad(big.cuda(), small.cuda(), dW, s, use_tc=True)
     assert rel_err(dW, 2 * ref) < 1e-4
+
+
+# (N, Hb, A_big, A, B, stride): the three layers served by the row-streaming kernel (csrc/tc_rowconv.cu)
+ROW_CASES = [
+    (3, 128, 8, 3, 32, 1),       # final conv input-gradient (M = 128 rows)
+    (3, 128, 8, 3, 64, 2),       # encoder conv1 forward (64-pixel rows)
+    (2, 128, 32, 32, 64, 2),     # decoder conv4 input-gradient
+    (5, 32, 8, 3, 64, 2),        # short maps: several strips per CTA, ring wrap
+]
+
+
+@pytest.mark.parametrize("with_nb", [False, True])
+@pytest.mark.parametrize("case", ROW_CASES)
+def test_rowconv_fprop(case, with_nb):
+    """Row-streaming shift-GEMM fprop == the oracle's SAME convolution (bias + statistics, or the fused
+    norm-backward epilogue)."""
+    from littlegan_b200 import kernels as K
+    N, Hb, A_big, A, B, s = case
+    Wb = 128
+    assert K.fprop_rows_supported(N, Hb, Wb, A_big, A, B, s)
+    x = _rand((N, Hb, Wb, A), 11, torch.bfloat16)
+    xp = torch.zeros(N, Hb, Wb, A_big, dtype=torch.bfloat16)
+    xp[..., :A] = x
+    W = _rand((5, 5, A, B), 12, torch.bfloat16, 0.05).float()
+    oshape = (N, Hb // s, Wb // s, B)
+    out = torch.zeros(oshape, dtype=torch.bfloat16, device="cuda")
+    if not with_nb:
+        b = _rand((B,), 13, torch.float32)
+        ref = O.conv2d_same(x.double(), W.double(), b.double(), s)
+        stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+        K.conv2d_fprop_rows(xp.cuda(), K.pack_rowconv_weights(W.cuda(), A_big, s), b.cuda(), out, stats, s, A)
+        torch.cuda.synchronize()
+        assert rel_err(out, ref) < 2e-2
+        ref_stats = torch.stack([ref.reshape(N, -1).sum(1), (ref.reshape(N, -1) ** 2).sum(1)], 1)
+        assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
+        return
+    g_ref = O.conv2d_same(x.double(), W.double(), torch.zeros(B, dtype=torch.float64), s)
+    z = (_rand(oshape, 14, torch.float32, 1.5) + 0.3).to(torch.bfloat16)
+    alpha = 0.3
+    dy_ref, red_ref = _norm_bwd_reference(g_ref, z, 0.9, 0.15, alpha)
+    zc = z.cuda()
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.rowstats(zc, stats, 1.0)
+    red = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    nb = K.norm_bwd_desc(zc, stats, torch.tensor([0.9]).cuda(), torch.tensor([0.15]).cuda(), red, 1e-3, alpha)
+    K.conv2d_fprop_rows(xp.cuda(), K.pack_rowconv_weights(W.cuda(), A_big, s), None, out, None, s, A, norm_bwd=nb)
+    torch.cuda.synchronize()
+    assert rel_err(out, dy_ref) < 1e-2
+    assert float(((red.cpu() - red_ref).abs() / red_ref.abs().max()).max()) < 1e-4
