@@ -90,6 +90,14 @@ int lg_conv2d_dgrad(const void* small, const float* W, const void* wpack, const 
                     int stride, int act, int dtype, int use_tc, const lg_norm_bwd_t* norm_bwd,
                     void* stream);
 
+/* dgrad with an RGB result (A = 3, stride 1, 128-pixel-wide maps: the generator's final Conv2DTranspose,
+ * model.py:86) on the row-streaming tensor-core kernel (csrc/tc_rowdeconv.cu).  Same arithmetic as
+ * lg_conv2d_dgrad (LG_BF16); big_out_pad8, if not NULL, also receives the image with 8-channel zero-padded
+ * pixels [N,Hb,Wb,8] - the layout lg_conv2d_fprop_rows fetches. */
+int lg_conv2d_dgrad_rgb_supported(int N, int Hb, int Wb, int A, int B, int stride);
+int lg_conv2d_dgrad_rgb(const void* small, const float* W, const float* bias, void* big_out, void* big_out_pad8,
+                        double* stats, int N, int Hb, int Wb, int A, int B, int stride, int act, void* stream);
+
 /* wgrad.  dW [5,5,A,B] fp32 is ACCUMULATED into (caller zeroes). */
 int lg_conv2d_wgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb,
                     int A, int B, int stride, int dtype, int use_tc, void* stream);

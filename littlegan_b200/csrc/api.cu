@@ -106,7 +106,10 @@ extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wp
   if (use_tc) {
     LG_REQUIRE(dtype == LG_BF16 && wpack, "tcgen05 path needs LG_BF16 activations and packed weights");
     int e;
-    if (W && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, stride)) {    // RGB layers: GEMM + col2im
+    if (W && lg_tc_rowdeconv_supported(N, Hb, Wb, A, B, stride)) {       // final RGB layer: row streaming
+      LG_REQUIRE(!norm_bwd, "no fused norm-backward epilogue on the RGB transposed-conv kernels");
+      e = lg_tc_rowdeconv(small, W, bias, big_out, nullptr, stats, N, Hb, Wb, A, B, stride, act, st);
+    } else if (W && lg_tc_deconv_small_supported(N, Hb, Wb, A, B, stride)) {    // RGB layers: GEMM + col2im
       LG_REQUIRE(!norm_bwd, "no fused norm-backward epilogue on the RGB transposed-conv kernel");
       e = lg_tc_deconv_small(small, W, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, st);
     } else if (lg_tc_dgrad4_supported(N, Hb, Wb, A, B, stride))          // <= 128 channels: 4 phases per pass
@@ -119,6 +122,23 @@ extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wp
     LG_REQUIRE(!norm_bwd, "the fused norm-backward epilogue exists on the tensor-core path only");
     lg_simt_dgrad(small, W, bias, big_out, stats, N, Hb, Wb, A, B, stride, act, dtype, st);
   }
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_conv2d_dgrad_rgb_supported(int N, int Hb, int Wb, int A, int B, int stride) {
+  return lg_tc_rowdeconv_supported(N, Hb, Wb, A, B, stride);
+}
+
+extern "C" int lg_conv2d_dgrad_rgb(const void* small, const float* W, const float* bias, void* big_out,
+                                   void* big_out_pad8, double* stats, int N, int Hb, int Wb, int A, int B, int stride,
+                                   int act, void* stream) {
+  if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, LG_BF16)) return e;
+  LG_REQUIRE(small && big_out && W, "NULL tensor");
+  LG_REQUIRE(act == LG_ACT_NONE || act == LG_ACT_TANH, "unsupported activation");
+  int e = lg_tc_rowdeconv(small, W, bias, big_out, big_out_pad8, stats, N, Hb, Wb, A, B, stride, act,
+                          (cudaStream_t)stream);
+  if (e) return e;
   LG_LAUNCH_CHECK();
   return LG_OK;
 }

@@ -418,6 +418,18 @@ __global__ void pad_channels_kernel(const T* __restrict__ src, T* __restrict__ d
   }
 }
 
+// RGB bf16 image -> 8-channel pixels (16 B, what the row-streaming conv kernel fetches by TMA): one pixel per
+// thread, three 2-byte loads (coalesced across the warp) and one 16-byte store.
+__global__ void __launch_bounds__(256) pad3to8_kernel(const uint16_t* __restrict__ src, uint4* __restrict__ dst,
+                                                      int64_t rows) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    const uint16_t* s = src + 3 * r;
+    const uint32_t c0 = __ldg(s), c1 = __ldg(s + 1), c2 = __ldg(s + 2);
+    dst[r] = make_uint4(c0 | (c1 << 16), c2, 0u, 0u);
+  }
+}
+
 // W[25][A][B] fp32 -> Wt[25][Ap][Bp] bf16 (b contiguous), Wf[25][Bp][Ap] bf16 (a contiguous).
 // One 64x64 (a, b) tile of one tap per CTA: W is read and Wt written along b, the tile is transposed in
 // shared memory and Wf written along a, so all three streams are coalesced (the weights are re-packed
@@ -684,7 +696,11 @@ extern "C" int lg_pad_channels(const void* src, void* dst, int64_t rows, int C, 
   const int64_t total = rows * Cpad;
   int64_t need = (total + 255) / 256, cap = (int64_t)lg_num_sms() * 16;
   int gsz = (int)(need < cap ? need : cap);
-  if (dtype == LG_BF16)
+  if (dtype == LG_BF16 && C == 3 && Cpad == 8) {
+    need = (rows + 255) / 256;
+    gsz = (int)(need < cap ? need : cap);
+    pad3to8_kernel<<<gsz, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, (uint4*)dst, rows);
+  } else if (dtype == LG_BF16)
     pad_channels_kernel<bf16><<<gsz, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows, C, Cpad);
   else
     pad_channels_kernel<float><<<gsz, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, rows, C, Cpad);

@@ -38,4 +38,7 @@ int lg_tc_rowconv_supported(int N, int Hb, int Wb, int A, int Cpad, int B, int s
 int lg_tc_rowconv_pack(const float* W, void* wpack, int A, int Cpad, int B, int s, cudaStream_t st);
 int lg_tc_rowconv_fprop(const void* big, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
                         int Wb, int A, int Cpad, int B, int s, const lg_norm_bwd_t* nb, cudaStream_t st);
+int lg_tc_rowdeconv_supported(int N, int Hb, int Wb, int A, int B, int s);
+int lg_tc_rowdeconv(const void* small, const float* W, const float* bias, void* out3, void* out8, double* stats,
+                    int N, int Hb, int Wb, int A, int B, int s, int act, cudaStream_t st);
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N);

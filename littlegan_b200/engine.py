@@ -47,6 +47,19 @@ class Runtime:
             r = self._tc_cache[key] = K.norm_bwd_supported(op, N, Hb, Wb, A, B, s)
         return r
 
+    def rows_ok(self, N, Hb, Wb, A, B, s):
+        """Does the row-streaming fprop kernel (csrc/tc_rowconv.cu) take this geometry?  Returns the channel
+        count its input must be stored with (8 for RGB maps, A otherwise) or 0."""
+        if not self.want_tc:
+            return 0
+        key = ("rows", N, Hb, Wb, A, B, s)
+        r = self._tc_cache.get(key)
+        if r is None:
+            A_big = 8 if A <= 8 else A
+            r = A_big if (K.tc_available() and K.fprop_rows_supported(N, Hb, Wb, A_big, A, B, s)) else 0
+            self._tc_cache[key] = r
+        return r
+
     def heads_workspace(self, N):
         """Scratch of the fused discriminator-heads forward (self-cleaning, allocated once per size)."""
         if self._heads_ws is None:
@@ -74,6 +87,29 @@ def _padded_for_tc(rt, x, op, B, s):
     return K.pad_channels(x, rt.empty(N, Hb, Wb, 16))
 
 
+def _fprop(rt, conv, x, bias, out, stats, s, nb=None, xrows=None):
+    """Conv2D forward / Conv2DTranspose input-gradient of `conv` on the best kernel: the row-streaming kernel
+    for the 128-pixel-wide maps with <= 32 channels (RGB maps through an 8-channel padded copy, `xrows` if the
+    caller already has one), else the generic tensor-core / SIMT path.  Returns the padded copy it used."""
+    N, Hb, Wb, A = x.shape
+    B = out.shape[3]
+    A_big = rt.rows_ok(N, Hb, Wb, A, B, s) if conv.wpack_rows is not None else 0
+    if A_big:
+        if A_big != A and xrows is None:
+            xrows = K.pad_channels(x, rt.empty(N, Hb, Wb, A_big))
+        K.conv2d_fprop_rows(xrows if A_big != A else x, conv.wpack_rows, bias, out, stats, s, A, norm_bwd=nb)
+        return xrows
+    K.conv2d_fprop(x, conv.kernel, bias, out, stats, s, conv.wpack, rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, s),
+                   norm_bwd=nb)
+    return None
+
+
+def _fprop_fuses_norm_bwd(rt, conv, N, Hb, Wb, A, B, s):
+    if conv.wpack_rows is not None and rt.rows_ok(N, Hb, Wb, A, B, s):
+        return True
+    return rt.fuse_norm_bwd(K.OP_FPROP, N, Hb, Wb, A, B, s)
+
+
 def _grad(p):
     """Gradient slot of a parameter (a view into the trainer's flat gradient arena)."""
     g = getattr(p, "lg_grad", None)
@@ -91,6 +127,10 @@ def refresh_packs(rt, conv_layers):
             A, B = layer.kernel.shape[2], layer.kernel.shape[3]
             layer.wpack = torch.empty(K.pack_conv_weights_bytes(A, B), dtype=torch.uint8, device=rt.device)
         K.pack_conv_weights(layer.kernel, layer.wpack)
+        A, B = layer.kernel.shape[2], layer.kernel.shape[3]
+        A_big = 8 if A <= 8 else A
+        if K.fprop_rows_supported(1, 128, 128, A_big, A, B, layer.strides):
+            layer.wpack_rows = K.pack_rowconv_weights(layer.kernel, A_big, layer.strides, layer.wpack_rows)
 
 
 # --------------------------------------------------------------------------------------------
@@ -109,8 +149,7 @@ def encoder_forward(rt, enc, x):
         if xpad is not None:
             K.conv2d_fprop(xpad, conv.kernel, conv.bias, z, stats[i], 2, conv.wpack, True)
         else:
-            tc = rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, 2)
-            K.conv2d_fprop(x, conv.kernel, conv.bias, z, stats[i], 2, conv.wpack, tc)
+            _fprop(rt, conv, x, conv.bias, z, stats[i], 2)
         a = rt.empty(N, Hb // 2, Wb // 2, B)
         K.instnorm_act_fwd(z, stats[i], norm.gamma, norm.beta, None, a, norm.epsilon, 1.0, rt.alpha)
         ctx.append((x, z, stats[i], xpad))
@@ -211,13 +250,12 @@ def decoder_backward(rt, dec, ctx, g, wgrad, red=None, dy_ready=False):
         g = torch.empty_like(x)
         nb = None
         dy_ready = False
-        if i > 0 and rt.fuse_norm_bwd(K.OP_FPROP, N, Hb, Wb, A, B, 2):
+        if i > 0 and _fprop_fuses_norm_bwd(rt, conv, N, Hb, Wb, A, B, 2):
             _, zp, sp = ctx[i - 1]
             nb = K.norm_bwd_desc(zp, sp, dec.norms[i - 1].gamma, dec.norms[i - 1].beta, red[i - 1],
                                  dec.norms[i - 1].epsilon, rt.alpha)
             dy_ready = True
-        K.conv2d_fprop(dz, conv.kernel, None, g, None, 2, conv.wpack, rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, B, 2),
-                       norm_bwd=nb)
+        _fprop(rt, conv, dz, None, g, None, 2, nb)
     return g
 
 
@@ -250,8 +288,7 @@ def final_conv_backward(rt, conv, x, dpre, wgrad, nb=None):
     if dpad is not None:
         K.conv2d_fprop(dpad, conv.kernel, None, g, None, 1, conv.wpack, True, norm_bwd=nb)
     else:
-        K.conv2d_fprop(dpre, conv.kernel, None, g, None, 1, conv.wpack, rt.use_tc(K.OP_FPROP, N, H, W, A, B, 1),
-                       norm_bwd=nb)
+        _fprop(rt, conv, dpre, None, g, None, 1, nb)
     return g
 
 
@@ -262,7 +299,7 @@ def generator_tail_backward(rt, dec, conv, dctx, x4, dpre, wgrad):
     A = conv.filters
     red, nb = None, None
     Ain = 16 if (_would_pad(rt, N, H, W, A, B)) else A
-    if rt.fuse_norm_bwd(K.OP_FPROP, N, H, W, Ain, B, 1):
+    if _fprop_fuses_norm_bwd(rt, conv, N, H, W, A, B, 1) or rt.fuse_norm_bwd(K.OP_FPROP, N, H, W, Ain, B, 1):
         red = rt.zeros(4, N, 2)
         _, z3, s3 = dctx[3]
         nb = K.norm_bwd_desc(z3, s3, dec.norms[3].gamma, dec.norms[3].beta, red[3], dec.norms[3].epsilon, rt.alpha)

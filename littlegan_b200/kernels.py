@@ -128,6 +128,20 @@ def conv2d_dgrad(small, W, bias, out, stats, stride, act=ACT_NONE, wpack=None, u
     return out
 
 
+def dgrad_rgb_supported(N, Hb, Wb, A, B, stride):
+    return bool(_lib.load().lg_conv2d_dgrad_rgb_supported(N, Hb, Wb, A, B, stride))
+
+
+def conv2d_dgrad_rgb(small, W, bias, out, out_pad8, stats, stride, act=ACT_NONE):
+    """RGB transposed conv on the row-streaming kernel; out_pad8 (or None): [N,H,W,8] zero-padded copy."""
+    _cuda(small, W, bias, out, out_pad8, stats)
+    N, Hb, Wb, A = out.shape
+    B = small.shape[3]
+    check(_lib.load().lg_conv2d_dgrad_rgb(_p(small), _p(W), _p(bias), _p(out), _p(out_pad8), _p(stats), N, Hb, Wb,
+                                          A, B, stride, act, _st()), "lg_conv2d_dgrad_rgb")
+    return out
+
+
 def conv2d_wgrad(big, small, dW, stride, use_tc=False):
     """dW[5,5,A,B] += correlation(big, small)."""
     _cuda(big, small, dW)

@@ -47,6 +47,7 @@ class Conv2D:
         self.kernel = _glorot((k, k, in_channels, filters), k * k * in_channels, k * k * filters)
         self.bias = torch.zeros(filters, dtype=torch.float32, device=_device())
         self.wpack = None
+        self.wpack_rows = None      # weight operand of the row-streaming kernel (engine.refresh_packs)
 
     @property
     def weights(self):
@@ -62,6 +63,7 @@ class Conv2DTranspose:
         self.kernel = _glorot((k, k, filters, in_channels), k * k * filters, k * k * in_channels)
         self.bias = torch.zeros(filters, dtype=torch.float32, device=_device())
         self.wpack = None
+        self.wpack_rows = None      # weight operand of the row-streaming kernel (engine.refresh_packs)
 
     @property
     def weights(self):

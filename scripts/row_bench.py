@@ -49,3 +49,17 @@ for name, A_big, A, B, s in [("final-dgrad", 8, 3, 32, 1), ("enc1-fwd", 8, 3, 64
         extra = out.numel() * 2 / 1e9 if "nb" in label else 0.0
         print("%-12s %-8s N=%3d %8.1f us %7.1f TFLOP/s %7.0f GB/s" % (name, label, N, us, flops / us / 1e6,
                                                                     (gb + extra) / us * 1e6), flush=True)
+
+# final Conv2DTranspose(3) forward: row-streaming kernel vs GEMM + col2im
+N, Hb = NB, 128
+x = torch.randn(N, Hb, Hb, 32, device="cuda").to(torch.bfloat16)
+W = torch.randn(5, 5, 3, 32, device="cuda") * 0.05
+wp = torch.empty(K.pack_conv_weights_bytes(3, 32), dtype=torch.uint8, device="cuda")
+K.pack_conv_weights(W, wp)
+out = torch.empty(N, Hb, Hb, 3, device="cuda", dtype=torch.bfloat16)
+out8 = torch.empty(N, Hb, Hb, 8, device="cuda", dtype=torch.bfloat16)
+bias = torch.zeros(3, device="cuda")
+for label, fn in [("rows", lambda: K.conv2d_dgrad_rgb(x, W, bias, out, None, None, 1, K.ACT_TANH)),
+                  ("rows+pad8", lambda: K.conv2d_dgrad_rgb(x, W, bias, out, out8, None, 1, K.ACT_TANH))]:
+    us = timeit(fn)
+    print("%-12s %-8s N=%3d %8.1f us %7.0f GB/s" % ("final-fwd", label, N, us, (x.numel() + out.numel()) * 2 / 1e3 / us), flush=True)

@@ -565,3 +565,32 @@ def test_rowconv_fprop(case, with_nb):
     torch.cuda.synchronize()
     assert rel_err(out, dy_ref) < 1e-2
     assert float(((red.cpu() - red_ref).abs() / red_ref.abs().max()).max()) < 1e-4
+
+
+@pytest.mark.parametrize("N,act", [(3, 1), (5, 0)])
+def test_rowdeconv_rgb(N, act):
+    """Final Conv2DTranspose(3, s1) on the row-streaming kernel, with the 8-channel padded second output."""
+    from littlegan_b200 import kernels as K
+    Hb, Wb, A, B, s = 128, 128, 3, 32, 1
+    assert K.dgrad_rgb_supported(N, Hb, Wb, A, B, s)
+    x = _rand((N, Hb, Wb, B), 4, torch.bfloat16)
+    W = _rand((5, 5, A, B), 5, torch.bfloat16, 0.05).float()
+    b = _rand((A,), 6, torch.float32)
+    pre = O.conv2d_transpose_same(x.double(), W.double(), b.double(), s)
+    ref = torch.tanh(pre) if act else pre
+    out = torch.zeros(N, Hb, Wb, A, dtype=torch.bfloat16, device="cuda")
+    out8 = torch.full((N, Hb, Wb, 8), 7.0, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.conv2d_dgrad_rgb(x.cuda(), W.cuda(), b.cuda(), out, out8, stats, s, act)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2
+    assert torch.equal(out8[..., :3], out) and float(out8[..., 3:].abs().max()) == 0.0
+    ref_stats = torch.stack([pre.reshape(N, -1).sum(1), (pre.reshape(N, -1) ** 2).sum(1)], 1)
+    assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
+
+
+def test_pad_channels_rgb8():
+    from littlegan_b200 import kernels as K
+    x = _rand((3, 16, 24, 3), 9, torch.bfloat16).cuda()
+    xp = K.pad_channels(x, torch.full((3, 16, 24, 8), 5.0, dtype=torch.bfloat16, device="cuda"))
+    assert torch.equal(xp[..., :3], x) and float(xp[..., 3:].abs().max()) == 0.0
