@@ -20,6 +20,7 @@
 // their own TMA ring (swizzled, conflict free), bf16 store.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -32,14 +33,14 @@ namespace {
 constexpr int RC_THREADS = 352;          // warps 0-7 epilogue (two groups, alternate rows), 8 row producer, 9 MMA issuer, 10 z producer
 constexpr int W_PRODUCER = 8, W_MMA = 9, W_ZPROD = 10;
 constexpr int RC_ACC = 4;                // TMEM accumulator stages
-constexpr int RC_ZSLOTS = 4;
+constexpr int RC_ZSLOTS = 4;              // upper bound; p.zslots (a power of two) are used
 
 struct RcParams {
   int Nimg, Hb, Wb, Hs, Ws, B, A_real;
   int R, strips_per_img, total_strips;   // R output rows per strip
   int ring, row_bytes, plane_bytes;      // ring slots; one input row = S*CH planes of Wp x 16 B
   int ktot;                              // K extent of the weight operand: 5 * NMK * 16
-  int w_bytes, z_slot_bytes;
+  int w_bytes, z_slot_bytes, zslots;     // one z slot = the 128 pixels of a TMEM stage
   const uint4* wpack;                    // bf16 weight operand in its shared-memory layout (rc_pack_kernel)
   const float* bias;
   bf16* out;                             // [N,Hs,Ws,B]
@@ -63,8 +64,9 @@ __host__ __device__ constexpr uint32_t a_lo_const(int p) {
     const int kx = p >> 1, cp = p & 1;
     const int xpar = (kx & 1) ? 0 : 1;
     const int d = (kx + 1) >> 1;                                               // 0,1,1,2,2
-    const uint32_t off = (uint32_t)((xpar * CH + 2 * cp) * PLANEB + d * 16);
-    return (off >> 4) | (((uint32_t)PLANEB >> 4) << 16);                       // K halves = two chunk planes
+    // 32-channel pixels are 64-byte rows of a SWIZZLE_64B K-major operand: x-parity plane, pixel shift, K step
+    const uint32_t off = (uint32_t)(xpar * CH * PLANEB + d * 64 + cp * 32);
+    return (off >> 4) | (1u << 16);                                            // LBO unused
   }
 }
 
@@ -106,7 +108,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sZ = smem;                                             // RC_ZSLOTS x z_slot_bytes (swizzled: 1024-aligned)
-  uint8_t* sW = sZ + (NB ? RC_ZSLOTS * p.z_slot_bytes : 0);       // B rows x ktot, no-swizzle K-major
+  uint8_t* sW = sZ + (NB ? p.zslots * p.z_slot_bytes : 0);       // B rows x ktot, no-swizzle K-major
   uint8_t* sRing = sW + ((p.w_bytes + 1023) & ~1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + (size_t)p.ring * p.row_bytes);
   uint64_t* full = bars;                     // [ring]   TMA -> MMA
@@ -123,6 +125,10 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   constexpr int PAD = (S == 2) ? 1 : 2;
   constexpr int PLANEB = (128 / S + 8) * 16;     // one plane: (Ws + 8) pixels x 16 B
   constexpr int ROWB = S * CH * PLANEB;          // one input row in the ring
+  // Output rows per TMEM stage: an M = 64 accumulator occupies lanes 0-15 of every 32-lane quadrant, or lanes
+  // 16-31 when the TMEM address carries a lane offset of 16 - two 64-pixel rows share one stage, so the
+  // epilogue's 32-lane tcgen05.ld returns 128 useful pixels exactly as in the M = 128 case.
+  constexpr int RPS = (MM == 64) ? 2 : 1;
   const uint32_t tmem_cols = RC_ACC * p.B <= 128 ? 128 : 256;
 
   // weights: already bf16 in the canonical no-swizzle K-major operand layout (rc_pack_kernel)
@@ -134,7 +140,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     if (NB) tc::tma_prefetch_desc(&tmZ);
     for (int i = 0; i < p.ring; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < RC_ACC; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
-    for (int i = 0; i < RC_ZSLOTS; ++i) { tc::mbar_init(&zfull[i], 1); tc::mbar_init(&zempty[i], 4); }
+    for (int i = 0; i < p.zslots; ++i) { tc::mbar_init(&zfull[i], 1); tc::mbar_init(&zempty[i], 4); }
     tc::fence_barrier_init();
   }
   if (warp == W_MMA) tc::tmem_alloc(tmem_slot, tmem_cols);
@@ -169,16 +175,17 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       }
     }
   } else if (warp == W_ZPROD) {
-    // ------------------------------------------------------------ z-row producer (norm-backward epilogue)
+    // ------------------------------------------------------------ z producer (norm-backward epilogue):
+    // the 128 pixels (RPS consecutive rows) of every TMEM stage
     if (NB && tc::elect_one()) {
       int zs = 0; uint32_t zphase = 0;
       for (int t = blockIdx.x; t < p.total_strips; t += gridDim.x) {
         const int n = t / p.strips_per_img, i0 = (t - n * p.strips_per_img) * p.R;
-        for (int i = i0; i < i0 + p.R; ++i) {
+        for (int i = i0; i < i0 + p.R; i += RPS) {
           tc::mbar_wait(&zempty[zs], zphase ^ 1);
           tc::mbar_expect_tx(&zfull[zs], (uint32_t)p.z_slot_bytes);
           tc::tma_load_2d(sZ + (size_t)zs * p.z_slot_bytes, &tmZ, &zfull[zs], 0, (n * p.Hs + i) * p.Ws);
-          if (++zs == RC_ZSLOTS) { zs = 0; zphase ^= 1; }
+          if (++zs == p.zslots) { zs = 0; zphase ^= 1; }
         }
       }
     }
@@ -191,7 +198,8 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       const uint32_t ring_lo = tc::smem_u32(sRing) >> 4;
       const uint32_t full_addr = tc::smem_u32(full), empty_addr = tc::smem_u32(empty);
       const uint32_t tfull_addr = tc::smem_u32(tfull), tempty_addr = tc::smem_u32(tempty);
-      const uint32_t a_hi = (128u >> 4) | (1u << 14);                               // SBO = 128 B, version 1
+      const uint32_t a_hi = CH == 1 ? ((128u >> 4) | (1u << 14))                     // no swizzle: SBO = 128 B, version 1
+                                    : ((512u >> 4) | (1u << 14) | (4u << 29));       // SWIZZLE_64B: SBO = 8 x 64-byte rows
       const uint32_t b_hi = (((uint32_t)(p.ktot >> 3) * 128u) >> 4) | (1u << 14);   // SBO = ktot/8 cores
       const uint32_t b_lo0 = (tc::smem_u32(sW) >> 4) | ((128u >> 4) << 16);         // LBO = 128 B
       const int ring = p.ring, R = p.R;
@@ -201,64 +209,79 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       for (int t = blockIdx.x; t < p.total_strips; t += gridDim.x) {
         const int n = t / p.strips_per_img, i0 = (t - n * p.strips_per_img) * R;
         (void)n;
-        for (int r = 0; r < R; ++r) {
-          // rows newly needed by this output row: 5 for the first row of a strip, S afterwards
-          const int need = (r == 0) ? 5 : S;
-          for (int k = 0; k < need; ++k) {
-            tc::mbar_wait_addr(full_addr + wslot * 8, wphase);
-            if (++wslot == ring) { wslot = 0; wphase ^= 1; }
-          }
+        for (int r = 0; r < R; r += RPS) {
           tc::mbar_wait_addr(tempty_addr + acc * 8, aphase ^ 1);
-          tc::fence_after_sync();
-          const uint32_t tacc = tmem_base + (uint32_t)(acc * p.B);
-          const int ytop = S * (i0 + r) - PAD;
-          uint32_t accum = 0;
 #pragma unroll
-          for (int ky = 0; ky < 5; ++ky) {
-            const int y = ytop + ky;
-            if (y < 0 || y >= p.Hb) continue;
-            int sl = s0 + ky;
-            if (sl >= ring) sl -= ring;
-            const uint32_t sa_lo = ring_lo + (uint32_t)sl * (uint32_t)(ROWB >> 4);
+          for (int sub = 0; sub < RPS; ++sub) {
+            // input rows newly needed by this output row: 5 for the first row of a strip, S afterwards
+            const int need = (r + sub == 0) ? 5 : S;
+            for (int k = 0; k < need; ++k) {
+              tc::mbar_wait_addr(full_addr + wslot * 8, wphase);
+              if (++wslot == ring) { wslot = 0; wphase ^= 1; }
+            }
+            tc::fence_after_sync();
+            const uint32_t tacc = tmem_base + (uint32_t)(acc * p.B) + ((uint32_t)(16 * sub) << 16);
+            const int ytop = S * (i0 + r + sub) - PAD;
+            const bool last = (r + sub == R - 1);
+            const int sb = s0;                                // ring slot of this output row's top input row
+            uint32_t accum = 0;
 #pragma unroll
-            for (int q = 0; q < NM; ++q) {
-              tc::mma_bf16_lohi(tacc, sa_lo + a_lo_const<S, CH, PLANEB>(q), a_hi,
-                                b_lo0 + (uint32_t)(ky * NM + q) * 16u, b_hi, idesc, accum);
-              accum = 1;
+            for (int ky = 0; ky < 5; ++ky) {
+              const int y = ytop + ky;
+              if (y >= 0 && y < p.Hb) {
+                int sl = sb + ky;
+                if (sl >= ring) sl -= ring;
+                const uint32_t sa_lo = ring_lo + (uint32_t)sl * (uint32_t)(ROWB >> 4);
+#pragma unroll
+                for (int q = 0; q < NM; ++q) {
+                  tc::mma_bf16_lohi(tacc, sa_lo + a_lo_const<S, CH, PLANEB>(q), a_hi,
+                                    b_lo0 + (uint32_t)(ky * NM + q) * 16u, b_hi, idesc, accum);
+                  accum = 1;
+                }
+              }
+              // the top S rows are not needed by any later output row: hand them back to the producer as soon
+              // as the MMAs reading them retire (everything at the strip's end)
+              if (ky == S - 1 && !last) {
+#pragma unroll
+                for (int k = 0; k < S; ++k) {
+                  tc::mma_commit_addr(empty_addr + s0 * 8);
+                  if (++s0 == ring) s0 = 0;
+                }
+              }
+            }
+            if (last) {
+              for (int k = 0; k < 5; ++k) {
+                tc::mma_commit_addr(empty_addr + s0 * 8);
+                if (++s0 == ring) s0 = 0;
+              }
             }
           }
           tc::mma_commit_addr(tfull_addr + acc * 8);
-          // rows no later output row of the strip needs: S per output row, everything at the strip's end
-          const int nfree = (r == R - 1) ? 5 : S;
-          for (int k = 0; k < nfree; ++k) {
-            tc::mma_commit_addr(empty_addr + s0 * 8);
-            if (++s0 == ring) s0 = 0;
-          }
           if (++acc == RC_ACC) { acc = 0; aphase ^= 1; }
         }
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue: one thread per output pixel;
-    // warp group 0 takes the even output rows of the CTA's row sequence, group 1 the odd ones
+    // ------------------------------------------------------------ epilogue: one thread per pixel of a stage;
+    // warp group 0 takes the even stages of the CTA's stage sequence, group 1 the odd ones
     const int q = warp & 3, grp = warp >> 2;
-    const int m = (MM == 64) ? q * 16 + lane : q * 32 + lane;     // M = 64: rows 16q..16q+15 sit in lanes 32q..32q+15
-    const bool active = (MM == 64) ? (lane < 16) : (m < p.Ws);
+    // pixel of the stage held by this thread's TMEM lane: M = 64 rows 16q..16q+15 of output row `sub`
+    const int m = (MM == 64) ? (lane >> 4) * 64 + q * 16 + (lane & 15) : q * 32 + lane;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const int zrow_bytes = p.B * 2;
     const int swz = zrow_bytes == 128 ? (m & 7) : ((m >> 1) & 3);
-    uint32_t rs = 0;                                              // output rows of this CTA before the current strip
-    for (int t = blockIdx.x; t < p.total_strips; t += gridDim.x, rs += (uint32_t)p.R) {
+    const int nstage = p.R / RPS;
+    uint32_t ps = 0;                                              // stages of this CTA before the current strip
+    for (int t = blockIdx.x; t < p.total_strips; t += gridDim.x, ps += (uint32_t)nstage) {
       const int n = t / p.strips_per_img, i0 = (t - n * p.strips_per_img) * p.R;
       NormBwdCoef coef = {0.f, 0.f, 0.f, 0.f};
       if constexpr (NB) coef = nb_coef(nb, n);
       float s1 = 0.f, s2 = 0.f;
-      for (int r = grp; r < p.R; r += 2) {
-        const int i = i0 + r;
-        const uint32_t seq = rs + (uint32_t)r;
-        const int acc = seq & (RC_ACC - 1), zs = seq & (RC_ZSLOTS - 1);
-        const uint32_t aphase = (seq / RC_ACC) & 1u, zphase = (seq / RC_ZSLOTS) & 1u;
-        bf16* orow = p.out + (((int64_t)n * p.Hs + i) * p.Ws + m) * p.B;
+      for (int sg = grp; sg < nstage; sg += 2) {
+        const uint32_t seq = ps + (uint32_t)sg;
+        const int acc = seq & (RC_ACC - 1), zs = seq & (p.zslots - 1);
+        const uint32_t aphase = (seq / RC_ACC) & 1u, zphase = (seq / (uint32_t)p.zslots) & 1u;
+        bf16* orow = p.out + (((int64_t)n * p.Hs + i0 + sg * RPS) * p.Ws + m) * p.B;
         tc::mbar_wait(&tfull[acc], aphase);
         if constexpr (NB) tc::mbar_wait(&zfull[zs], zphase);
         tc::fence_after_sync();
@@ -267,7 +290,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         for (int cb = 0; cb < p.B; cb += 32) {
           float v[32];
           tc::tmem_ld32(taddr + cb, v);
-          if (active) {
+          {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               uint32_t pk[8];
@@ -344,10 +367,11 @@ bool plan_rc(int Nimg, int Hb, int Wb, int A, int Cpad, int B, int s, bool with_
   const int nmk = pl->CH == 1 ? 3 : 10;
   p.ktot = 5 * nmk * 16;
   p.w_bytes = B * p.ktot * 2;
-  p.z_slot_bytes = p.Ws * B * 2;
+  p.z_slot_bytes = 128 * B * 2;
+  p.zslots = B <= 32 ? 4 : 2;
   const int sms = lg_num_sms();
   // ring: at least the 5 + s rows one output row touches, deeper while shared memory allows
-  const size_t fixed = (with_nb ? (size_t)RC_ZSLOTS * p.z_slot_bytes : 0) + ((p.w_bytes + 1023) & ~1023) + 2048 + 1024;
+  const size_t fixed = (with_nb ? (size_t)p.zslots * p.z_slot_bytes : 0) + ((p.w_bytes + 1023) & ~1023) + 2048 + 1024;
   int ring = 16;
   const size_t budget = (pl->CH == 1) ? 100 * 1024 : 220 * 1024;
   while (ring > 5 + s + 1 && fixed + (size_t)ring * p.row_bytes > budget) --ring;
@@ -364,6 +388,7 @@ bool plan_rc(int Nimg, int Hb, int Wb, int A, int Cpad, int B, int s, bool with_
     const double eff = (double)tiles / ((double)waves * ctas) * (1.0 - 0.25 * 4.0 / (s * R + 4.0));
     if (eff > best) { best = eff; bestR = R; }
   }
+  if (const char* e = getenv("LG_RC_R")) { const int R = atoi(e); if (R >= 4 && p.Hs % R == 0 && R % 2 == 0) bestR = R; }   // tuning knob
   if (!bestR) return false;
   p.R = bestR; p.strips_per_img = p.Hs / bestR; p.total_strips = Nimg * p.strips_per_img;
   pl->grid = p.total_strips < ctas ? p.total_strips : ctas;
@@ -422,14 +447,16 @@ int lg_tc_rowconv_fprop(const void* big, const void* wpack, const float* bias, v
   if (!enc) { lg_set_error("cuTensorMapEncodeTiled entry point not available"); return LG_ERR_CUDA; }
   CUtensorMap tmIn, tmZ;
   {
-    // (8 channels) x (pixels of one x parity) x (parity, chunk) x (rows of all images)
-    cuuint64_t dims[4] = {8, (cuuint64_t)(Wb / s), (cuuint64_t)(s * pl.CH), (cuuint64_t)Nimg * Hb};
-    cuuint64_t strides[3] = {(cuuint64_t)s * Cpad * 2, 16, (cuuint64_t)Wb * Cpad * 2};
-    cuuint32_t box[4] = {8, (cuuint32_t)pl.Wp, (cuuint32_t)(s * pl.CH), 1};
+    // (channels of a pixel) x (pixels of one x parity) x (parity) x (rows of all images): 16-byte pixels land
+    // as no-swizzle planes, 64-byte pixels as SWIZZLE_64B rows (TMA moves one inner run per pixel either way;
+    // 16-byte runs of a split 64-byte pixel would quarter its throughput)
+    cuuint64_t dims[4] = {(cuuint64_t)Cpad, (cuuint64_t)(Wb / s), (cuuint64_t)s, (cuuint64_t)Nimg * Hb};
+    cuuint64_t strides[3] = {(cuuint64_t)s * Cpad * 2, (cuuint64_t)Cpad * 2, (cuuint64_t)Wb * Cpad * 2};
+    cuuint32_t box[4] = {(cuuint32_t)Cpad, (cuuint32_t)pl.Wp, (cuuint32_t)s, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(big), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, pl.CH == 1 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { lg_set_error("row-streaming conv: input tensor map failed: %d", (int)r); return LG_ERR_CUDA; }
   }
   NormBwdDev nbd = {};
@@ -437,7 +464,7 @@ int lg_tc_rowconv_fprop(const void* big, const void* wpack, const float* bias, v
     nbd = lg_make_norm_bwd(nb, (int64_t)p.Hs * p.Ws * B);
     cuuint64_t dims[2] = {(cuuint64_t)B, (cuuint64_t)Nimg * p.Hs * p.Ws};
     cuuint64_t strides[1] = {(cuuint64_t)B * 2};
-    cuuint32_t box[2] = {(cuuint32_t)B, (cuuint32_t)p.Ws};
+    cuuint32_t box[2] = {(cuuint32_t)B, 128};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&tmZ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(nb->z), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, B == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,

@@ -6,8 +6,9 @@
 //
 //   T_y[X][(ky,a)] = sum_{kx,b} small[y][X+2-kx][b] * W[ky][kx][a][b]       per INPUT row y: 10 MMAs
 //                    (M = 128 pixels, N = 16 >= 5*3, K = 16), the A operand of tap kx being the input row in
-//                    its shared-memory ring slot read at a start address shifted by kx pixels (planes of
-//                    [8-channel chunk][pixel][16 B] = canonical no-swizzle K-major, see tc_rowconv.cu);
+//                    its shared-memory ring slot read at a start address shifted by kx pixels: the slot is
+//                    [pixel][64 B] exactly as TMA writes it with SWIZZLE_64B = a swizzled K-major operand whose
+//                    descriptor may start at any 64-byte row (the swizzle is a function of the absolute address);
 //   out[Y][X][a]   = bias[a] + sum_ky T_{Y+2-ky}[X][(ky,a)]                   the same TMEM lane (thread X) for
 //                    every term: five rolling 3-channel accumulators per thread, one row retired per input row.
 //
@@ -28,8 +29,7 @@ constexpr int RD_THREADS = 192;          // warps 0-3 epilogue, 4 row producer, 
 constexpr int RD_ACC = 4;                // TMEM accumulator stages (16 columns each)
 constexpr int RD_W = 128;                // map width = MMA M
 constexpr int RD_B = 32;                 // input channels
-constexpr int RD_PLANEB = (RD_W + 8) * 16;
-constexpr int RD_ROWB = (RD_B / 8) * RD_PLANEB;
+constexpr int RD_ROWB = (RD_W + 8) * RD_B * 2;   // one input row: 136 pixels x 64 B
 constexpr int RD_KTOT = 5 * RD_B;        // K of the weight operand: (kx, b)
 constexpr int RD_RING = 8;
 
@@ -45,10 +45,10 @@ struct RdParams {
 __global__ void __launch_bounds__(RD_THREADS)
 tc_rowdeconv_kernel(const __grid_constant__ CUtensorMap tmIn, const RdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  uint8_t* sW = smem;                                             // 16 rows x 160 k, no-swizzle K-major (5 KB)
-  uint8_t* sRing = sW + 16 * RD_KTOT * 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + RD_RING * RD_ROWB);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sRing = smem;                                          // RING x [136 px][64 B], SWIZZLE_64B (slots 512-B aligned)
+  uint8_t* sW = sRing + RD_RING * RD_ROWB;                        // 16 rows x 160 k, no-swizzle K-major (5 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 16 * RD_KTOT * 2);
   uint64_t* full = bars;                     // [RING] TMA -> MMA
   uint64_t* empty = full + RD_RING;          // [RING] MMA -> TMA
   uint64_t* tfull = empty + RD_RING;         // [ACC]  MMA -> epilogue
@@ -91,7 +91,7 @@ tc_rowdeconv_kernel(const __grid_constant__ CUtensorMap tmIn, const RdParams p) 
           if (y < 0 || y >= p.H) continue;
           tc::mbar_wait_addr(empty_addr + slot * 8, phase ^ 1);
           tc::mbar_expect_tx_addr(full_addr + slot * 8, (uint32_t)RD_ROWB);
-          tc::tma_load_4d_addr(ring_addr + slot * RD_ROWB, &tmIn, full_addr + slot * 8, 0, -2, 0, n * p.H + y);
+          tc::tma_load_3d_addr(ring_addr + slot * RD_ROWB, &tmIn, full_addr + slot * 8, 0, -2, n * p.H + y);
           if (++slot == RD_RING) { slot = 0; phase ^= 1; }
         }
       }
@@ -103,10 +103,10 @@ tc_rowdeconv_kernel(const __grid_constant__ CUtensorMap tmIn, const RdParams p) 
       const uint32_t ring_lo = tc::smem_u32(sRing) >> 4;
       const uint32_t full_addr = tc::smem_u32(full), empty_addr = tc::smem_u32(empty);
       const uint32_t tfull_addr = tc::smem_u32(tfull), tempty_addr = tc::smem_u32(tempty);
-      const uint32_t a_hi = (128u >> 4) | (1u << 14);                               // SBO = 128 B
+      const uint32_t a_hi = (512u >> 4) | (1u << 14) | (4u << 29);                   // SBO = 8 rows x 64 B, SWIZZLE_64B
       const uint32_t b_hi = (((uint32_t)(RD_KTOT / 8) * 128u) >> 4) | (1u << 14);   // SBO = 20 cores
       const uint32_t b_lo0 = (tc::smem_u32(sW) >> 4) | ((128u >> 4) << 16);         // LBO = 128 B
-      constexpr uint32_t A_LBO = ((uint32_t)RD_PLANEB >> 4) << 16;                  // K halves = two chunk planes
+      constexpr uint32_t A_LBO = 1u << 16;                                          // unused for swizzled K-major
       int slot = 0; uint32_t phase = 0;
       int acc = 0; uint32_t aphase = 0;
       for (int t = blockIdx.x; t < p.total_strips; t += gridDim.x) {
@@ -124,7 +124,7 @@ tc_rowdeconv_kernel(const __grid_constant__ CUtensorMap tmIn, const RdParams p) 
           for (int kx = 0; kx < 5; ++kx) {
 #pragma unroll
             for (int cp = 0; cp < 2; ++cp) {
-              const uint32_t a_off = (uint32_t)((2 * cp) * RD_PLANEB + (4 - kx) * 16) >> 4;
+              const uint32_t a_off = (uint32_t)((4 - kx) * 64 + cp * 32) >> 4;       // pixel shift + K step inside the 64-B row
               tc::mma_bf16_lohi(tacc, sa_lo + (a_off | A_LBO), a_hi, b_lo0 + (uint32_t)(kx * 2 + cp) * 16u, b_hi, idesc,
                                 (kx | cp) ? 1u : 0u);
             }
@@ -233,15 +233,15 @@ int lg_tc_rowdeconv(const void* small, const float* W, const float* bias, void* 
   tc_host::EncodeTiledFn enc = tc_host::get_encode();
   if (!enc) { lg_set_error("cuTensorMapEncodeTiled entry point not available"); return LG_ERR_CUDA; }
   CUtensorMap tmIn;
-  cuuint64_t dims[4] = {8, (cuuint64_t)Wb, (cuuint64_t)(B / 8), (cuuint64_t)Nimg * Hb};
-  cuuint64_t strides[3] = {(cuuint64_t)B * 2, 16, (cuuint64_t)Wb * B * 2};
-  cuuint32_t box[4] = {8, (cuuint32_t)(RD_W + 8), (cuuint32_t)(B / 8), 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(small), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  cuuint64_t dims[3] = {(cuuint64_t)B, (cuuint64_t)Wb, (cuuint64_t)Nimg * Hb};
+  cuuint64_t strides[2] = {(cuuint64_t)B * 2, (cuuint64_t)Wb * B * 2};
+  cuuint32_t box[3] = {(cuuint32_t)B, (cuuint32_t)(RD_W + 8), 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(&tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(small), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { lg_set_error("row-streaming RGB transposed conv: tensor map failed: %d", (int)r); return LG_ERR_CUDA; }
-  const size_t shm = 16 * RD_KTOT * 2 + (size_t)RD_RING * RD_ROWB + 512 + 128;
+  const size_t shm = 16 * RD_KTOT * 2 + (size_t)RD_RING * RD_ROWB + 512 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_rowdeconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
