@@ -90,6 +90,16 @@ int lg_conv2d_dgrad(const void* small, const float* W, const void* wpack, const 
                     int stride, int act, int dtype, int use_tc, const lg_norm_bwd_t* norm_bwd,
                     void* stream);
 
+/* dgrad on the row-streaming tensor-core kernel (csrc/tc_rowdgrad.cu) for the decoder's last transposed conv
+ * (A = 32 output channels, B = 64, stride 2, 128-pixel-wide result; model.py:39): every input row is fetched
+ * once into a shared-memory ring and all 25 taps read it in place.  wpack: from lg_pack_rowdgrad_weights
+ * (W [5,5,A,B] fp32; call with W or wpack NULL for the size in bytes; refresh after every weight update).
+ * bias / stats as for lg_conv2d_dgrad, LG_BF16 only, no activation. */
+int lg_conv2d_dgrad_rows_supported(int N, int Hb, int Wb, int A, int B, int stride);
+int lg_pack_rowdgrad_weights(const float* W, void* wpack, int A, int B, void* stream);
+int lg_conv2d_dgrad_rows(const void* small, const void* wpack, const float* bias, void* big_out, double* stats,
+                         int N, int Hb, int Wb, int A, int B, int stride, void* stream);
+
 /* dgrad with an RGB result (A = 3, stride 1, 128-pixel-wide maps: the generator's final Conv2DTranspose,
  * model.py:86) on the row-streaming tensor-core kernel (csrc/tc_rowdeconv.cu).  Same arithmetic as
  * lg_conv2d_dgrad (LG_BF16); big_out_pad8, if not NULL, also receives the image with 8-channel zero-padded

@@ -28,6 +28,9 @@ SIGNATURES = {
     "lg_pack_rowconv_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "lg_conv2d_fprop_rows": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lg_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lg_conv2d_dgrad_rows_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "lg_pack_rowdgrad_weights": (_i, [_vp, _vp, _i, _i, _vp]),
+    "lg_conv2d_dgrad_rows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_conv2d_dgrad_rgb_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "lg_conv2d_dgrad_rgb": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_conv2d_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

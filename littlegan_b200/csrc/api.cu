@@ -126,6 +126,27 @@ extern "C" int lg_conv2d_dgrad(const void* small, const float* W, const void* wp
   return LG_OK;
 }
 
+extern "C" int lg_conv2d_dgrad_rows_supported(int N, int Hb, int Wb, int A, int B, int stride) {
+  return lg_tc_rowdgrad_supported(N, Hb, Wb, A, B, stride);
+}
+
+extern "C" int lg_pack_rowdgrad_weights(const float* W, void* wpack, int A, int B, void* stream) {
+  int e = lg_tc_rowdgrad_pack(W, wpack, A, B, (cudaStream_t)stream);
+  if (e < 0 || !W || !wpack) return e;
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_conv2d_dgrad_rows(const void* small, const void* wpack, const float* bias, void* big_out,
+                                    double* stats, int N, int Hb, int Wb, int A, int B, int stride, void* stream) {
+  if (int e = check_geom(__func__, N, Hb, Wb, A, B, stride, LG_BF16)) return e;
+  LG_REQUIRE(small && big_out && wpack, "NULL tensor");
+  int e = lg_tc_rowdgrad(small, wpack, bias, big_out, stats, N, Hb, Wb, A, B, stride, (cudaStream_t)stream);
+  if (e) return e;
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
 extern "C" int lg_conv2d_dgrad_rgb_supported(int N, int Hb, int Wb, int A, int B, int stride) {
   return lg_tc_rowdeconv_supported(N, Hb, Wb, A, B, stride);
 }

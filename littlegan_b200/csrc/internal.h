@@ -41,4 +41,8 @@ int lg_tc_rowconv_fprop(const void* big, const void* wpack, const float* bias, v
 int lg_tc_rowdeconv_supported(int N, int Hb, int Wb, int A, int B, int s);
 int lg_tc_rowdeconv(const void* small, const float* W, const float* bias, void* out3, void* out8, double* stats,
                     int N, int Hb, int Wb, int A, int B, int s, int act, cudaStream_t st);
+int lg_tc_rowdgrad_supported(int N, int Hb, int Wb, int A, int B, int s);
+int lg_tc_rowdgrad_pack(const float* W, void* wpack, int A, int B, cudaStream_t st);
+int lg_tc_rowdgrad(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
+                   int Wb, int A, int B, int s, cudaStream_t st);
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N);

@@ -132,8 +132,20 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   const uint32_t tmem_cols = RC_ACC * p.B <= 128 ? 128 : 256;
 
   // weights: already bf16 in the canonical no-swizzle K-major operand layout (rc_pack_kernel)
-  for (int e = threadIdx.x; e < (p.w_bytes >> 4); e += RC_THREADS)
-    reinterpret_cast<uint4*>(sW)[e] = __ldg(p.wpack + e);
+  // (four independent 16-byte loads in flight per thread before the stores)
+  for (int e0 = 0; e0 < (p.w_bytes >> 4); e0 += 4 * RC_THREADS) {
+    uint4 wv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = e0 + i * RC_THREADS + (int)threadIdx.x;
+      wv[i] = e < (p.w_bytes >> 4) ? __ldg(p.wpack + e) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = e0 + i * RC_THREADS + (int)threadIdx.x;
+      if (e < (p.w_bytes >> 4)) reinterpret_cast<uint4*>(sW)[e] = wv[i];
+    }
+  }
   for (int e = threadIdx.x; e < p.B; e += RC_THREADS) sbias[e] = p.bias ? p.bias[e] : 0.f;
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmIn);
@@ -271,6 +283,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     const int zrow_bytes = p.B * 2;
     const int swz = zrow_bytes == 128 ? (m & 7) : ((m >> 1) & 3);
     const int nstage = p.R / RPS;
+    const int zshift = p.zslots == 4 ? 2 : 1;
     uint32_t ps = 0;                                              // stages of this CTA before the current strip
     for (int t = blockIdx.x; t < p.total_strips; t += gridDim.x, ps += (uint32_t)nstage) {
       const int n = t / p.strips_per_img, i0 = (t - n * p.strips_per_img) * p.R;
@@ -280,7 +293,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       for (int sg = grp; sg < nstage; sg += 2) {
         const uint32_t seq = ps + (uint32_t)sg;
         const int acc = seq & (RC_ACC - 1), zs = seq & (p.zslots - 1);
-        const uint32_t aphase = (seq / RC_ACC) & 1u, zphase = (seq / (uint32_t)p.zslots) & 1u;
+        const uint32_t aphase = (seq / RC_ACC) & 1u, zphase = (seq >> zshift) & 1u;
         bf16* orow = p.out + (((int64_t)n * p.Hs + i0 + sg * RPS) * p.Ws + m) * p.B;
         tc::mbar_wait(&tfull[acc], aphase);
         if constexpr (NB) tc::mbar_wait(&zfull[zs], zphase);

@@ -31,7 +31,8 @@ constexpr int RD_W = 128;                // map width = MMA M
 constexpr int RD_B = 32;                 // input channels
 constexpr int RD_ROWB = (RD_W + 8) * RD_B * 2;   // one input row: 136 pixels x 64 B
 constexpr int RD_KTOT = 5 * RD_B;        // K of the weight operand: (kx, b)
-constexpr int RD_RING = 8;
+constexpr int RD_RING = 5;
+constexpr int RD_CTAS_PER_SM = 4;        // 49 KB of shared memory and 64 TMEM columns each: the epilogue is latency bound
 
 struct RdParams {
   int Nimg, H, R, strips_per_img, total_strips, act;
@@ -57,13 +58,25 @@ tc_rowdeconv_kernel(const __grid_constant__ CUtensorMap tmIn, const RdParams p) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // weights: W[ky][kx][a][b] -> bf16 operand row n = ky*3 + a (row 15 = 0), k = kx*32 + b
-  for (int e = threadIdx.x; e < 16 * RD_KTOT; e += RD_THREADS) {
-    const int n = e / RD_KTOT, k = e - n * RD_KTOT;
-    const int ky = n / 3, a = n - ky * 3, kx = k >> 5, b = k & 31;
-    const float v = n < 15 ? p.W[((ky * 5 + kx) * 3 + a) * RD_B + b] : 0.f;
-    const int off = (n >> 3) * ((RD_KTOT / 8) * 128) + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
-    *reinterpret_cast<bf16*>(sW + off) = __float2bfloat16_rn(v);
+  // weights: W[ky][kx][a][b] -> bf16 operand row n = ky*3 + a (row 15 = 0), k = kx*32 + b.  All loads are issued
+  // before the first store: a load-store-load chain would pay one memory round trip per element.
+  {
+    constexpr int TOT = 16 * RD_KTOT, PER = (TOT + RD_THREADS - 1) / RD_THREADS;
+    float wv[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = threadIdx.x + i * RD_THREADS;
+      const int n = e / RD_KTOT, k = e - n * RD_KTOT;
+      const int ky = n / 3, a = n - ky * 3, kx = k >> 5, b = k & 31;
+      wv[i] = (e < TOT && n < 15) ? __ldg(p.W + ((ky * 5 + kx) * 3 + a) * RD_B + b) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = threadIdx.x + i * RD_THREADS;
+      const int n = e / RD_KTOT, k = e - n * RD_KTOT;
+      const int off = (n >> 3) * ((RD_KTOT / 8) * 128) + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+      if (e < TOT) *reinterpret_cast<bf16*>(sW + off) = __float2bfloat16_rn(wv[i]);
+    }
   }
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmIn);
@@ -201,7 +214,7 @@ tc_rowdeconv_kernel(const __grid_constant__ CUtensorMap tmIn, const RdParams p) 
 
 bool plan_rd(int Nimg, int Hb, int Wb, int A, int B, int s, RdParams* p, int* grid) {
   if (s != 1 || A != 3 || B != RD_B || Wb != RD_W || Hb < 8 || (Hb & (Hb - 1))) return false;
-  const int ctas = lg_num_sms() * 2;
+  const int ctas = lg_num_sms() * RD_CTAS_PER_SM;
   int bestR = 0; double best = -1.0;
   for (int R = Hb; R >= 4; R >>= 1) {
     const int tiles = Nimg * (Hb / R);

@@ -26,6 +26,12 @@ class Runtime:
         self.want_tc = mode == "bf16" and getattr(args, "tensor_cores", True)
         self._tc_cache = {}
         self._heads_ws = None
+        # weight-gradient launches run on a side stream: nothing in the backward chain consumes them, so they
+        # overlap with the bandwidth-bound norm kernels that follow on the main stream (also inside a captured
+        # CUDA graph, where the fork / join become parallel branches)
+        self.overlap = bool(getattr(args, "overlap_wgrad", True))
+        self._side = None
+        self._side_keep = []
 
     def use_tc(self, op, N, Hb, Wb, A, B, s):
         if not self.want_tc:
@@ -59,6 +65,37 @@ class Runtime:
             r = A_big if (K.tc_available() and K.fprop_rows_supported(N, Hb, Wb, A_big, A, B, s)) else 0
             self._tc_cache[key] = r
         return r
+
+    def drows_ok(self, N, Hb, Wb, A, B, s):
+        """Does the row-streaming dgrad kernel (csrc/tc_rowdgrad.cu) take this geometry?"""
+        if not self.want_tc:
+            return False
+        key = ("drows", N, Hb, Wb, A, B, s)
+        r = self._tc_cache.get(key)
+        if r is None:
+            r = self._tc_cache[key] = K.tc_available() and K.dgrad_rows_supported(N, Hb, Wb, A, B, s)
+        return r
+
+    def on_side(self, fn, *keep):
+        """Run the launches of `fn` on the side stream, ordered after everything issued so far on the current
+        stream.  `keep`: tensors the launches read - held until join_side() so the caching allocator cannot
+        hand their memory to later main-stream work while the side stream is still reading."""
+        if not self.overlap:
+            fn()
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            fn()
+        self._side_keep.append(keep)
+
+    def join_side(self):
+        """Make the current stream wait for the side-stream launches (before their results are consumed)."""
+        if self._side_keep:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_keep = []
 
     def heads_workspace(self, N):
         """Scratch of the fused discriminator-heads forward (self-cleaning, allocated once per size)."""
@@ -131,6 +168,8 @@ def refresh_packs(rt, conv_layers):
         A_big = 8 if A <= 8 else A
         if K.fprop_rows_supported(1, 128, 128, A_big, A, B, layer.strides):
             layer.wpack_rows = K.pack_rowconv_weights(layer.kernel, A_big, layer.strides, layer.wpack_rows)
+        if K.dgrad_rows_supported(1, 128, 128, A, B, layer.strides):
+            layer.wpack_drows = K.pack_rowdgrad_weights(layer.kernel, layer.wpack_drows)
 
 
 # --------------------------------------------------------------------------------------------
@@ -188,9 +227,10 @@ def encoder_backward(rt, enc, ctx, g, wgrad, input_grad):
         B = conv.filters
         if wgrad:
             if xpad is not None and rt.use_tc(K.OP_WGRAD, N, Hb, Wb, 16, B, 2):
-                K.conv2d_wgrad_padded(xpad, dz, _grad(conv.kernel), 2)
+                rt.on_side(lambda: K.conv2d_wgrad_padded(xpad, dz, _grad(conv.kernel), 2), xpad, dz)
             else:
-                K.conv2d_wgrad(x, dz, _grad(conv.kernel), 2, rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2))
+                tcw = rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2)
+                rt.on_side(lambda: K.conv2d_wgrad(x, dz, _grad(conv.kernel), 2, tcw), x, dz)
         dy_ready = False
         if i > 0 or input_grad:
             g = torch.empty_like(x)
@@ -204,6 +244,7 @@ def encoder_backward(rt, enc, ctx, g, wgrad, input_grad):
                            rt.use_tc(K.OP_DGRAD, N, Hb, Wb, A, B, 2), norm_bwd=nb)
         else:
             g = None
+    rt.join_side()
     return g
 
 
@@ -221,8 +262,11 @@ def decoder_forward(rt, dec, x, skips_after=(None, None, None)):
         _, Hs, Ws, B = x.shape
         A = conv.filters
         z = rt.empty(N, 2 * Hs, 2 * Ws, A)
-        tc = rt.use_tc(K.OP_DGRAD, N, 2 * Hs, 2 * Ws, A, B, 2)
-        K.conv2d_dgrad(x, conv.kernel, conv.bias, z, stats[i], 2, K.ACT_NONE, conv.wpack, tc)
+        if conv.wpack_drows is not None and rt.drows_ok(N, 2 * Hs, 2 * Ws, A, B, 2):
+            K.conv2d_dgrad_rows(x, conv.wpack_drows, conv.bias, z, stats[i], 2)
+        else:
+            tc = rt.use_tc(K.OP_DGRAD, N, 2 * Hs, 2 * Ws, A, B, 2)
+            K.conv2d_dgrad(x, conv.kernel, conv.bias, z, stats[i], 2, K.ACT_NONE, conv.wpack, tc)
         a = torch.empty_like(z)
         skip = skips_after[i] if i < 3 else None
         K.instnorm_act_fwd(z, stats[i], norm.gamma, norm.beta, skip, a, norm.epsilon, 1.0, rt.alpha)
@@ -246,7 +290,8 @@ def decoder_backward(rt, dec, ctx, g, wgrad, red=None, dy_ready=False):
         _, Hb, Wb, A = z.shape
         B = x.shape[3]
         if wgrad:
-            K.conv2d_wgrad(dz, x, _grad(conv.kernel), 2, rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2))
+            tcw = rt.use_tc(K.OP_WGRAD, N, Hb, Wb, A, B, 2)
+            rt.on_side(lambda: K.conv2d_wgrad(dz, x, _grad(conv.kernel), 2, tcw), dz, x)
         g = torch.empty_like(x)
         nb = None
         dy_ready = False
@@ -256,6 +301,7 @@ def decoder_backward(rt, dec, ctx, g, wgrad, red=None, dy_ready=False):
                                  dec.norms[i - 1].epsilon, rt.alpha)
             dy_ready = True
         _fprop(rt, conv, dz, None, g, None, 2, nb)
+    rt.join_side()
     return g
 
 
@@ -279,11 +325,13 @@ def final_conv_backward(rt, conv, x, dpre, wgrad, nb=None):
     A = conv.filters
     dpad = _padded_for_tc(rt, dpre, K.OP_FPROP, B, 1)
     if wgrad:
-        K.bias_grad(dpre, _grad(conv.bias))
-        if dpad is not None and rt.use_tc(K.OP_WGRAD, N, H, W, 16, B, 1):
-            K.conv2d_wgrad_padded(dpad, x, _grad(conv.kernel), 1)
-        else:
-            K.conv2d_wgrad(dpre, x, _grad(conv.kernel), 1, rt.use_tc(K.OP_WGRAD, N, H, W, A, B, 1))
+        def _wg():
+            K.bias_grad(dpre, _grad(conv.bias))
+            if dpad is not None and rt.use_tc(K.OP_WGRAD, N, H, W, 16, B, 1):
+                K.conv2d_wgrad_padded(dpad, x, _grad(conv.kernel), 1)
+            else:
+                K.conv2d_wgrad(dpre, x, _grad(conv.kernel), 1, rt.use_tc(K.OP_WGRAD, N, H, W, A, B, 1))
+        rt.on_side(_wg, dpre, dpad, x)
     g = torch.empty_like(x)
     if dpad is not None:
         K.conv2d_fprop(dpad, conv.kernel, None, g, None, 1, conv.wpack, True, norm_bwd=nb)

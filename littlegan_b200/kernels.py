@@ -128,6 +128,32 @@ def conv2d_dgrad(small, W, bias, out, stats, stride, act=ACT_NONE, wpack=None, u
     return out
 
 
+def dgrad_rows_supported(N, Hb, Wb, A, B, stride):
+    return bool(_lib.load().lg_conv2d_dgrad_rows_supported(N, Hb, Wb, A, B, stride))
+
+
+def pack_rowdgrad_weights(W, wpack=None):
+    """bf16 weight operand of the row-streaming dgrad kernel for W [5,5,32,64]."""
+    A, B = W.shape[2], W.shape[3]
+    lib = _lib.load()
+    if wpack is None:
+        nbytes = int(_lib.check(lib.lg_pack_rowdgrad_weights(None, None, A, B, None)))
+        wpack = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    _cuda(W, wpack)
+    check(lib.lg_pack_rowdgrad_weights(_p(W), _p(wpack), A, B, _st()), "lg_pack_rowdgrad_weights")
+    return wpack
+
+
+def conv2d_dgrad_rows(small, wpack, bias, out, stats, stride):
+    """Row-streaming tcgen05 dgrad (decoder conv4 forward): small [N,Hs,64,64] -> out [N,2Hs,128,32]."""
+    _cuda(small, wpack, bias, out, stats)
+    N, Hb, Wb, A = out.shape
+    B = small.shape[3]
+    check(_lib.load().lg_conv2d_dgrad_rows(_p(small), _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
+                                           stride, _st()), "lg_conv2d_dgrad_rows")
+    return out
+
+
 def dgrad_rgb_supported(N, Hb, Wb, A, B, stride):
     return bool(_lib.load().lg_conv2d_dgrad_rgb_supported(N, Hb, Wb, A, B, stride))
 

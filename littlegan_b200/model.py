@@ -48,6 +48,7 @@ class Conv2D:
         self.bias = torch.zeros(filters, dtype=torch.float32, device=_device())
         self.wpack = None
         self.wpack_rows = None      # weight operand of the row-streaming kernel (engine.refresh_packs)
+        self.wpack_drows = None     # ... of the row-streaming dgrad kernel
 
     @property
     def weights(self):
@@ -64,6 +65,7 @@ class Conv2DTranspose:
         self.bias = torch.zeros(filters, dtype=torch.float32, device=_device())
         self.wpack = None
         self.wpack_rows = None      # weight operand of the row-streaming kernel (engine.refresh_packs)
+        self.wpack_drows = None     # ... of the row-streaming dgrad kernel
 
     @property
     def weights(self):

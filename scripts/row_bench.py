@@ -63,3 +63,19 @@ for label, fn in [("rows", lambda: K.conv2d_dgrad_rgb(x, W, bias, out, None, Non
                   ("rows+pad8", lambda: K.conv2d_dgrad_rgb(x, W, bias, out, out8, None, 1, K.ACT_TANH))]:
     us = timeit(fn)
     print("%-12s %-8s N=%3d %8.1f us %7.0f GB/s" % ("final-fwd", label, N, us, (x.numel() + out.numel()) * 2 / 1e3 / us), flush=True)
+
+# decoder conv4 forward: row-streaming dgrad vs the four-phase implicit-GEMM kernel
+x = torch.randn(N, 64, 64, 64, device="cuda").to(torch.bfloat16)
+W = torch.randn(5, 5, 32, 64, device="cuda") * 0.05
+wp = torch.empty(K.pack_conv_weights_bytes(32, 64), dtype=torch.uint8, device="cuda")
+K.pack_conv_weights(W, wp)
+wd = K.pack_rowdgrad_weights(W)
+out = torch.empty(N, 128, 128, 32, device="cuda", dtype=torch.bfloat16)
+bias = torch.zeros(32, device="cuda")
+stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+flops = 2.0 * 25 * 32 * 64 * N * 64 * 64
+for label, fn in [("rows", lambda: K.conv2d_dgrad_rows(x, wd, bias, out, stats, 2)),
+                  ("old", lambda: K.conv2d_dgrad(x, W, bias, out, stats, 2, K.ACT_NONE, wp, True))]:
+    us = timeit(fn)
+    print("%-12s %-8s N=%3d %8.1f us %7.1f TFLOP/s %7.0f GB/s" % ("dec4-fwd", label, N, us, flops / us / 1e6,
+                                                                (x.numel() + out.numel()) * 2 / 1e3 / us), flush=True)

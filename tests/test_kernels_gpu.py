@@ -594,3 +594,22 @@ def test_pad_channels_rgb8():
     x = _rand((3, 16, 24, 3), 9, torch.bfloat16).cuda()
     xp = K.pad_channels(x, torch.full((3, 16, 24, 8), 5.0, dtype=torch.bfloat16, device="cuda"))
     assert torch.equal(xp[..., :3], x) and float(xp[..., 3:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,Hb", [(3, 128), (5, 32)])
+def test_rowdgrad(N, Hb):
+    """Decoder conv4 forward (64 -> 32 channels, stride 2) on the row-streaming dgrad kernel."""
+    from littlegan_b200 import kernels as K
+    Wb, A, B, s = 128, 32, 64, 2
+    assert K.dgrad_rows_supported(N, Hb, Wb, A, B, s)
+    x = _rand((N, Hb // s, Wb // s, B), 4, torch.bfloat16)
+    W = _rand((5, 5, A, B), 5, torch.bfloat16, 0.05).float()
+    b = _rand((A,), 6, torch.float32)
+    ref = O.conv2d_transpose_same(x.double(), W.double(), b.double(), s)
+    out = torch.zeros(N, Hb, Wb, A, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.conv2d_dgrad_rows(x.cuda(), K.pack_rowdgrad_weights(W.cuda()), b.cuda(), out, stats, s)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2
+    ref_stats = torch.stack([ref.reshape(N, -1).sum(1), (ref.reshape(N, -1) ** 2).sum(1)], 1)
+    assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4

