@@ -100,8 +100,8 @@ int lg_pack_rowdgrad_weights(const float* W, void* wpack, int A, int B, void* st
 int lg_conv2d_dgrad_rows(const void* small, const void* wpack, const float* bias, void* big_out, double* stats,
                          int N, int Hb, int Wb, int A, int B, int stride, void* stream);
 
-/* dgrad with an RGB result (A = 3, stride 1, 128-pixel-wide maps: the generator's final Conv2DTranspose,
- * model.py:86) on the row-streaming tensor-core kernel (csrc/tc_rowdeconv.cu).  Same arithmetic as
+/* dgrad with an RGB result (A = 3, 128-pixel-wide result: stride 1 / B = 32 = the generator's final
+ * Conv2DTranspose, model.py:86; stride 2 / B = 64 = the input gradient of the encoder's first Conv2D, model.py:15) on the row-streaming tensor-core kernel (csrc/tc_rowdeconv.cu).  Same arithmetic as
  * lg_conv2d_dgrad (LG_BF16); big_out_pad8, if not NULL, also receives the image with 8-channel zero-padded
  * pixels [N,Hb,Wb,8] - the layout lg_conv2d_fprop_rows fetches. */
 int lg_conv2d_dgrad_rgb_supported(int N, int Hb, int Wb, int A, int B, int stride);

@@ -79,3 +79,10 @@ for label, fn in [("rows", lambda: K.conv2d_dgrad_rows(x, wd, bias, out, stats, 
     us = timeit(fn)
     print("%-12s %-8s N=%3d %8.1f us %7.1f TFLOP/s %7.0f GB/s" % ("dec4-fwd", label, N, us, flops / us / 1e6,
                                                                 (x.numel() + out.numel()) * 2 / 1e3 / us), flush=True)
+
+# encoder conv1 input gradient (64 -> 3 channels, stride 2): row-streaming kernel (routed through lg_conv2d_dgrad)
+x = torch.randn(N, 64, 64, 64, device="cuda").to(torch.bfloat16)
+W = torch.randn(5, 5, 3, 64, device="cuda") * 0.05
+out = torch.empty(N, 128, 128, 3, device="cuda", dtype=torch.bfloat16)
+us = timeit(lambda: K.conv2d_dgrad_rgb(x, W, None, out, None, None, 2, K.ACT_NONE))
+print("%-12s %-8s N=%3d %8.1f us %7.0f GB/s" % ("enc1-dgrad", "rows", N, us, (x.numel() + out.numel()) * 2 / 1e3 / us), flush=True)

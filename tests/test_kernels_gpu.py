@@ -613,3 +613,21 @@ def test_rowdgrad(N, Hb):
     assert rel_err(out, ref) < 1e-2
     ref_stats = torch.stack([ref.reshape(N, -1).sum(1), (ref.reshape(N, -1) ** 2).sum(1)], 1)
     assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
+
+
+@pytest.mark.parametrize("N,Hb", [(3, 128), (5, 32)])
+def test_rowdeconv_rgb_stride2(N, Hb):
+    """Input gradient of the encoder's first Conv2D (64 -> 3 channels, stride 2) on the row-streaming kernel."""
+    from littlegan_b200 import kernels as K
+    Wb, A, B, s = 128, 3, 64, 2
+    assert K.dgrad_rgb_supported(N, Hb, Wb, A, B, s)
+    x = _rand((N, Hb // s, Wb // s, B), 4, torch.bfloat16)
+    W = _rand((5, 5, A, B), 5, torch.bfloat16, 0.05).float()
+    ref = O.conv2d_transpose_same(x.double(), W.double(), torch.zeros(A, dtype=torch.float64), s)
+    out = torch.zeros(N, Hb, Wb, A, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    K.conv2d_dgrad_rgb(x.cuda(), W.cuda(), None, out, None, stats, s, K.ACT_NONE)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2
+    ref_stats = torch.stack([ref.reshape(N, -1).sum(1), (ref.reshape(N, -1) ** 2).sum(1)], 1)
+    assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
