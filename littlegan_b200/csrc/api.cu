@@ -172,7 +172,9 @@ extern "C" int lg_conv2d_wgrad(const void* big, const void* small, float* dW, in
   if (use_tc) {
     LG_REQUIRE(dtype == LG_BF16, "tcgen05 path needs LG_BF16 activations");
     int e;
-    if (lg_tc_cin3_supported(N, Hb, Wb, A, B, stride))
+    if (lg_tc_rowwgrad_supported(N, Hb, Wb, A, B, stride))               // dec4: row streaming, all taps resident
+      e = lg_tc_rowwgrad(big, small, dW, N, Hb, Wb, A, B, stride, st);
+    else if (lg_tc_cin3_supported(N, Hb, Wb, A, B, stride))
       e = lg_tc_cin3_wgrad(big, small, dW, N, Hb, Wb, B, stride, st);
     else
       e = lg_tc_wgrad(big, small, dW, N, Hb, Wb, A, B, stride, st);

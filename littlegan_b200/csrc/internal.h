@@ -45,4 +45,7 @@ int lg_tc_rowdgrad_supported(int N, int Hb, int Wb, int A, int B, int s);
 int lg_tc_rowdgrad_pack(const float* W, void* wpack, int A, int B, cudaStream_t st);
 int lg_tc_rowdgrad(const void* small, const void* wpack, const float* bias, void* out, double* stats, int N, int Hb,
                    int Wb, int A, int B, int s, cudaStream_t st);
+int lg_tc_rowwgrad_supported(int N, int Hb, int Wb, int A, int B, int s);
+int lg_tc_rowwgrad(const void* big, const void* small, float* dW, int N, int Hb, int Wb, int A, int B, int s,
+                   cudaStream_t st);
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N);

@@ -86,3 +86,12 @@ W = torch.randn(5, 5, 3, 64, device="cuda") * 0.05
 out = torch.empty(N, 128, 128, 3, device="cuda", dtype=torch.bfloat16)
 us = timeit(lambda: K.conv2d_dgrad_rgb(x, W, None, out, None, None, 2, K.ACT_NONE))
 print("%-12s %-8s N=%3d %8.1f us %7.0f GB/s" % ("enc1-dgrad", "rows", N, us, (x.numel() + out.numel()) * 2 / 1e3 / us), flush=True)
+
+# decoder conv4 weight gradient: row-streaming kernel (routed through lg_conv2d_wgrad)
+big = torch.randn(N, 128, 128, 32, device="cuda").to(torch.bfloat16)
+small = torch.randn(N, 64, 64, 64, device="cuda").to(torch.bfloat16)
+dW = torch.zeros(5, 5, 32, 64, device="cuda")
+flops = 2.0 * 25 * 32 * 64 * N * 64 * 64
+us = timeit(lambda: K.conv2d_wgrad(big, small, dW, 2, True))
+print("%-12s %-8s N=%3d %8.1f us %7.1f TFLOP/s %7.0f GB/s" % ("dec4-wgrad", "rows", N, us, flops / us / 1e6,
+                                                            (big.numel() + small.numel()) * 2 / 1e3 / us), flush=True)

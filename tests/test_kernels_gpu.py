@@ -495,7 +495,8 @@ TC_W = [
     (4, 64, 64, 64, 128, 2),     # enc2 / dec3: 2 taps per 128-row tile
     (6, 32, 32, 128, 256, 2),    # enc3 / dec2
     (5, 16, 16, 256, 384, 2),    # enc4 / dec1: 2 a-tiles, b split 2 x 192, 8x8 position boxes (odd batch)
-    (3, 128, 128, 32, 64, 2),    # dec4: 32-channel boxes (SWIZZLE_64B), 4 taps per tile
+    (3, 128, 128, 32, 64, 2),    # dec4: row-streaming wgrad kernel (all taps resident in TMEM)
+    (5, 32, 128, 32, 64, 2),     # ... short maps: several strips per CTA, ring wrap
     (2, 32, 32, 64, 64, 1),      # stride 1
 ]
 
