@@ -148,6 +148,10 @@ int lg_conv2d_transpose_dgrad(const void* dy_big, const float* W, const void* wp
  * Apad = round_up(A,16), Bpad = round_up(B,16), zero padded.  Returns bytes needed when
  * wpack == NULL. */
 int64_t lg_pack_conv_weights(const float* W, void* wpack, int A, int B, void* stream);
+/* The same for n <= LG_PACK_MAX layers in one launch (arrays of host pointers / sizes). */
+#define LG_PACK_MAX 12
+int lg_pack_conv_weights_multi(const float* const* W, void* const* wpack, const int* A, const int* B, int n,
+                               void* stream);
 
 /* db[c] += sum_rows g[row, c]  (bias gradient; rows = N*H*W).  fp32 accumulate. */
 int lg_bias_grad(const void* g, float* db, int64_t rows, int C, int dtype, void* stream);
@@ -217,6 +221,20 @@ int lg_bias_act(float* x, const float* bias, int rows, int cols, int act, void* 
  * weight/(rows*cols) * dBCE/dp * p*(1-p)   (gradient w.r.t. the pre-sigmoid logits). */
 int lg_bce_sigmoid(const float* p, const float* target, float target_const, int rows, int cols,
                    float weight, float* loss_accum, float* dlogit, void* stream);
+/* n <= LG_BCE_MAX such terms in one launch (same arithmetic per item: p [n] probabilities, target tensor or constant,
+ * weight, loss accumulator (+=), optional d(loss)/d(logit) output). */
+#define LG_BCE_MAX 8
+typedef struct lg_bce_item {
+  const float* p;
+  const float* target;   /* NULL: use target_const */
+  float* loss_accum;     /* may be NULL */
+  float* dlogit;         /* may be NULL */
+  float target_const;
+  float weight;
+  int n;                 /* rows * cols */
+  int pad_;
+} lg_bce_item_t;
+int lg_bce_sigmoid_multi(const lg_bce_item_t* items, int n, void* stream);
 
 /* y = tanh output image, t = target image (both activation-typed, n elements).
  * loss_accum[0] += weight * mean|t - y|  (if loss_accum != NULL);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "lg_conv2d_transpose_fprop": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_conv2d_transpose_dgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lg_pack_conv_weights": (_i64, [_vp, _vp, _i, _i, _vp]),
+    "lg_pack_conv_weights_multi": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "lg_bias_grad": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "lg_rowstats": (_i, [_vp, _vp, _i, _i64, _f, _i, _vp]),
     "lg_instnorm_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _i, _i, _vp]),
@@ -52,6 +53,7 @@ SIGNATURES = {
     "lg_dense_heads_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lg_bias_act": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "lg_bce_sigmoid": (_i, [_vp, _vp, _f, _i, _i, _f, _vp, _vp, _vp]),
+    "lg_bce_sigmoid_multi": (_i, [_vp, _i, _vp]),
     "lg_l1_tanh_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _vp, _i, _vp]),
     "lg_adam_advance": (_i, [_vp, _d, _d, _d, _vp]),
     "lg_adam_apply": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp]),
@@ -60,6 +62,15 @@ SIGNATURES = {
     "lg_fid_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
 }
 
+
+
+class BceItem(C.Structure):
+    """lg_bce_item_t"""
+    _fields_ = [("p", _vp), ("target", _vp), ("loss_accum", _vp), ("dlogit", _vp), ("target_const", _f),
+                ("weight", _f), ("n", _i), ("pad_", _i)]
+
+
+PACK_MAX, BCE_MAX = 12, 8
 
 
 class NormBwd(C.Structure):

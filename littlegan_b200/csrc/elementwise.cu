@@ -457,6 +457,74 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   }
 }
 
+// The same for up to LG_PACK_MAX layers in ONE launch (the nine conv layers are re-packed every step: nine ~5 us
+// launches otherwise); a CTA finds its layer by its position in the table of CTA prefix sums.
+struct PackTable {
+  const float* W[LG_PACK_MAX];
+  bf16* Wt[LG_PACK_MAX];
+  bf16* Wf[LG_PACK_MAX];
+  int A[LG_PACK_MAX], B[LG_PACK_MAX], Ap[LG_PACK_MAX], Bp[LG_PACK_MAX];
+  int cta_end[LG_PACK_MAX];          // exclusive prefix sums of (b tiles x a tiles x 25)
+  int n;
+};
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackTable t) {
+  __shared__ float tile[64][65];
+  int l = 0;
+  while (l < t.n - 1 && (int)blockIdx.x >= t.cta_end[l]) ++l;
+  const int local = blockIdx.x - (l ? t.cta_end[l - 1] : 0);
+  const int A = t.A[l], B = t.B[l], Ap = t.Ap[l], Bp = t.Bp[l];
+  const int bt = (Bp + 63) / 64, at = (Ap + 63) / 64;
+  const int tap = local / (bt * at), rem = local - tap * (bt * at);
+  const int a0 = (rem / bt) * 64, b0 = (rem % bt) * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* Wp = t.W[l] + (int64_t)tap * A * B;
+  bf16* Wt = t.Wt[l];
+  bf16* Wf = t.Wf[l];
+  for (int r = ty; r < 64; r += 8) {
+    const int a = a0 + r, b = b0 + 2 * tx;
+    const float v0 = (a < A && b < B) ? Wp[(int64_t)a * B + b] : 0.f;
+    const float v1 = (a < A && b + 1 < B) ? Wp[(int64_t)a * B + b + 1] : 0.f;
+    tile[r][2 * tx] = v0; tile[r][2 * tx + 1] = v1;
+    if (a < Ap && b < Bp)
+      *reinterpret_cast<__nv_bfloat162*>(Wt + ((int64_t)tap * Ap + a) * Bp + b) = __floats2bfloat162_rn(v0, v1);
+  }
+  __syncthreads();
+  for (int r = ty; r < 64; r += 8) {
+    const int b = b0 + r, a = a0 + 2 * tx;
+    if (a < Ap && b < Bp)
+      *reinterpret_cast<__nv_bfloat162*>(Wf + ((int64_t)tap * Bp + b) * Ap + a) =
+          __floats2bfloat162_rn(tile[2 * tx][r], tile[2 * tx + 1][r]);
+  }
+}
+
+// Several Keras-BCE terms in one launch (one CTA per term): the seven loss terms of a train step are 1-CTA kernels
+// whose cost is launch latency.
+struct BceTable {
+  lg_bce_item_t it[LG_BCE_MAX];
+};
+
+__global__ void __launch_bounds__(NT) bce_multi_kernel(const BceTable t) {
+  __shared__ double sh[64];
+  const lg_bce_item_t& q = t.it[blockIdx.x];
+  const float eps = 1e-7f, hi = 1.f - 1e-7f;
+  float s = 0.f;
+  const float scale = q.weight / (float)q.n;
+  for (int i = threadIdx.x; i < q.n; i += NT) {
+    float pr = q.p[i], tg = q.target ? q.target[i] : q.target_const;
+    float pc = fminf(fmaxf(pr, eps), hi);
+    s += -(tg * logf(pc + eps) + (1.f - tg) * logf(1.f - pc + eps));
+    if (q.dlogit) {
+      float d = 0.f;
+      if (pr >= eps && pr <= hi) d = -(tg / (pc + eps) - (1.f - tg) / (1.f - pc + eps));
+      q.dlogit[i] = scale * d * pr * (1.f - pr);
+    }
+  }
+  double a = s, b = 0.0;
+  block_sum2(a, b, sh);
+  if (threadIdx.x == 0 && q.loss_accum) atomicAdd(q.loss_accum, (float)(a * (double)scale));
+}
+
 inline void chunking(int64_t M, int V, int N, int64_t* per_cta, int* chunks) {
   // ~4 vector iterations per thread, rounded so that chunk boundaries stay vector aligned
   int64_t unit = (int64_t)NT * V;
@@ -640,6 +708,18 @@ extern "C" int lg_bce_sigmoid(const float* p, const float* target, float target_
   return LG_OK;
 }
 
+extern "C" int lg_bce_sigmoid_multi(const lg_bce_item_t* items, int n, void* stream) {
+  LG_REQUIRE(items && n > 0 && n <= LG_BCE_MAX, "bad arguments");
+  BceTable t;
+  for (int i = 0; i < n; ++i) {
+    LG_REQUIRE(items[i].p && items[i].n > 0, "bad item");
+    t.it[i] = items[i];
+  }
+  bce_multi_kernel<<<n, NT, 0, (cudaStream_t)stream>>>(t);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
 extern "C" int lg_l1_tanh_bwd(const void* y, const void* t, const void* g_in, void* dpre, int64_t n, float weight,
                               float* loss_accum, int dtype, void* stream) {
   LG_REQUIRE(y && t && n > 0, "bad arguments");
@@ -704,6 +784,25 @@ extern "C" int lg_pad_channels(const void* src, void* dst, int64_t rows, int C, 
     pad_channels_kernel<bf16><<<gsz, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows, C, Cpad);
   else
     pad_channels_kernel<float><<<gsz, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, rows, C, Cpad);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_pack_conv_weights_multi(const float* const* W, void* const* wpack, const int* A, const int* B, int n,
+                                          void* stream) {
+  LG_REQUIRE(W && wpack && A && B && n > 0 && n <= LG_PACK_MAX, "bad arguments");
+  PackTable t;
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    LG_REQUIRE(W[i] && wpack[i] && A[i] > 0 && B[i] > 0, "bad layer");
+    const int Ap = (A[i] + 15) / 16 * 16, Bp = (B[i] + 15) / 16 * 16;
+    t.W[i] = W[i]; t.Wt[i] = (bf16*)wpack[i]; t.Wf[i] = (bf16*)wpack[i] + (int64_t)25 * Ap * Bp;
+    t.A[i] = A[i]; t.B[i] = B[i]; t.Ap[i] = Ap; t.Bp[i] = Bp;
+    total += ((Bp + 63) / 64) * ((Ap + 63) / 64) * 25;
+    t.cta_end[i] = total;
+  }
+  t.n = n;
+  pack_weights_multi_kernel<<<total, 256, 0, (cudaStream_t)stream>>>(t);
   LG_LAUNCH_CHECK();
   return LG_OK;
 }

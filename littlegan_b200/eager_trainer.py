@@ -208,6 +208,7 @@ class EagerTrainer:
         E.refresh_packs(rt, self._conv_layers())
         self.Gd.zero_()
         loss.zero_()
+        rt.begin_step()
         self._prepare_inputs(S)
 
         # ---- forward: G, then D on [new_image ; fake] (eager_trainer.py:134-137)
@@ -218,13 +219,13 @@ class EagerTrainer:
         # ---- losses + gradients w.r.t. the logits (eager_trainer.py:139-140)
         dl_pr_d = rt.empty(2 * B, 1, dtype=f32)
         dl_c_d = rt.zeros(2 * B, a.cond_dim, dtype=f32)          # fake half: no D-loss term on fake_c
-        K.bce_sigmoid(c[:B], S["cond1"], 2.0, l_disc, dl_c_d[:B])
-        K.bce_sigmoid(pr[:B], soft(1.0), 1.0, l_disc, dl_pr_d[:B])
-        K.bce_sigmoid(pr[B:], soft(0.0), 1.0, l_disc, dl_pr_d[B:])
         dl_pr_g = rt.empty(B, 1, dtype=f32)
         dl_c_g = rt.empty(B, a.cond_dim, dtype=f32)
-        K.bce_sigmoid(pr[B:], soft(1.0), 1.0, l_gen, dl_pr_g)
-        K.bce_sigmoid(c[B:], S["cond2"], 1.0, l_gen, dl_c_g)
+        K.bce_sigmoid_multi([(c[:B], S["cond1"], 2.0, l_disc, dl_c_d[:B]),
+                             (pr[:B], soft(1.0), 1.0, l_disc, dl_pr_d[:B]),
+                             (pr[B:], soft(0.0), 1.0, l_disc, dl_pr_d[B:]),
+                             (pr[B:], soft(1.0), 1.0, l_gen, dl_pr_g),
+                             (c[B:], S["cond2"], 1.0, l_gen, dl_c_g)])
 
         # ---- disc_tape.gradient(disc_loss, D weights): both halves, no input gradient (:145)
         g4 = E.disc_heads_backward(rt, D, outs[3], dl_pr_d, dl_c_d, wgrad=True)
@@ -249,8 +250,7 @@ class EagerTrainer:
             apr, ac = E.disc_heads_forward(rt, D, outs2[3])
             dl_pr_a = rt.empty(2 * B, 1, dtype=f32)
             dl_c_a = rt.empty(2 * B, a.cond_dim, dtype=f32)
-            K.bce_sigmoid(apr, soft(1.0), 1.0, l_adj, dl_pr_a)
-            K.bce_sigmoid(ac, S["acond_t"], 1.0, l_adj, dl_c_a)
+            K.bce_sigmoid_multi([(apr, soft(1.0), 1.0, l_adj, dl_pr_a), (ac, S["acond_t"], 1.0, l_adj, dl_c_a)])
             g4 = E.disc_heads_backward(rt, D, outs2[3], dl_pr_a, dl_c_a, wgrad=False)
             g_img = E.encoder_backward(rt, D.encoder, ectx2, g4, wgrad=False, input_grad=True)
             dpre = torch.empty_like(adj)
@@ -272,6 +272,7 @@ class EagerTrainer:
             clip = a.clip_range if (name == "Discriminator" and a.use_clip) else 0.0
             K.adam_apply(self.P[lo:hi], grad, self.M[lo:hi], self.V[lo:hi], self.adam_state[name], b1, b2, 1e-8,
                          clip)
+        rt.end_step()
 
     def _reduce_async(self, name, batch_no):
         """Data parallel: average this optimiser's (active range of the) flat gradient arena over the

@@ -29,6 +29,9 @@ class Runtime:
         # weight-gradient launches run on a side stream: nothing in the backward chain consumes them, so they
         # overlap with the bandwidth-bound norm kernels that follow on the main stream (also inside a captured
         # CUDA graph, where the fork / join become parallel branches)
+        # per-step arena for the small zero-initialised buffers (statistics, reductions, logit gradients): one
+        # memset per step instead of one fill launch per buffer
+        self._zarena, self._zoff, self._zactive = None, 0, False
         self.overlap = bool(getattr(args, "overlap_wgrad", True))
         self._side = None
         self._side_keep = []
@@ -109,7 +112,28 @@ class Runtime:
     def empty(self, *shape, dtype=None):
         return torch.empty(*shape, dtype=dtype or self.act_dtype, device=self.device)
 
+    ZARENA_BYTES = 1 << 20
+
+    def begin_step(self):
+        """Start of a train step: zero the arena (one memset) and hand out zeros() from it until end_step()."""
+        if self._zarena is None:
+            self._zarena = torch.empty(self.ZARENA_BYTES, dtype=torch.uint8, device=self.device)
+        self._zarena.zero_()
+        self._zoff, self._zactive = 0, True
+
+    def end_step(self):
+        self._zactive = False
+
     def zeros(self, *shape, dtype=torch.float64):
+        if self._zactive:
+            n = 1
+            for d in shape:
+                n *= int(d)
+            nbytes = n * torch.empty(0, dtype=dtype).element_size()
+            if self._zoff + nbytes <= self.ZARENA_BYTES:
+                t = self._zarena[self._zoff:self._zoff + nbytes].view(dtype).view(*shape)
+                self._zoff += (nbytes + 255) & ~255
+                return t
         return torch.zeros(*shape, dtype=dtype, device=self.device)
 
 
@@ -163,7 +187,8 @@ def refresh_packs(rt, conv_layers):
         if layer.wpack is None:
             A, B = layer.kernel.shape[2], layer.kernel.shape[3]
             layer.wpack = torch.empty(K.pack_conv_weights_bytes(A, B), dtype=torch.uint8, device=rt.device)
-        K.pack_conv_weights(layer.kernel, layer.wpack)
+    K.pack_conv_weights_multi([layer.kernel for layer in conv_layers], [layer.wpack for layer in conv_layers])
+    for layer in conv_layers:
         A, B = layer.kernel.shape[2], layer.kernel.shape[3]
         A_big = 8 if A <= 8 else A
         if K.fprop_rows_supported(1, 128, 128, A_big, A, B, layer.strides):

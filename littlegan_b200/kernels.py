@@ -203,6 +203,21 @@ def pack_conv_weights(W, wpack):
     check(_lib.load().lg_pack_conv_weights(_p(W), _p(wpack), A, B, _st()), "lg_pack_conv_weights")
 
 
+def pack_conv_weights_multi(Ws, wpacks):
+    """pack_conv_weights for several layers in one launch."""
+    import ctypes
+    lib = _lib.load()
+    for i in range(0, len(Ws), _lib.PACK_MAX):
+        W, P = Ws[i:i + _lib.PACK_MAX], wpacks[i:i + _lib.PACK_MAX]
+        _cuda(*W, *P)
+        n = len(W)
+        wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in W])
+        pp = (ctypes.c_void_p * n)(*[q.data_ptr() for q in P])
+        aa = (ctypes.c_int * n)(*[w.shape[2] for w in W])
+        bb = (ctypes.c_int * n)(*[w.shape[3] for w in W])
+        check(lib.lg_pack_conv_weights_multi(wp, pp, aa, bb, n, _st()), "lg_pack_conv_weights_multi")
+
+
 def bias_grad(g, db):
     _cuda(g, db)
     C = g.shape[-1]
@@ -302,6 +317,21 @@ def bce_sigmoid(p, target, weight, loss_accum, dlogit):
     _cuda(p, tt, loss_accum, dlogit)
     check(_lib.load().lg_bce_sigmoid(_p(p), _p(tt), tc, rows, cols, weight, _p(loss_accum), _p(dlogit), _st()),
           "lg_bce_sigmoid")
+
+
+def bce_sigmoid_multi(terms):
+    """Several bce_sigmoid terms in one launch; terms = [(p, target, weight, loss_accum, dlogit), ...]."""
+    lib = _lib.load()
+    for i in range(0, len(terms), _lib.BCE_MAX):
+        chunk = terms[i:i + _lib.BCE_MAX]
+        items = (_lib.BceItem * len(chunk))()
+        for it, (p, target, weight, loss_accum, dlogit) in zip(items, chunk):
+            tt = target if torch.is_tensor(target) else None
+            _cuda(p, tt, loss_accum, dlogit)
+            it.p, it.target, it.loss_accum, it.dlogit = _p(p), _p(tt), _p(loss_accum), _p(dlogit)
+            it.target_const = 0.0 if tt is not None else float(target)
+            it.weight, it.n = float(weight), p.numel()
+        check(lib.lg_bce_sigmoid_multi(items, len(chunk), _st()), "lg_bce_sigmoid_multi")
 
 
 def l1_tanh_bwd(y, t, g_in, dpre, weight, loss_accum):
