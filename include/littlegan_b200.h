@@ -53,6 +53,11 @@ int lg_tensor_core_path_available(void);
 #define LG_OP_DGRAD 1
 #define LG_OP_WGRAD 2
 int lg_conv2d_tc_supported(int op, int N, int Hb, int Wb, int A, int B, int stride);
+/* CTA pairs (tcgen05 cta_group::2: the two SMs of a TPC share one 256-row MMA tile and each fetches half
+ * of the weight tile) in the generic conv kernels.  mode 0 = never, 1 = when the launch has enough tiles
+ * to fill every TPC (default; LG_TC_PAIRS in the environment sets the initial mode), 2 = whenever the
+ * geometry allows (tests).  Returns the previous mode.  Process-wide, not thread-safe. */
+int lg_set_cta_pairs(int mode);
 
 /* ---- convolution family (replaces TF Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter,
  *      model.py:15,39,86 and their autodiff from eager_trainer.py:145,149,163) -------------- */

@@ -22,6 +22,7 @@ SIGNATURES = {
     "lg_last_error": (C.c_char_p, []),
     "lg_tensor_core_path_available": (_i, []),
     "lg_conv2d_tc_supported": (_i, [_i] * 7),
+    "lg_set_cta_pairs": (_i, [_i]),
     "lg_conv2d_norm_bwd_supported": (_i, [_i] * 7),
     "lg_conv2d_fprop": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "lg_conv2d_fprop_rows_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),

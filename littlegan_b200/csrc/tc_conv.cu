@@ -13,12 +13,13 @@
 // accumulators live in TMEM (double buffered) and are drained by 4 epilogue warps that add the
 // bias, accumulate the per-sample InstanceNorm statistics, apply tanh where asked and store bf16.
 //
-// Persistent: grid = min(#tiles, #SMs); warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue.  The producer and MMA-issue loops are single-thread and latency bound
+// Persistent: grid = min(#tiles, #SMs); warps 0..7 = epilogue, warp 8 = TMA producer, warp 9 = MMA
+// issuer + TMEM owner.  The producer and MMA-issue loops are single-thread and latency bound
 // (~450 cycles per mbarrier round trip measured), so one pipeline stage carries `nsub` k-blocks
 // (up to 64 KB) and the loops use 32-bit shared addresses and loop-invariant descriptor halves.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -30,10 +31,13 @@ namespace {
 
 constexpr int OP_F = 0, OP_T = 1;
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 192;
-// Warp roles: the epilogue owns warps 0-3 (TMEM lane quarter = warp id); the two latency-critical
-// single-thread roles get the HIGHEST warp ids because the SM's warp arbiter favours high ids.
-constexpr int PRODUCER_WARP = 4, MMA_WARP = 5;
+constexpr int NUM_THREADS = 320;
+// Warp roles: the epilogue owns warps 0-7 (TMEM lane quarter = warp id % 4, column half = warp id / 4: a
+// 4-warp epilogue of a 128-column tile lasts about as long as the tile's MMAs and stalls the issuer); the
+// two latency-critical single-thread roles get the HIGHEST warp ids because the SM's warp arbiter favours
+// high ids.
+constexpr int EPI_WARPS = 8;
+constexpr int PRODUCER_WARP = 8, MMA_WARP = 9;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_SUB = 4;
 constexpr int SMEM_BUDGET = 200 * 1024;
@@ -49,6 +53,7 @@ struct TcParams {
   int tilesW, tilesH, tilesN;
   int m_tiles, total_tiles, phases;
   int per_phase, lg_nt, lg_tw, lg_th;   // division-free tile decode (all tile counts are powers of two)
+  int pair;       // 1: CTA pairs (cta_group::2) - a scheduled tile is two neighbouring M tiles, one per CTA
   int a_bytes, sub_bytes, nsub, stage_bytes, stages;
   int act;
   const float* bias;
@@ -68,8 +73,15 @@ template <int OP, int S> __device__ __forceinline__ int tap_d(int ph, int i) {
 
 struct TileCoord { int ph_y, ph_x, nt, n0, i0, j0; };
 
+template <bool CTA2>
+__device__ __forceinline__ void mma(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                    uint32_t idesc, uint32_t accum) {
+  if (CTA2) tc::mma_bf16_lohi_2sm(d, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+  else tc::mma_bf16_lohi(d, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+}
+
 template <int OP, int S>
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int rank = 0) {
   TileCoord c;
   // heavier phases (more taps) first: q = 0 -> (1,1), 1 -> (1,0), 2 -> (0,1), 3 -> (0,0)
   int q = 0;
@@ -78,7 +90,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   if (OP == OP_T && S == 2) { c.ph_y = (q < 2) ? 1 : 0; c.ph_x = (q & 1) ? 0 : 1; }
   else { c.ph_y = 0; c.ph_x = 0; }
   c.nt = r & ((1 << p.lg_nt) - 1);
-  const int mt0 = r >> p.lg_nt;
+  const int mt0 = ((r >> p.lg_nt) << p.pair) | rank;
   const int tw = mt0 & ((1 << p.lg_tw) - 1);
   const int mt1 = mt0 >> p.lg_tw;
   const int th = mt1 & ((1 << p.lg_th) - 1);
@@ -88,7 +100,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
 }
 
 // NB: fuse the InstanceNorm-backward reduction of the layer below into the epilogue (norm_bwd.cuh).
-template <int OP, int S, bool NB>
+// CTA2: CTA pairs.  The two CTAs of a cluster own neighbouring M tiles of the same (phase, channel tile);
+// the even CTA issues 256-row tcgen05.mma.cta_group::2 instructions over both CTAs' shared memory, so each
+// CTA fetches only HALF of the weight tile (the kernels are bound by the L2 -> SM fill rate, not by the
+// tensor pipe).  Each CTA drains its own 128 TMEM lanes.
+template <int OP, int S, bool NB, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                const NormBwdDev nb) {
@@ -103,6 +119,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* sbias = reinterpret_cast<float*>(bars + 32);     // n_tiles * NT floats (<= 512)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CTA2 ? (int)tc::cluster_ctarank() : 0;
+  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t tmem_cols = (2 * p.NT <= 32) ? 32 : (2 * p.NT <= 64) ? 64 : (2 * p.NT <= 128) ? 128
                              : (2 * p.NT <= 256) ? 256 : 512;
 
@@ -110,13 +129,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
     for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], CTA2 ? 2 * EPI_WARPS : EPI_WARPS); }
     tc::fence_barrier_init();
   }
-  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == MMA_WARP) {
+    if (CTA2) tc::tmem_alloc_2sm(tmem_slot, tmem_cols);
+    else tc::tmem_alloc(tmem_slot, tmem_cols);
+  }
   for (int i = threadIdx.x; i < p.n_tiles * p.NT; i += NUM_THREADS) sbias[i] = (p.bias && i < p.Nch) ? p.bias[i] : 0.f;
   tc::fence_before_sync();
-  __syncthreads();
+  if (CTA2) tc::cluster_sync_all(); else __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -131,26 +153,35 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== TMA producer =====================================
     if (tc::elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile<OP, S>(p, t);
+      // pairs: both CTAs' loads complete on the LEADER's full barrier, which the leader arms for both
+      const uint32_t full_tma = CTA2 ? tc::mapa(full_u32, 0) : full_u32;
+      for (int t = tile0; t < p.total_tiles; t += tstep) {
+        const TileCoord c = decode_tile<OP, S>(p, t, rank);
         const int nty = taps_n<OP, S>(c.ph_y), ntx = taps_n<OP, S>(c.ph_x);
         const int num_kb = nty * ntx * kc_per_tap;
         const int bx = (OP == OP_F) ? S * c.j0 : c.j0, by = (OP == OP_F) ? S * c.i0 : c.i0;
-        const int n_off = c.nt * p.NT;
+        const int n_off = c.nt * p.NT + (CTA2 ? rank * (p.NT >> 1) : 0);
         int iy = 0, ix = 0, kc = 0;
         for (int kb0 = 0; kb0 < num_kb; kb0 += nsub) {
           const int nvalid = min(nsub, num_kb - kb0);
-          const uint32_t fb = full_u32 + (uint32_t)stage * 8u;
+          const uint32_t fb = full_tma + (uint32_t)stage * 8u;
           uint32_t sa = smem_u32 + (uint32_t)stage * stage_bytes_u;
           tc::mbar_wait_addr(empty_u32 + (uint32_t)stage * 8u, phase ^ 1);
-          tc::mbar_expect_tx_addr(fb, (uint32_t)nvalid * sub_bytes_u);
+          if (!CTA2) tc::mbar_expect_tx_addr(fb, (uint32_t)nvalid * sub_bytes_u);
+          else if (rank == 0) tc::mbar_expect_tx_addr(full_u32 + (uint32_t)stage * 8u, 2u * (uint32_t)nvalid * sub_bytes_u);
 #pragma unroll
           for (int j = 0; j < MAX_SUB; ++j) {
             if (j < nvalid) {
               const int tap = tap_k<OP, S>(c.ph_y, iy) * 5 + tap_k<OP, S>(c.ph_x, ix);
-              tc::tma_load_4d_addr(sa, &tmA, fb, kc * KCc, bx + tap_d<OP, S>(c.ph_x, ix), by + tap_d<OP, S>(c.ph_y, iy),
-                                   c.n0);
-              tc::tma_load_3d_addr(sa + a_bytes_u, &tmB, fb, kc * KCc, n_off, tap);
+              if (CTA2) {
+                tc::tma_load_4d_2sm(sa, &tmA, fb, kc * KCc, bx + tap_d<OP, S>(c.ph_x, ix),
+                                    by + tap_d<OP, S>(c.ph_y, iy), c.n0);
+                tc::tma_load_3d_2sm(sa + a_bytes_u, &tmB, fb, kc * KCc, n_off, tap);
+              } else {
+                tc::tma_load_4d_addr(sa, &tmA, fb, kc * KCc, bx + tap_d<OP, S>(c.ph_x, ix),
+                                     by + tap_d<OP, S>(c.ph_y, iy), c.n0);
+                tc::tma_load_3d_addr(sa + a_bytes_u, &tmB, fb, kc * KCc, n_off, tap);
+              }
               sa += sub_bytes_u;
               if (++kc == kc_per_tap) { kc = 0; if (++ix == ntx) { ix = 0; ++iy; } }
             }
@@ -161,8 +192,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == MMA_WARP) {
     // ===================================== MMA issuer =======================================
-    if (tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc(TILE_M, p.NT, 0, 0);
+    if ((!CTA2 || rank == 0) && tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc(CTA2 ? 2 * TILE_M : TILE_M, p.NT, 0, 0);
       const uint32_t layout = (KCc == 64) ? 2u : (KCc == 32) ? 4u : 6u;     // SWIZZLE_128B / 64B / 32B
       const uint32_t sbo = 8u * (uint32_t)KCc * 2u;                        // 8 rows of KC bf16
       // K-major swizzled descriptor: lo = start>>4 | LBO(16 B)<<16 ; hi = SBO>>4 | version<<14 | layout<<29
@@ -171,7 +202,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stage_units = stage_bytes_u >> 4, sub_units = sub_bytes_u >> 4, a_units = a_bytes_u >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < p.total_tiles; t += tstep) {
         const TileCoord c = decode_tile<OP, S>(p, t);
         const int num_kb = taps_n<OP, S>(c.ph_y) * taps_n<OP, S>(c.ph_x) * kc_per_tap;
         tc::mbar_wait_addr(tc::smem_u32(&tempty[acc]), acc_phase ^ 1);
@@ -189,20 +220,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t b_lo = a_lo + a_units;
               if (KCc == 64) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
+                for (int k = 0; k < 4; ++k) { mma<CTA2>(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
               } else if (KCc == 32) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) { tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
+                for (int k = 0; k < 2; ++k) { mma<CTA2>(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum); accum = 1; }
               } else {
-                tc::mma_bf16_lohi(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, accum); accum = 1;
+                mma<CTA2>(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, accum); accum = 1;
               }
               a_lo += sub_units;
             }
           }
-          tc::mma_commit_addr(empty_u32 + (uint32_t)stage * 8u);   // frees the smem slot when the MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+          if (CTA2) tc::mma_commit_2sm(empty_u32 + (uint32_t)stage * 8u);
+          else tc::mma_commit_addr(empty_u32 + (uint32_t)stage * 8u);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&tfull[acc]);                     // accumulator complete -> epilogue
+        if (CTA2) tc::mma_commit_2sm(tc::smem_u32(&tfull[acc]));   // accumulator complete -> both epilogues
+        else tc::mma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -212,9 +246,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;                       // row of the tile == TMEM lane
     const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
     const bool vec_ok = (p.Nch & 7) == 0;
+    // column range of this warp: half of the tile when that is a whole number of 16-column chunks
+    const int half = warp >> 2;
+    const bool split = (p.NT & 31) == 0;
+    const int ncol = split ? (p.NT >> 1) : (half == 0 ? p.NT : 0);
+    const int col0 = split ? half * ncol : 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord c = decode_tile<OP, S>(p, t);
+    const uint32_t tempty_leader = CTA2 ? tc::mapa(tc::smem_u32(tempty), 0) : 0u;
+    for (int t = tile0; t < p.total_tiles; t += tstep) {
+      const TileCoord c = decode_tile<OP, S>(p, t, rank);
       const int n = c.n0 + bn, i = c.i0 + bh, j = c.j0 + bw;
       const bool valid = n < p.Nimg;
       int64_t off;
@@ -229,20 +269,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (NB) {
         // z row of this output position: first 64 channels into registers, the rest of the row towards L2,
         // all in flight while the MMAs of this tile still run
-        zrow = nb.z + off + ch0;
+        zrow = nb.z + off + ch0 + col0;
         if (valid) coef = nb_coef(nb, n);
-        nb_load(zc, zrow, p.NT >> 4, valid);
-        if (p.NT > 64) nb_prefetch_l2(zrow + 64, (p.NT - 64) * 2, valid);
+        nb_load(zc, zrow, ncol >> 4, valid);
+        if (ncol > 64) nb_prefetch_l2(zrow + 64, (ncol - 64) * 2, valid);
         // the NEXT tile's z row towards L2 now: a whole tile period ahead of its use (the loads above miss
         // to HBM only for the first tile of a CTA)
-        const int tn = t + gridDim.x;
+        const int tn = t + tstep;
         if (tn < p.total_tiles) {
-          const TileCoord cn = decode_tile<OP, S>(p, tn);
+          const TileCoord cn = decode_tile<OP, S>(p, tn, rank);
           const int n2 = cn.n0 + bn, i2 = cn.i0 + bh, j2 = cn.j0 + bw;
           int64_t off2;
           if (OP == OP_F) off2 = (((int64_t)n2 * p.Hs + i2) * p.Ws + j2) * p.Nch;
           else off2 = (((int64_t)n2 * p.Hb + (S * i2 + cn.ph_y)) * p.Wb + (S * j2 + cn.ph_x)) * p.Nch;
-          nb_prefetch_l2(nb.z + off2 + cn.nt * p.NT, p.NT * 2, n2 < p.Nimg);
+          nb_prefetch_l2(nb.z + off2 + cn.nt * p.NT + col0, ncol * 2, n2 < p.Nimg);
         }
       }
       tc::mbar_wait(&tfull[acc], acc_phase);
@@ -251,13 +291,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
       if constexpr (NB) {
         // s1 / s2 carry (sum dy, sum dy*xhat); the host guarantees Nch % 16 == 0, no activation
-        for (int sc = 0; sc < p.NT; sc += 64) {
+        for (int sc = 0; sc < ncol; sc += 64) {
           NormBwdZ zn;
-          if (sc + 64 < p.NT) nb_load(zn, zrow + sc + 64, (p.NT - sc - 64) >> 4, valid);
+          if (sc + 64 < ncol) nb_load(zn, zrow + sc + 64, (ncol - sc - 64) >> 4, valid);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const int cb = sc + 16 * c;
-            if (cb < p.NT) {
+            const int cb = col0 + sc + 16 * c;
+            if (cb < col0 + ncol) {
               float v[16];
               tc::tmem_ld16(taddr + cb, v);
 #pragma unroll
@@ -271,10 +311,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          if (sc + 64 < p.NT) zc = zn;
+          if (sc + 64 < ncol) zc = zn;
         }
       } else {
-      for (int cb = 0; cb < p.NT; cb += 16) {
+      for (int cb = col0; cb < col0 + ncol; cb += 16) {
         float v[16];
         tc::tmem_ld16(taddr + cb, v);
         const int chb = ch0 + cb;
@@ -308,7 +348,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16)
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CTA2) tc::mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
+        else tc::mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
       double* sums = NB ? nb.red : p.stats;
@@ -325,10 +368,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc::fence_before_sync();
-  __syncthreads();
+  if (CTA2) tc::cluster_sync_all(); else __syncthreads();
   if (warp == MMA_WARP) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, tmem_cols);
+    if (CTA2) tc::tmem_dealloc_2sm(tmem_base, tmem_cols);
+    else tc::tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -341,7 +385,7 @@ using tc_host::is_pow2;
 using tc_host::encode_act_map;
 
 // Geometry shared by the support query and the launcher.  Returns false if not covered.
-bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
+bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p, int pair_mode = 0) {
   if (s != 1 && s != 2) return false;
   const int Hs = Hb / s, Ws = Wb / s;
   if (!is_pow2(Hs) || !is_pow2(Ws) || Ws > 128 || Hs * Ws < 32) return false;
@@ -361,13 +405,16 @@ bool plan(int op, int Nimg, int Hb, int Wb, int A, int B, int s, TcParams* p) {
   p->tilesW = Ws / p->BW; p->tilesH = Hs / p->BH; p->tilesN = (Nimg + p->BN - 1) / p->BN;
   p->m_tiles = p->tilesW * p->tilesH * p->tilesN;
   p->phases = (op == OP_T) ? s * s : 1;
-  p->total_tiles = p->m_tiles * p->n_tiles * p->phases;
-  p->per_phase = p->m_tiles * p->n_tiles;
+  // CTA pairs need an even number of M tiles and enough pair tiles to fill the 74 TPCs
+  p->pair = (pair_mode > 0 && p->m_tiles % 2 == 0 && p->NT % 16 == 0 &&
+             (pair_mode == 2 || (p->m_tiles / 2) * n_tiles * p->phases >= lg_num_sms() / 2)) ? 1 : 0;
+  p->per_phase = (p->m_tiles >> p->pair) * p->n_tiles;
+  p->total_tiles = p->per_phase * p->phases;
   auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
   if (!is_pow2(p->n_tiles) || !is_pow2(p->tilesW) || !is_pow2(p->tilesH)) return false;
   p->lg_nt = lg2(p->n_tiles); p->lg_tw = lg2(p->tilesW); p->lg_th = lg2(p->tilesH);
   p->a_bytes = TILE_M * p->KC * 2;
-  p->sub_bytes = p->a_bytes + p->NT * p->KC * 2;
+  p->sub_bytes = p->a_bytes + (p->NT >> p->pair) * p->KC * 2;
   // k-blocks per pipeline stage: amortise the ~450-cycle mbarrier round trip over >= ~512 MMA cycles
   int nsub = 65536 / p->sub_bytes;
   if (nsub > MAX_SUB) nsub = MAX_SUB;
@@ -405,18 +452,44 @@ void launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParam
                    cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_conv_kernel<OP, S, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_conv_kernel<OP, S, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_conv_kernel<OP, S, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
+  if (p.pair) {
+    // one CTA pair (cluster of 2 = the two SMs of a TPC) per pair tile, persistent over the 74 TPCs
+    const int npairs = p.total_tiles < lg_num_sms() / 2 ? p.total_tiles : lg_num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * npairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes(p);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, tc_conv_kernel<OP, S, NB, true>, tmA, tmB, p, nb);
+    return;
+  }
   const int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
-  tc_conv_kernel<OP, S, NB><<<grid, NUM_THREADS, smem_bytes(p), st>>>(tmA, tmB, p, nb);
+  tc_conv_kernel<OP, S, NB, false><<<grid, NUM_THREADS, smem_bytes(p), st>>>(tmA, tmB, p, nb);
+}
+
+// 0 = single-CTA tiles only, 1 = pairs when the launch fills every TPC, 2 = pairs whenever possible
+int g_pair_mode = -1;
+int pair_mode() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("LG_TC_PAIRS");
+    g_pair_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return g_pair_mode;
 }
 
 template <int OP>
 int launch_tc(const void* act_in, const void* wpack, const float* bias, void* out, double* stats, int Nimg, int Hb,
               int Wb, int A, int B, int s, int act, const lg_norm_bwd_t* nbh, cudaStream_t st) {
   TcParams p;
-  if (!plan(OP, Nimg, Hb, Wb, A, B, s, &p)) {
+  if (!plan(OP, Nimg, Hb, Wb, A, B, s, &p, pair_mode())) {
     lg_set_error("tcgen05 path: unsupported geometry");
     return LG_ERR_UNSUPPORTED;
   }
@@ -439,11 +512,11 @@ int launch_tc(const void* act_in, const void* wpack, const float* bias, void* ou
   if (OP == OP_F) {
     e = encode_act_map(&tmA, act_in, Nimg, Hb, Wb, A, p.KC, p.BW, p.BH, p.BN, s, sw);
     if (e) return e;
-    e = encode_w_map(&tmB, wf, Bp, Ap, p.KC, p.NT, sw);
+    e = encode_w_map(&tmB, wf, Bp, Ap, p.KC, p.NT >> p.pair, sw);
   } else {
     e = encode_act_map(&tmA, act_in, Nimg, p.Hs, p.Ws, B, p.KC, p.BW, p.BH, p.BN, 1, sw);
     if (e) return e;
-    e = encode_w_map(&tmB, wt, Ap, Bp, p.KC, p.NT, sw);
+    e = encode_w_map(&tmB, wt, Ap, Bp, p.KC, p.NT >> p.pair, sw);
   }
   if (e) return e;
   if (nbh != nullptr) {
@@ -459,6 +532,12 @@ int launch_tc(const void* act_in, const void* wpack, const float* bias, void* ou
 }  // namespace
 
 int lg_tc_wgrad_supported(int Nimg, int Hb, int Wb, int A, int B, int s);   // tc_wgrad.cu
+
+extern "C" int lg_set_cta_pairs(int mode) {
+  const int prev = pair_mode();
+  if (mode >= 0 && mode <= 2) g_pair_mode = mode;
+  return prev;
+}
 
 int lg_tc_supported(int op, int Hb, int Wb, int A, int B, int s, int N) {
   if (op != LG_OP_DGRAD && lg_tc_cin3_supported(N, Hb, Wb, A, B, s)) return 1;

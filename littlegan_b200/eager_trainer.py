@@ -76,6 +76,7 @@ class EagerTrainer:
         self._pool = None
         self._noise_gen = None
         self._comm_stream = None
+        self._chain_streams = {}
         if getattr(args, "result_dir", None) and getattr(args, "init_dirs", False):
             self._init_dir()
 
@@ -227,10 +228,25 @@ class EagerTrainer:
                              (pr[B:], soft(1.0), 1.0, l_gen, dl_pr_g),
                              (c[B:], S["cond2"], 1.0, l_gen, dl_c_g)])
 
+        # From here on the step is three chains that depend only on the forward above and on the (read-only
+        # until Adam) weights: the D-loss backward, the G-loss backward and the whole adjuster sub-step.  They
+        # run on separate streams - parallel branches of the captured graph - so that the HBM-bound norm / loss
+        # / dense kernels of one chain execute under the L2- and tensor-bound conv kernels of another.  Every
+        # chain allocates its temporaries on its own stream (the caching allocator never hands a block to
+        # another stream), and the tensors chains share stay referenced until the join below.
+        main = torch.cuda.current_stream()
+        sD, sA = self._chain_stream("D", main), (self._chain_stream("A", main) if adj_on else None)
+
         # ---- disc_tape.gradient(disc_loss, D weights): both halves, no input gradient (:145)
-        g4 = E.disc_heads_backward(rt, D, outs[3], dl_pr_d, dl_c_d, wgrad=True)
-        E.encoder_backward(rt, D.encoder, ectx, g4, wgrad=True, input_grad=False)
-        self._reduce_async("Discriminator", batch_no)        # overlaps with the G backward + adjuster step
+        with torch.cuda.stream(sD):
+            g4d = E.disc_heads_backward(rt, D, outs[3], dl_pr_d, dl_c_d, wgrad=True)
+            E.encoder_backward(rt, D.encoder, ectx, g4d, wgrad=True, input_grad=False)
+            self._reduce_async("Discriminator", batch_no)    # overlaps with the G backward + adjuster step
+
+        # ---- adjuster sub-step on 2B samples (eager_trainer.py:152-164)
+        if adj_on:
+            with torch.cuda.stream(sA):
+                self._adjuster_chain(S, batch_no)
 
         # ---- gen_tape.gradient(gen_loss, G weights): dgrad-only through D(fake), then G (:149)
         ectx_f = [(x[B:], z[B:], st[B:], None) for (x, z, st, _) in ectx]
@@ -240,28 +256,13 @@ class EagerTrainer:
         K.l1_tanh_bwd(fake, S["img2"], g_img, dpre, a.l1_lambda, l_gen)
         g = E.generator_tail_backward(rt, G.decoder, G.conv, g_dctx, g_x4, dpre, wgrad=True)
         E.head_backward(rt, G.dense, G.norm, g_hctx, g)
-        self._reduce_async("Generator", batch_no)             # overlaps with the adjuster step
+        self._reduce_async("Generator", batch_no)
 
-        # ---- adjuster sub-step on 2B samples (eager_trainer.py:152-164)
+        main.wait_stream(sD)
         if adj_on:
-            S["aimg"][B:].copy_(fake)
-            adj, (a_hctx, a_dctx, a_x4) = A.forward_ctx(S["aimg"], S["acond_in"])
-            outs2, ectx2 = E.encoder_forward(rt, D.encoder, adj)
-            apr, ac = E.disc_heads_forward(rt, D, outs2[3])
-            dl_pr_a = rt.empty(2 * B, 1, dtype=f32)
-            dl_c_a = rt.empty(2 * B, a.cond_dim, dtype=f32)
-            K.bce_sigmoid_multi([(apr, soft(1.0), 1.0, l_adj, dl_pr_a), (ac, S["acond_t"], 1.0, l_adj, dl_c_a)])
-            g4 = E.disc_heads_backward(rt, D, outs2[3], dl_pr_a, dl_c_a, wgrad=False)
-            g_img = E.encoder_backward(rt, D.encoder, ectx2, g4, wgrad=False, input_grad=True)
-            dpre = torch.empty_like(adj)
-            K.l1_tanh_bwd(adj, S["aimg_t"], g_img, dpre, a.l1_lambda, l_adj)
-            g = E.generator_tail_backward(rt, A.decoder, A.conv, a_dctx, a_x4, dpre, wgrad=False)
-            E.head_backward(rt, A.dense, A.norm, a_hctx, g)
-            S["adj"] = adj
+            main.wait_stream(sA)
 
         # ---- apply: A (if trained), D, G (eager_trainer.py:164-168); D grads value-clipped (:146-148)
-        if adj_on:
-            self._reduce_async("Adjuster", batch_no)
         if _dist() is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)   # join the gradient all-reduces
         for name in (["Adjuster"] if adj_on else []) + ["Discriminator", "Generator"]:
@@ -273,6 +274,41 @@ class EagerTrainer:
             K.adam_apply(self.P[lo:hi], grad, self.M[lo:hi], self.V[lo:hi], self.adam_state[name], b1, b2, 1e-8,
                          clip)
         rt.end_step()
+
+    def _chain_stream(self, name, main):
+        """Stream of one independent chain of the step, ordered after everything issued so far on `main`."""
+        if not bool(getattr(self.args, "overlap_chains", True)):
+            return main
+        s = self._chain_streams.get(name)
+        if s is None:
+            s = self._chain_streams[name] = torch.cuda.Stream()
+        s.wait_stream(main)
+        return s
+
+    def _adjuster_chain(self, S, batch_no):
+        """eager_trainer.py:152-164 on the current stream: forward A on [image ; fake], D on the result, the
+        gradient of adj_loss w.r.t. the adjuster's own dense + norm (dgrad-only through D and the decoder)."""
+        a, rt = self.args, self.rt
+        B = a.batch_size
+        D, A = self.discriminator, self.adjuster
+        f32 = torch.float32
+        l_adj = S["loss"][2:3]
+        fake = S["dimg"][B:]
+        S["aimg"][B:].copy_(fake)
+        adj, (a_hctx, a_dctx, a_x4) = A.forward_ctx(S["aimg"], S["acond_in"])
+        outs2, ectx2 = E.encoder_forward(rt, D.encoder, adj)
+        apr, ac = E.disc_heads_forward(rt, D, outs2[3])
+        dl_pr_a = rt.empty(2 * B, 1, dtype=f32)
+        dl_c_a = rt.empty(2 * B, a.cond_dim, dtype=f32)
+        K.bce_sigmoid_multi([(apr, soft(1.0), 1.0, l_adj, dl_pr_a), (ac, S["acond_t"], 1.0, l_adj, dl_c_a)])
+        g4 = E.disc_heads_backward(rt, D, outs2[3], dl_pr_a, dl_c_a, wgrad=False)
+        g_img = E.encoder_backward(rt, D.encoder, ectx2, g4, wgrad=False, input_grad=True)
+        dpre = torch.empty_like(adj)
+        K.l1_tanh_bwd(adj, S["aimg_t"], g_img, dpre, a.l1_lambda, l_adj)
+        g = E.generator_tail_backward(rt, A.decoder, A.conv, a_dctx, a_x4, dpre, wgrad=False)
+        E.head_backward(rt, A.dense, A.norm, a_hctx, g)
+        S["adj"] = adj
+        self._reduce_async("Adjuster", batch_no)
 
     def _reduce_async(self, name, batch_no):
         """Data parallel: average this optimiser's (active range of the) flat gradient arena over the

@@ -33,8 +33,9 @@ class Runtime:
         # memset per step instead of one fill launch per buffer
         self._zarena, self._zoff, self._zactive = None, 0, False
         self.overlap = bool(getattr(args, "overlap_wgrad", True))
-        self._side = None
-        self._side_keep = []
+        # one side stream per launching stream: the train step runs its independent backward chains on
+        # separate streams (EagerTrainer._step_body), each with its own weight-gradient branch
+        self._sides = {}
 
     def use_tc(self, op, N, Hb, Wb, A, B, s):
         if not self.want_tc:
@@ -86,19 +87,22 @@ class Runtime:
         if not self.overlap:
             fn()
             return
-        if self._side is None:
-            self._side = torch.cuda.Stream()
         main = torch.cuda.current_stream()
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
+        ent = self._sides.get(main.cuda_stream)
+        if ent is None:
+            ent = self._sides[main.cuda_stream] = [torch.cuda.Stream(), []]
+        ent[0].wait_stream(main)
+        with torch.cuda.stream(ent[0]):
             fn()
-        self._side_keep.append(keep)
+        ent[1].append(keep)
 
     def join_side(self):
-        """Make the current stream wait for the side-stream launches (before their results are consumed)."""
-        if self._side_keep:
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._side_keep = []
+        """Make the current stream wait for its side-stream launches (before their results are consumed)."""
+        main = torch.cuda.current_stream()
+        ent = self._sides.get(main.cuda_stream)
+        if ent is not None and ent[1]:
+            main.wait_stream(ent[0])
+            ent[1] = []
 
     def heads_workspace(self, N):
         """Scratch of the fused discriminator-heads forward (self-cleaning, allocated once per size)."""

@@ -61,6 +61,11 @@ def tc_available():
     return bool(_lib.load().lg_tensor_core_path_available())
 
 
+def set_cta_pairs(mode):
+    """0 never / 1 auto / 2 always use CTA pairs (cta_group::2) in the generic conv kernels; returns the old mode."""
+    return _lib.load().lg_set_cta_pairs(int(mode))
+
+
 # ------------------------------------------------------------------------------------------- conv
 def norm_bwd_supported(op, N, Hb, Wb, A, B, stride):
     return bool(_lib.load().lg_conv2d_norm_bwd_supported(op, N, Hb, Wb, A, B, stride))

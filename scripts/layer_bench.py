@@ -1,5 +1,5 @@
 """Per-layer timing of the conv-family kernels (CUDA events, L2 flushed between launches).
-usage: python scripts/layer_bench.py [batch] [filter-substring]"""
+usage: python scripts/layer_bench.py [batch] [filter-substring] [cta-pair mode]"""
 import sys
 sys.path.insert(0, ".")
 import torch
@@ -7,6 +7,8 @@ from littlegan_b200 import kernels as K
 
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 flt = sys.argv[2] if len(sys.argv) > 2 else ""
+if len(sys.argv) > 3:       # CTA-pair mode of the generic kernels: 0 never, 1 auto, 2 always
+    K.set_cta_pairs(int(sys.argv[3]))
 # name, Hb, A, B, stride   (big map Hb x Hb x A  <->  small map Hb/s x Hb/s x B)
 LAYERS = [("enc1", 128, 3, 64, 2), ("enc2", 64, 64, 128, 2), ("enc3", 32, 128, 256, 2), ("enc4", 16, 256, 384, 2),
           ("dec4", 128, 32, 64, 2), ("final", 128, 3, 32, 1)]

@@ -335,6 +335,25 @@ def test_tc_dgrad(geom):
     assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
 
 
+@pytest.fixture
+def forced_cta_pairs():
+    """Run the generic tcgen05 conv kernels as CTA pairs (cta_group::2) even on these few-tile shapes."""
+    from littlegan_b200 import kernels as K
+    prev = K.set_cta_pairs(2)
+    yield
+    K.set_cta_pairs(prev)
+
+
+@pytest.mark.parametrize("geom", TC_F + [(8, 32, 32, 128, 256, 2), (64, 16, 16, 256, 384, 2)])
+def test_tc_fprop_cta_pairs(geom, forced_cta_pairs):
+    test_tc_fprop(geom)
+
+
+@pytest.mark.parametrize("geom", TC_T + [(8, 32, 32, 128, 256, 2, 0), (64, 16, 16, 256, 384, 2, 0)])
+def test_tc_dgrad_cta_pairs(geom, forced_cta_pairs):
+    test_tc_dgrad(geom)
+
+
 @pytest.mark.parametrize("geom", [(3, 128, 128, 3, 64, 2), (2, 128, 128, 3, 32, 1)])
 def test_tc_three_channel_layers_via_padding(geom):
     """enc1 fprop / wgrad and the final conv's input-gradient (fprop, stride 1) with the image padded
@@ -465,6 +484,11 @@ def test_tc_fused_norm_backward_epilogue(op, geom):
     assert rel_err(dgam, dg_ref) < 2e-3 and rel_err(dbet, db_ref) < 2e-3
     if dbias is not None:      # sums of 10^3..10^4 terms built from the bf16-rounded dy, with cancellation
         assert rel_err(dbias, dz_ref.reshape(-1, C).sum(0)) < 1e-2
+
+
+@pytest.mark.parametrize("op,geom", NB_CASES)
+def test_tc_fused_norm_backward_epilogue_cta_pairs(op, geom, forced_cta_pairs):
+    test_tc_fused_norm_backward_epilogue(op, geom)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
