@@ -214,6 +214,21 @@ class EagerTrainer:
 
         # ---- forward: G, then D on [new_image ; fake] (eager_trainer.py:134-137)
         fake, (g_hctx, g_dctx, g_x4) = G.forward_ctx(S["noise"], S["cond2"], out=S["dimg"][B:])
+
+        # The step is three chains that depend only on the forward pass and on the (read-only until Adam)
+        # weights: the D-loss backward, the G-loss backward and the whole adjuster sub-step.  They run on
+        # separate streams - parallel branches of the captured graph - so that the HBM-bound norm / loss / dense
+        # kernels of one chain execute under the L2- and tensor-bound conv kernels of another.  Every chain
+        # allocates its temporaries on its own stream (the caching allocator never hands a block to another
+        # stream), and the tensors chains share stay referenced until the join below.
+        # The adjuster sub-step (eager_trainer.py:152-164) is almost half of the step's conv work and needs
+        # only `fake`: it forks first, on a high-priority stream, and the other chains fill in around it.
+        main = torch.cuda.current_stream()
+        sA = self._chain_stream("A", main, high=True) if adj_on else None
+        if adj_on:
+            with torch.cuda.stream(sA):
+                self._adjuster_chain(S, batch_no)
+
         outs, ectx = E.encoder_forward(rt, D.encoder, S["dimg"])
         pr, c = E.disc_heads_forward(rt, D, outs[3])
 
@@ -228,25 +243,12 @@ class EagerTrainer:
                              (pr[B:], soft(1.0), 1.0, l_gen, dl_pr_g),
                              (c[B:], S["cond2"], 1.0, l_gen, dl_c_g)])
 
-        # From here on the step is three chains that depend only on the forward above and on the (read-only
-        # until Adam) weights: the D-loss backward, the G-loss backward and the whole adjuster sub-step.  They
-        # run on separate streams - parallel branches of the captured graph - so that the HBM-bound norm / loss
-        # / dense kernels of one chain execute under the L2- and tensor-bound conv kernels of another.  Every
-        # chain allocates its temporaries on its own stream (the caching allocator never hands a block to
-        # another stream), and the tensors chains share stay referenced until the join below.
-        main = torch.cuda.current_stream()
-        sD, sA = self._chain_stream("D", main), (self._chain_stream("A", main) if adj_on else None)
-
         # ---- disc_tape.gradient(disc_loss, D weights): both halves, no input gradient (:145)
+        sD = self._chain_stream("D", main)
         with torch.cuda.stream(sD):
             g4d = E.disc_heads_backward(rt, D, outs[3], dl_pr_d, dl_c_d, wgrad=True)
             E.encoder_backward(rt, D.encoder, ectx, g4d, wgrad=True, input_grad=False)
             self._reduce_async("Discriminator", batch_no)    # overlaps with the G backward + adjuster step
-
-        # ---- adjuster sub-step on 2B samples (eager_trainer.py:152-164)
-        if adj_on:
-            with torch.cuda.stream(sA):
-                self._adjuster_chain(S, batch_no)
 
         # ---- gen_tape.gradient(gen_loss, G weights): dgrad-only through D(fake), then G (:149)
         ectx_f = [(x[B:], z[B:], st[B:], None) for (x, z, st, _) in ectx]
@@ -275,13 +277,13 @@ class EagerTrainer:
                          clip)
         rt.end_step()
 
-    def _chain_stream(self, name, main):
+    def _chain_stream(self, name, main, high=False):
         """Stream of one independent chain of the step, ordered after everything issued so far on `main`."""
         if not bool(getattr(self.args, "overlap_chains", True)):
             return main
         s = self._chain_streams.get(name)
         if s is None:
-            s = self._chain_streams[name] = torch.cuda.Stream()
+            s = self._chain_streams[name] = torch.cuda.Stream(priority=-1 if high else 0)
         s.wait_stream(main)
         return s
 

@@ -105,12 +105,14 @@ class Runtime:
             ent[1] = []
 
     def heads_workspace(self, N):
-        """Scratch of the fused discriminator-heads forward (self-cleaning, allocated once per size)."""
+        """Scratch of the fused discriminator-heads forward (self-cleaning, allocated once per size and per
+        launching stream: two chains of the train step may run the heads at the same time)."""
         if self._heads_ws is None:
             self._heads_ws = {}                 # never freed: captured CUDA graphs hold the pointers
-        ws = self._heads_ws.get(N)
+        key = (N, torch.cuda.current_stream().cuda_stream)
+        ws = self._heads_ws.get(key)
         if ws is None:
-            ws = self._heads_ws[N] = K.dense_heads_workspace(N, self.device)
+            ws = self._heads_ws[key] = K.dense_heads_workspace(N, self.device)
         return ws
 
     def empty(self, *shape, dtype=None):
