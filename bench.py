@@ -229,12 +229,18 @@ def run_product(a):
     ms_dev = e0.elapsed_time(e1) / a.steps
 
     # ---- end to end through the public API, host batches, loss read-back every step
+    # (the loss scalars of step i are read on the host right after step i+1 has been submitted: every step's
+    # result is read inside the timed region, without draining the GPU between steps)
     barrier()
     t0 = time.perf_counter()
+    prev = None
     for _ in range(a.steps):
         b += 1
         res = trainer._train_step(b, it)
-        losses = (float(res[3]), float(res[4]), float(res[5]))
+        if prev is not None:
+            losses = (float(prev[3]), float(prev[4]), float(prev[5]))
+        prev = res
+    losses = (float(prev[3]), float(prev[4]), float(prev[5]))
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / a.steps
     clocks = sampler.stop() if rank == 0 else None

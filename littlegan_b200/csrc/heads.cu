@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(HT) heads_fwd_kernel(const TF* __restrict__ fe
     }
   }
   // last CTA: bias + activation, write the two outputs, leave the workspace zeroed for the next call
-  __threadfence();
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");     // release of this thread's reductions (lighter than fence.sc)
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(counter, 1u);
@@ -177,16 +177,26 @@ __global__ void __launch_bounds__(HT) heads_fwd_kernel(const TF* __restrict__ fe
   __syncthreads();
   if (!last) return;
   __threadfence();
-  for (int e = threadIdx.x; e < N * UP; e += HT) {
-    const int n = e / UP, u = e - n * UP;
-    if (u >= U) continue;
-    float v = __ldcg(&ws_acc[e]);
-    ws_acc[e] = 0.f;
-    v += (u < U0) ? (b0 ? b0[u] : 0.f) : (b1 ? b1[u - U0] : 0.f);
-    if (act == LG_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
-    else if (act == LG_ACT_TANH) v = tanhf(v);
-    if (u < U0) out0[(int64_t)n * U0 + u] = v;
-    else out1[(int64_t)n * U1 + (u - U0)] = v;
+  for (int e0 = threadIdx.x; e0 < N * UP; e0 += 4 * HT) {
+    float v4[4];                                 // four independent L2 reads in flight per thread
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = e0 + i * HT;
+      v4[i] = e < N * UP ? __ldcg(&ws_acc[e]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = e0 + i * HT;
+      if (e >= N * UP) continue;
+      ws_acc[e] = 0.f;
+      const int n = e / UP, u = e - n * UP;
+      if (u >= U) continue;
+      float v = v4[i] + ((u < U0) ? (b0 ? b0[u] : 0.f) : (b1 ? b1[u - U0] : 0.f));
+      if (act == LG_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+      else if (act == LG_ACT_TANH) v = tanhf(v);
+      if (u < U0) out0[(int64_t)n * U0 + u] = v;
+      else out1[(int64_t)n * U1 + (u - U0)] = v;
+    }
   }
   if (threadIdx.x == 0) *counter = 0u;
 }
@@ -281,12 +291,21 @@ __global__ void __launch_bounds__(HT) heads_bwd_kernel(const TF* __restrict__ fe
     }
   }
   if (wgrad) {
+    // dW += wacc: all twelve loads in flight before the first add (a load-add-store chain per element
+    // pays one global round trip per element: it was half of this kernel's time)
+    float* q[12];
+    float old[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
       const int u = uh * 12 + j;
-      if (u < U0) { if (dW0) dW0[(int64_t)(k0 + kw) * U0 + u] += wacc[j]; }
-      else if (u < U) { if (dW1) dW1[(int64_t)(k0 + kw) * U1 + (u - U0)] += wacc[j]; }
+      q[j] = nullptr;
+      if (u < U0) { if (dW0) q[j] = dW0 + (int64_t)(k0 + kw) * U0 + u; }
+      else if (u < U) { if (dW1) q[j] = dW1 + (int64_t)(k0 + kw) * U1 + (u - U0); }
     }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) old[j] = q[j] ? *q[j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) if (q[j]) *q[j] = old[j] + wacc[j];
   }
   if (blockIdx.x == 0 && threadIdx.x < U) {
     const int u = threadIdx.x;

@@ -33,6 +33,43 @@ def _dist():
     return None
 
 
+class LossValue:
+    """A loss scalar of one train step (what the reference returns as a 0-d EagerTensor): the three losses of
+    a step are copied to pinned host memory on a read-back stream right behind the step, and `float()` /
+    `.item()` / `.numpy()` wait for THAT copy only - a loop that logs the losses of step i after submitting
+    step i+1 never drains the GPU.  `.tensor` is the device value."""
+    __slots__ = ("tensor", "_slot", "_gen", "_idx")
+
+    def __init__(self, tensor, slot, gen, idx):
+        self.tensor, self._slot, self._gen, self._idx = tensor, slot, gen, idx
+
+    def __float__(self):
+        host, event, gen = self._slot
+        if gen[0] == self._gen:                 # the pinned slot still holds this step
+            event.synchronize()
+            if gen[0] == self._gen:
+                return float(host[self._idx])
+        return float(self.tensor)               # slot recycled: plain (stream-synchronising) device read
+
+    def item(self):
+        return float(self)
+
+    def numpy(self):
+        return np.float32(float(self))
+
+    def cpu(self):
+        return torch.tensor(float(self))
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(float(self), dtype=dtype or np.float32)
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def __repr__(self):
+        return "LossValue(%r)" % float(self)
+
+
 class EagerTrainer:
     def __init__(self, args, generator, discriminator, adjuster, dataset):
         self.args = args
@@ -77,6 +114,7 @@ class EagerTrainer:
         self._noise_gen = None
         self._comm_stream = None
         self._chain_streams = {}
+        self._rb, self._rb_count = None, 0
         if getattr(args, "result_dir", None) and getattr(args, "init_dirs", False):
             self._init_dir()
 
@@ -172,9 +210,16 @@ class EagerTrainer:
         S["cond1"] = rt.empty(B, a.cond_dim, dtype=f32)
         S["cond2"] = rt.empty(B, a.cond_dim, dtype=f32)
         S["noise"] = rt.empty(B, a.noise_dim, dtype=f32)
-        S["dimg"] = rt.empty(2 * B, H, H, C)                 # [new_image ; fake_image]
+        # One image buffer [real_image_1 ; fake_image ; new_image]: the adjuster's input is its first 2B
+        # images (eager_trainer.py:157), the discriminator's batch [fake ; new_image] its last 2B, so ONE encoder
+        # pass over the 3B images serves D(new_image), D(fake) AND the adjuster's encoder(real_image_1 ; fake):
+        # the adjuster shares D's encoder (model.py:119), nothing has been updated yet, and the norm is per
+        # sample - encoder(fake) is the same tensor in both.
+        S["img3"] = rt.empty(3 * B, H, H, C)
+        S["aimg"] = S["img3"][:2 * B]                        # [real_image_1 ; fake_image]
+        S["dimg"] = S["img3"][B:]                            # [fake_image ; new_image]
+        S["fake"] = S["img3"][B:2 * B]
         S["img2"] = rt.empty(B, H, H, C)
-        S["aimg"] = rt.empty(2 * B, H, H, C)                 # [real_image_1 ; fake_image]
         S["aimg_t"] = rt.empty(2 * B, H, H, C)               # [real_image_2 ; real_image_1]
         S["acond_in"] = rt.empty(2 * B, a.cond_dim, dtype=f32)
         S["acond_t"] = rt.empty(2 * B, a.cond_dim, dtype=f32)
@@ -188,9 +233,9 @@ class EagerTrainer:
     def _prepare_inputs(self, S):
         """Casts / concatenations of the step inputs (part of the captured step)."""
         B = self.args.batch_size
-        K.cast(S["in_new"], S["dimg"][:B])
+        K.cast(S["in_new"], S["img3"][2 * B:])
         K.cast(S["in_img2"], S["img2"])
-        K.cast(S["in_img1"], S["aimg"][:B])
+        K.cast(S["in_img1"], S["img3"][:B])
         S["aimg_t"][:B].copy_(S["img2"])
         S["aimg_t"][B:].copy_(S["aimg"][:B])
         # eager_trainer.py:155-156
@@ -212,8 +257,12 @@ class EagerTrainer:
         rt.begin_step()
         self._prepare_inputs(S)
 
-        # ---- forward: G, then D on [new_image ; fake] (eager_trainer.py:134-137)
-        fake, (g_hctx, g_dctx, g_x4) = G.forward_ctx(S["noise"], S["cond2"], out=S["dimg"][B:])
+        # ---- forward: G, then the encoder on [real_image_1 ; fake ; new_image] (eager_trainer.py:134-137, 157-160)
+        fake, (g_hctx, g_dctx, g_x4) = G.forward_ctx(S["noise"], S["cond2"], out=S["fake"])
+        off = B if adj_on else 0                                  # where D's batch [fake ; new_image] starts
+        outs3, ectx3 = E.encoder_forward(rt, D.encoder, S["img3"] if adj_on else S["dimg"])
+        outs = [o[off:] for o in outs3]
+        ectx = [(x[off:], z[off:], st[off:], None if xp is None else xp[off:]) for (x, z, st, xp) in ectx3]
 
         # The step is three chains that depend only on the forward pass and on the (read-only until Adam)
         # weights: the D-loss backward, the G-loss backward and the whole adjuster sub-step.  They run on
@@ -221,27 +270,26 @@ class EagerTrainer:
         # kernels of one chain execute under the L2- and tensor-bound conv kernels of another.  Every chain
         # allocates its temporaries on its own stream (the caching allocator never hands a block to another
         # stream), and the tensors chains share stay referenced until the join below.
-        # The adjuster sub-step (eager_trainer.py:152-164) is almost half of the step's conv work and needs
-        # only `fake`: it forks first, on a high-priority stream, and the other chains fill in around it.
+        # The adjuster sub-step (eager_trainer.py:152-164) is the longest chain: it forks first, on a
+        # high-priority stream, and the other chains fill in around it.
         main = torch.cuda.current_stream()
         sA = self._chain_stream("A", main, high=True) if adj_on else None
         if adj_on:
             with torch.cuda.stream(sA):
-                self._adjuster_chain(S, batch_no)
+                self._adjuster_chain(S, batch_no, [o[:2 * B] for o in outs3])
 
-        outs, ectx = E.encoder_forward(rt, D.encoder, S["dimg"])
-        pr, c = E.disc_heads_forward(rt, D, outs[3])
+        pr, c = E.disc_heads_forward(rt, D, outs[3])              # rows [:B] fake, [B:] new_image
 
         # ---- losses + gradients w.r.t. the logits (eager_trainer.py:139-140)
         dl_pr_d = rt.empty(2 * B, 1, dtype=f32)
         dl_c_d = rt.zeros(2 * B, a.cond_dim, dtype=f32)          # fake half: no D-loss term on fake_c
         dl_pr_g = rt.empty(B, 1, dtype=f32)
         dl_c_g = rt.empty(B, a.cond_dim, dtype=f32)
-        K.bce_sigmoid_multi([(c[:B], S["cond1"], 2.0, l_disc, dl_c_d[:B]),
-                             (pr[:B], soft(1.0), 1.0, l_disc, dl_pr_d[:B]),
-                             (pr[B:], soft(0.0), 1.0, l_disc, dl_pr_d[B:]),
-                             (pr[B:], soft(1.0), 1.0, l_gen, dl_pr_g),
-                             (c[B:], S["cond2"], 1.0, l_gen, dl_c_g)])
+        K.bce_sigmoid_multi([(c[B:], S["cond1"], 2.0, l_disc, dl_c_d[B:]),
+                             (pr[B:], soft(1.0), 1.0, l_disc, dl_pr_d[B:]),
+                             (pr[:B], soft(0.0), 1.0, l_disc, dl_pr_d[:B]),
+                             (pr[:B], soft(1.0), 1.0, l_gen, dl_pr_g),
+                             (c[:B], S["cond2"], 1.0, l_gen, dl_c_g)])
 
         # ---- disc_tape.gradient(disc_loss, D weights): both halves, no input gradient (:145)
         sD = self._chain_stream("D", main)
@@ -251,8 +299,8 @@ class EagerTrainer:
             self._reduce_async("Discriminator", batch_no)    # overlaps with the G backward + adjuster step
 
         # ---- gen_tape.gradient(gen_loss, G weights): dgrad-only through D(fake), then G (:149)
-        ectx_f = [(x[B:], z[B:], st[B:], None) for (x, z, st, _) in ectx]
-        g4 = E.disc_heads_backward(rt, D, outs[3][B:], dl_pr_g, dl_c_g, wgrad=False)
+        ectx_f = [(x[:B], z[:B], st[:B], None) for (x, z, st, _) in ectx]
+        g4 = E.disc_heads_backward(rt, D, outs[3][:B], dl_pr_g, dl_c_g, wgrad=False)
         g_img = E.encoder_backward(rt, D.encoder, ectx_f, g4, wgrad=False, input_grad=True)
         dpre = torch.empty_like(fake)
         K.l1_tanh_bwd(fake, S["img2"], g_img, dpre, a.l1_lambda, l_gen)
@@ -287,17 +335,16 @@ class EagerTrainer:
         s.wait_stream(main)
         return s
 
-    def _adjuster_chain(self, S, batch_no):
-        """eager_trainer.py:152-164 on the current stream: forward A on [image ; fake], D on the result, the
-        gradient of adj_loss w.r.t. the adjuster's own dense + norm (dgrad-only through D and the decoder)."""
+    def _adjuster_chain(self, S, batch_no, enc):
+        """eager_trainer.py:152-164 on the current stream: forward A on [image ; fake] (`enc`: the shared
+        encoder's four maps of exactly that batch, already computed), D on the result, the gradient of adj_loss
+        w.r.t. the adjuster's own dense + norm (dgrad-only through D and the decoder)."""
         a, rt = self.args, self.rt
         B = a.batch_size
         D, A = self.discriminator, self.adjuster
         f32 = torch.float32
         l_adj = S["loss"][2:3]
-        fake = S["dimg"][B:]
-        S["aimg"][B:].copy_(fake)
-        adj, (a_hctx, a_dctx, a_x4) = A.forward_ctx(S["aimg"], S["acond_in"])
+        adj, (a_hctx, a_dctx, a_x4) = A.forward_ctx(S["aimg"], S["acond_in"], enc=enc)
         outs2, ectx2 = E.encoder_forward(rt, D.encoder, adj)
         apr, ac = E.disc_heads_forward(rt, D, outs2[3])
         dl_pr_a = rt.empty(2 * B, 1, dtype=f32)
@@ -397,10 +444,31 @@ class EagerTrainer:
         adj_on, _ = self._variant(batch_no)
         self._run_step(S, batch_no)
         B = a.batch_size
-        losses = S["loss"].clone()
-        fake_image = S["dimg"][B:]
+        losses = self._read_back(S["loss"].clone())
+        fake_image = S["fake"]
         adj_image = S["adj"] if adj_on else None
         return True, fake_image, adj_image, losses[0], losses[1], (losses[2] if adj_on else None)
+
+    _RB_SLOTS = 16
+
+    def _read_back(self, dev):
+        """Start the device->host copy of this step's three loss scalars on the read-back stream."""
+        if self._rb is None:
+            self._rb = (torch.cuda.Stream(),
+                        [(torch.empty(dev.numel(), dtype=torch.float32).pin_memory(), torch.cuda.Event(), [0])
+                         for _ in range(self._RB_SLOTS)])
+        stream, slots = self._rb
+        self._rb_count += 1
+        slot = slots[self._rb_count % self._RB_SLOTS]
+        host, event, gen = slot
+        stream.wait_stream(torch.cuda.current_stream())
+        if gen[0]:
+            event.synchronize()                 # a reader of the step that owned this slot may be mid-copy
+        gen[0] = self._rb_count
+        with torch.cuda.stream(stream):
+            host.copy_(dev, non_blocking=True)
+            event.record(stream)
+        return [LossValue(dev[i], slot, self._rb_count, i) for i in range(3)]
 
     # ------------------------------------------------------------------ epoch loop (host glue)
     def train(self):

@@ -243,9 +243,12 @@ class Adjuster(_Model):
         return (self.encoder.weights + self.dense.weights + self.norm.weights + self.decoder.weights
                 + self.conv.weights)
 
-    def forward_ctx(self, image, cond, out=None):
+    def forward_ctx(self, image, cond, out=None, enc=None):
+        """`enc`: the four maps of self.encoder(image) if the caller already has them (the train step runs the
+        shared encoder once for the discriminator and the adjuster)."""
         rt, a = self.rt, self.args
-        enc, _ = E.encoder_forward(rt, self.encoder, image)
+        if enc is None:
+            enc, _ = E.encoder_forward(rt, self.encoder, image)
         c0, hctx = E.head_forward(rt, self.dense, self.norm, cond,
                                   (cond.shape[0], a.init_dim, a.init_dim, a.conv_filter[0]), skip=enc[3])
         x4, dctx = E.decoder_forward(rt, self.decoder, c0, (enc[2], enc[1], enc[0]))
