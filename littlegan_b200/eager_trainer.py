@@ -16,7 +16,7 @@ import torch
 
 from . import engine as E
 from . import kernels as K
-from .utils import save_image, soft
+from .utils import save_image, soft, upload
 
 
 class OutOfRangeError(Exception):
@@ -535,31 +535,47 @@ class EagerTrainer:
     # ------------------------------------------------------------------ predict
     @torch.no_grad()
     def predict(self, noise, cond, image, gen_image_save_path=None, json_save_path=None, adj_image_save_path=None):
-        """eager_trainer.py:265-298: 1 G + 2 D + 2 A forward passes, four MSE scalars."""
+        """eager_trainer.py:265-298: G(noise, cond); D(image), D(gen_image); the four MSE scalars; A(image, cond),
+        A(gen_image, cond).  The reference runs 1 G + 2 D + 2 A forward passes; D and A share one encoder
+        (model.py:119) and every norm is per sample, so ONE encoder pass over [image ; gen_image] serves both
+        discriminator calls and both adjuster calls, and one decoder pass serves both adjuster calls."""
         G, D, A = self.generator, self.discriminator, self.adjuster
-        gen_image = G([noise, cond])
+        rt, a = self.rt, self.args
+        if rt is None:
+            raise K._lib.LittleGANError("littlegan_b200 has no CPU path: a CUDA device is required")
+
+        def dev(x, dtype):                     # host -> device in the source dtype, cast on the device
+            return upload(x, rt.device).to(dtype).contiguous()
+
+        noise_d, cond_d = dev(noise, torch.float32), dev(cond, torch.float32)
+        image_d = dev(image, rt.act_dtype)
+        B = image_d.shape[0]
+        E.refresh_packs(rt, self._conv_layers())
+        both = rt.empty(2 * B, *image_d.shape[1:])
+        both[:B].copy_(image_d)
+        gen_image = G.forward_ctx(noise_d, cond_d, out=both[B:])[0]
         if gen_image_save_path is not None:
             save_image(gen_image, gen_image_save_path)
-        dev = gen_image.device
-        cond_d = (torch.from_numpy(cond) if isinstance(cond, np.ndarray) else cond).to(dev, torch.float32)
+        enc, _ = E.encoder_forward(rt, D.encoder, both)
+        pr, c = E.disc_heads_forward(rt, D, enc[3])
         save = dict()
         save["real_cond"] = cond_d
-        save["real_pr"], save["real_c"] = D(image)
-        save["fake_pr"], save["fake_c"] = D(gen_image)
-        mse = lambda t, p: float(((t - p) ** 2).mean(dim=-1).mean(dim=0))
-        save["real_pr_mse"] = mse(soft(1.0), save["real_pr"])
-        save["real_c_mse"] = mse(cond_d, save["real_c"])
-        save["fake_pr_mse"] = mse(soft(0.0), save["fake_pr"])
-        save["fake_c_mse"] = mse(cond_d, save["fake_c"])
+        save["real_pr"], save["real_c"] = pr[:B], c[:B]
+        save["fake_pr"], save["fake_c"] = pr[B:], c[B:]
+        mse = lambda t, p: ((t - p) ** 2).mean(dim=-1).mean(dim=0)
+        mses = torch.stack([mse(soft(1.0), save["real_pr"]), mse(cond_d, save["real_c"]),
+                            mse(soft(0.0), save["fake_pr"]), mse(cond_d, save["fake_c"])]).tolist()
+        save["real_pr_mse"], save["real_c_mse"], save["fake_pr_mse"], save["fake_c_mse"] = mses
         for x in ["real_cond", "real_pr", "real_c", "fake_c", "fake_pr"]:
             save[x] = torch.round(save[x] * 100).to(torch.int64).cpu().tolist()
         if json_save_path is not None:
             with open(json_save_path, "w") as f:
                 json.dump(save, f)
         adj_fake_image, adj_real_image = None, None
-        if self.args.train_adj:
-            adj_real_image = A([image, cond])          # note: raw cond here, as the reference (:292)
-            adj_fake_image = A([gen_image, cond])
+        if a.train_adj:
+            # note: raw cond here, as the reference (:292)
+            adj = A.forward_ctx(both, torch.cat([cond_d, cond_d], 0), enc=enc)[0]
+            adj_real_image, adj_fake_image = adj[:B], adj[B:]
             if adj_image_save_path is not None:
-                save_image(torch.cat([adj_real_image, adj_fake_image], 0), adj_image_save_path)
+                save_image(adj, adj_image_save_path)
         return gen_image, save, adj_real_image, adj_fake_image

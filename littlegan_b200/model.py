@@ -89,9 +89,8 @@ def _as_input(rt, x, dtype=None):
     """numpy / CPU / CUDA input -> contiguous CUDA tensor of the requested dtype."""
     if not torch.cuda.is_available():
         raise K._lib.LittleGANError("littlegan_b200 has no CPU path: a CUDA device is required")
-    if isinstance(x, np.ndarray):
-        x = torch.from_numpy(x)
-    return x.to(device=rt.device, dtype=dtype or rt.act_dtype).contiguous()
+    from .utils import upload
+    return upload(x, rt.device).to(dtype or rt.act_dtype).contiguous()
 
 
 class _Model:

@@ -16,6 +16,38 @@ def inverse_rescale(y):
     return torch.round((y + 1) * 127.5) if torch.is_tensor(y) else np.round((np.asarray(y) + 1) * 127.5)
 
 
+_STAGE = {}
+
+
+def upload(x, device, chunk_bytes=4 << 20):
+    """Host array / CPU tensor -> device tensor of the same dtype.  Large pageable arrays go through two pinned
+    staging buffers in chunks, so the host memcpy of chunk i+1 overlaps the DMA of chunk i (a plain pageable
+    cudaMemcpy of a 50 MB image batch runs at ~3 GB/s; this path is bound by the host memcpy)."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if x.is_cuda:
+        return x
+    x = x.contiguous()
+    nbytes = x.numel() * x.element_size()
+    if x.is_pinned() or nbytes < 2 * chunk_bytes:
+        return x.to(device, non_blocking=True)
+    src = x.view(-1).view(torch.uint8)
+    out = torch.empty(x.shape, dtype=x.dtype, device=device)
+    dst = out.view(-1).view(torch.uint8)
+    st = _STAGE.get(chunk_bytes)
+    if st is None:
+        st = _STAGE[chunk_bytes] = [(torch.empty(chunk_bytes, dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+                                    for _ in range(2)]
+    for i, off in enumerate(range(0, nbytes, chunk_bytes)):
+        buf, ev = st[i & 1]
+        n = min(chunk_bytes, nbytes - off)
+        ev.synchronize()                       # the DMA that last read this staging buffer is done
+        buf[:n].copy_(src[off:off + n])
+        dst[off:off + n].copy_(buf[:n], non_blocking=True)
+        ev.record()
+    return out
+
+
 def save_image(image, path=None, shape=(None, None)):
     """utils.py:6-44: writes one image or a grid (column-major fill, as the reference does)."""
     from PIL import Image
