@@ -64,6 +64,15 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* sh) {
   __syncthreads();
 }
 
+// Grid of a persistent kernel that walks `items` work items round-robin over at most `max_ctas` CTAs: the
+// smallest grid with the same number of rounds.  512 tiles on 148 SMs are 4 rounds either way; 128 CTAs do them
+// with no idle tail and leave 20 SMs to the kernels of the step's other streams.
+static inline int lg_even_grid(int items, int max_ctas) {
+  if (items <= max_ctas) return items < 1 ? 1 : items;
+  const int rounds = (items + max_ctas - 1) / max_ctas;
+  return (items + rounds - 1) / rounds;
+}
+
 static inline int lg_num_sms() {
   static int sms = 0;
   if (!sms) {

@@ -458,7 +458,7 @@ void launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParam
   }
   if (p.pair) {
     // one CTA pair (cluster of 2 = the two SMs of a TPC) per pair tile, persistent over the 74 TPCs
-    const int npairs = p.total_tiles < lg_num_sms() / 2 ? p.total_tiles : lg_num_sms() / 2;
+    const int npairs = lg_even_grid(p.total_tiles, lg_num_sms() / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * npairs);
     cfg.blockDim = dim3(NUM_THREADS);
@@ -471,7 +471,7 @@ void launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParam
     cudaLaunchKernelEx(&cfg, tc_conv_kernel<OP, S, NB, true>, tmA, tmB, p, nb);
     return;
   }
-  const int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
+  const int grid = lg_even_grid(p.total_tiles, lg_num_sms());
   tc_conv_kernel<OP, S, NB, false><<<grid, NUM_THREADS, smem_bytes(p), st>>>(tmA, tmB, p, nb);
 }
 

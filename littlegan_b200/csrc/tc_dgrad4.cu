@@ -374,7 +374,7 @@ int lg_tc_dgrad4(const void* small, const void* wpack, const float* bias, void* 
     attr_set = true;
   }
   const size_t shm = (size_t)p.stages * p.stage_bytes + 1024 + 256 + 2048;
-  const int grid = p.total_tiles < lg_num_sms() ? p.total_tiles : lg_num_sms();
+  const int grid = lg_even_grid(p.total_tiles, lg_num_sms());
   if (nbh != nullptr) tc_dgrad4_kernel<true><<<grid, NUM_THREADS, shm, st>>>(tmA, tmB, p, nb);
   else tc_dgrad4_kernel<false><<<grid, NUM_THREADS, shm, st>>>(tmA, tmB, p, nb);
   return LG_OK;

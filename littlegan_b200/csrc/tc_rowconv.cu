@@ -404,7 +404,7 @@ bool plan_rc(int Nimg, int Hb, int Wb, int A, int Cpad, int B, int s, bool with_
   if (const char* e = getenv("LG_RC_R")) { const int R = atoi(e); if (R >= 4 && p.Hs % R == 0 && R % 2 == 0) bestR = R; }   // tuning knob
   if (!bestR) return false;
   p.R = bestR; p.strips_per_img = p.Hs / bestR; p.total_strips = Nimg * p.strips_per_img;
-  pl->grid = p.total_strips < ctas ? p.total_strips : ctas;
+  pl->grid = lg_even_grid(p.total_strips, ctas);
   return true;
 }
 

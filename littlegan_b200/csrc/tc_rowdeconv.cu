@@ -420,7 +420,7 @@ bool plan_rd(int Nimg, int Hb, int Wb, int A, int B, int s, RdParams* p, int* gr
     if (eff > best) { best = eff; bestR = R; }
   }
   p->Nimg = Nimg; p->H = Hb; p->R = bestR; p->strips_per_img = Hin / bestR; p->total_strips = Nimg * p->strips_per_img;
-  *grid = p->total_strips < ctas ? p->total_strips : ctas;
+  *grid = lg_even_grid(p->total_strips, ctas);
   return true;
 }
 

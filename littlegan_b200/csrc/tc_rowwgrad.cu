@@ -236,7 +236,7 @@ bool plan_rw(int Nimg, int Hb, int Wb, int A, int B, int s, RwParams* p, int* gr
   if (const char* e = getenv("LG_RW_R")) { const int R = atoi(e); if (R >= 4 && Hs % R == 0) bestR = R; }
   p->Nimg = Nimg; p->Hb = Hb; p->Hs = Hs; p->R = bestR; p->strips_per_img = Hs / bestR;
   p->total_strips = Nimg * p->strips_per_img;
-  *grid = p->total_strips < ctas ? p->total_strips : ctas;
+  *grid = lg_even_grid(p->total_strips, ctas);
   return true;
 }
 

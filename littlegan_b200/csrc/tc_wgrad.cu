@@ -218,12 +218,25 @@ bool plan_wgrad(int Nimg, int Hb, int Wb, int A, int A_real, int B, int s, WgPar
   int st = SMEM_BUDGET / p->stage_bytes;
   p->stages = st > MAX_STAGES ? MAX_STAGES : st;
   if (p->stages < 2) return false;
+  // Split K so that the CTAs (one per SM: a CTA holds ~200 KB of shared memory) come in WHOLE waves: with
+  // tiles x slices just above a multiple of the SM count the last wave runs a handful of CTAs on an otherwise
+  // idle GPU (300 CTAs on 148 SMs took three CTA lifetimes instead of two).  Cost of a candidate =
+  // waves x (k-blocks per CTA + a fixed prologue / pipeline fill / reduction epilogue of ~12 k-block times).
   const int tiles = p->groups * p->a_tiles * p->n_tiles;
-  int slices = (2 * lg_num_sms() + tiles - 1) / tiles;
-  int max_slices = (p->total_kb + 3) / 4;                 // at least ~4 k-blocks per CTA
-  if (slices > max_slices) slices = max_slices;
-  if (slices < 1) slices = 1;
-  p->kb_per_slice = (p->total_kb + slices - 1) / slices;
+  const int sms = lg_num_sms();
+  const int max_slices = (p->total_kb + 3) / 4;           // at least ~4 k-blocks per CTA
+  int best_kbs = p->total_kb;
+  long best_cost = -1;
+  for (int w = 1; w <= 4; ++w) {
+    int sl = (w * sms) / tiles;
+    if (sl < 1) continue;
+    if (sl > max_slices) sl = max_slices;
+    const int kbs = (p->total_kb + sl - 1) / sl;
+    const int ctas = tiles * ((p->total_kb + kbs - 1) / kbs);
+    const long cost = (long)((ctas + sms - 1) / sms) * (kbs + 12);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_kbs = kbs; }
+  }
+  p->kb_per_slice = best_kbs;
   return true;
 }
 
