@@ -233,3 +233,59 @@ def test_public_loss_functions():
     assert abs(float(gl) - float(O.generator_loss(oargs, c_true, c_pred, pr_f, img_a, img_b))) < 1e-5
     al = trainer.adjuster_loss(c_true.cuda(), c_pred.cuda(), pr_f.cuda(), img_a.cuda(), img_b.cuda())
     assert abs(float(al) - float(gl)) < 1e-7
+
+
+def _run_steps(oargs, n, **extra):
+    """Final parameter arena and per-step losses of n train steps (batch_no 11.., adjuster on from 11) from the
+    same initial weights and batches."""
+    from littlegan_b200.eager_trainer import EagerTrainer
+    pargs = product_args(oargs, dtype="fp32", cuda_graph=extra.pop("cuda_graph", False))
+    for k, v in extra.items():
+        setattr(pargs, k, v)
+    gen, disc, adj = build_product(pargs, 0)
+    trainer = EagerTrainer(pargs, gen, disc, adj, None)
+    i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=5)
+    losses = []
+    for b in range(11, 11 + n):
+        res = trainer._train_step(b, _ListIterator([(i1, c1), (i2, c2)]), noise=noise, new_image=i1)
+        losses.append(res)
+    vals = [[float(r[3]), float(r[4]), float(r[5])] for r in losses]
+    return trainer.P.clone(), vals, losses
+
+
+def test_parallel_chains_match_the_serial_schedule():
+    """The three chains of the step on three streams (and as branches of a captured graph) compute what the
+    single-stream schedule computes; fp32 atomics make the sums order dependent, hence a tolerance."""
+    oargs = small_args()
+    P0, l0, _ = _run_steps(oargs, 4, overlap_chains=False, overlap_wgrad=False)
+    P1, l1, _ = _run_steps(oargs, 4)
+    P2, l2, _ = _run_steps(oargs, 4, cuda_graph=True)
+    for P, l in ((P1, l1), (P2, l2)):
+        assert rel_err(P, P0) < 1e-5
+        for a, b in zip(l, l0):
+            for x, y in zip(a, b):
+                assert abs(x - y) <= 1e-4 * abs(y) + 1e-6
+
+
+def test_loss_values_survive_slot_recycling():
+    """LossValue reads the pinned copy made behind its step; once the ring slot has been reused by a later
+    step it falls back to the device scalar - either way float() is that step's loss."""
+    from littlegan_b200.eager_trainer import EagerTrainer
+    oargs = small_args()
+    n = EagerTrainer._RB_SLOTS + 3
+    _, vals, res = _run_steps(oargs, n)
+    for r, v in zip(res, vals):            # vals were read after ALL steps: the first ones through the fallback
+        assert [float(r[3]), float(r[4]), float(r[5])] == v
+        assert abs(float(r[3].tensor) - v[0]) == 0.0 and format(r[4], ".3f") == "%.3f" % v[1]
+
+
+def test_upload_pinned_chunks_roundtrip():
+    import numpy as np
+    from littlegan_b200.utils import upload
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((37, 128, 128, 3)).astype(np.float32)       # 7 MB: 2 chunks of 3 MB + a tail
+    y = upload(x, torch.device("cuda"), chunk_bytes=3 << 20)
+    assert y.shape == x.shape and y.dtype == torch.float32
+    assert torch.equal(y.cpu(), torch.from_numpy(x))
+    small = upload(x[:1], torch.device("cuda"))
+    assert torch.equal(small.cpu(), torch.from_numpy(x[:1]))
