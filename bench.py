@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
     python bench.py --impl reference [...]                        # the CPU restatement, host cores
 
-One "step" = one full `_train_step` (batch_no > 10: generator + discriminator + adjuster
-sub-step, use_partition off, sample.config.json hyper-parameters, cond_dim 40) on a synthetic
+One "step" = one full `_train_step` (batch_no > 10: input augmentation + generator + discriminator +
+adjuster sub-step, use_partition off, sample.config.json hyper-parameters, cond_dim 40) on a synthetic
 CelebA-shaped batch.  Per-GPU batch is fixed at 64 (configs[1]; at 8 GPUs this is configs[2]'s
 global batch 512) => weak scaling.  images/sec counts `batch_size` images per step (the
 reference's progress bar counts 2x that, eager_trainer.py:213).
@@ -91,7 +91,7 @@ class ClockSampler:
 def _bench_args(batch):
     from littlegan_b200.config import Arg
     return Arg.from_dict(batch_size=batch, attr=list(range(COND_DIM)), use_partition=False, train_adj=True,
-                         dtype="bf16", cuda_graph=True)
+                         dtype="bf16", cuda_graph=True, augment=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,7 +215,7 @@ def run_product(a):
         b += 1
         trainer._train_step(b, it)
     torch.cuda.synchronize()
-    graph = trainer._graphs[(True, None)][0]
+    graph = trainer._graphs[(True, None, True)][0]
     launches = K.launch_count_of_last_capture()
 
     # ---- device-resident timing: K replays of the captured step

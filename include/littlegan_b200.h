@@ -257,6 +257,19 @@ int lg_adam_advance(double* state, double lr, double beta1, double beta2, void* 
 int lg_adam_apply(float* p, const float* g, float* m, float* v, int64_t n, const double* state,
                   float beta1, float beta2, float eps, float clip, void* stream);
 
+/* ---- input augmentation of the train step (eager_trainer.py:127-131: tf.image.random_flip_left_right,
+ *      random_brightness(0.02), random_contrast(0.75, 1.003), random_hue(0.03) and + 0.1 * N(0, 0.2)) -----------
+ * x: [N,H,W,3] fp32 (H*W and W multiples of 4).  params: float[4 + 4 N] = { brightness delta, contrast factor, hue
+ * delta (turns), step ; per image: mean_r, mean_g, mean_b, flip (0/1) }.  state: uint64[2] = { seed, step } on the
+ * device.  lg_augment_prepare writes the per-image channel means and, with draw != 0, this step's draws from
+ * Philox4x32-10(seed, step) (draw == 0: the caller has filled the three scalars and the flips).
+ * lg_augment_apply writes out = hue(contrast(brightness(flip(x)))) + noise in out_dtype; noise: a [N,H,W,3] fp32
+ * tensor added as is, or NULL = N(0, noise_std) from Philox(seed, step), in which case it also advances state[1]. */
+int lg_augment_prepare(const float* x, int N, int H, int W, void* state, float* params, float max_brightness,
+                       float contrast_lo, float contrast_hi, float max_hue, int draw, void* stream);
+int lg_augment_apply(const float* x, const float* params, const float* noise, void* state, float noise_std,
+                     void* out, int N, int H, int W, int out_dtype, void* stream);
+
 /* ---- casts ------------------------------------------------------------------------------- */
 int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
 

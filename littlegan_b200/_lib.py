@@ -58,6 +58,8 @@ SIGNATURES = {
     "lg_l1_tanh_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _vp, _i, _vp]),
     "lg_adam_advance": (_i, [_vp, _d, _d, _d, _vp]),
     "lg_adam_apply": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp]),
+    "lg_augment_prepare": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
+    "lg_augment_apply": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "lg_cast": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "lg_fid_accumulate": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lg_fid_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),

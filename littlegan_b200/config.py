@@ -1,7 +1,7 @@
 """Layered configuration, same schema and precedence as the reference's `config.py:6-42`:
 `sample.config.json` <- `<env>.config.json` <- command line.  The three keys at the end of the
-packaged sample file (`dtype`, `cuda_graph`, `seed`) are new and default, so reference config
-files keep loading unchanged.
+packaged sample file (`dtype`, `cuda_graph`, `seed`) and `augment` (the reference's input augmentation,
+always on there) are new and default, so reference config files keep loading unchanged.
 """
 import json
 import os
@@ -53,7 +53,7 @@ class Arg:
             gpu = [int(i) for i in gpu.split(",") if i.isnumeric() and int(i) >= 0]
         self.gpu = gpu
         self.prefetch = self.prefetch_batch * self.batch_size
-        for key, default in (("dtype", "bf16"), ("cuda_graph", True), ("seed", 0)):
+        for key, default in (("dtype", "bf16"), ("cuda_graph", True), ("seed", 0), ("augment", True)):
             if not hasattr(self, key):
                 setattr(self, key, default)
 

@@ -115,6 +115,7 @@ class EagerTrainer:
         self._comm_stream = None
         self._chain_streams = {}
         self._rb, self._rb_count = None, 0
+        self._aug_state = None
         if getattr(args, "result_dir", None) and getattr(args, "init_dirs", False):
             self._init_dir()
 
@@ -220,6 +221,7 @@ class EagerTrainer:
         S["dimg"] = S["img3"][B:]                            # [fake_image ; new_image]
         S["fake"] = S["img3"][B:2 * B]
         S["img2"] = rt.empty(B, H, H, C)
+        S["aug_params"] = rt.empty(4 + 4 * B, dtype=f32)     # draws + per-image channel means of the augmentation
         S["aimg_t"] = rt.empty(2 * B, H, H, C)               # [real_image_2 ; real_image_1]
         S["acond_in"] = rt.empty(2 * B, a.cond_dim, dtype=f32)
         S["acond_t"] = rt.empty(2 * B, a.cond_dim, dtype=f32)
@@ -230,10 +232,17 @@ class EagerTrainer:
     def _conv_layers(self):
         return self.discriminator.encoder.convs + self.generator.decoder.convs + [self.generator.conv]
 
-    def _prepare_inputs(self, S):
-        """Casts / concatenations of the step inputs (part of the captured step)."""
+    def _prepare_inputs(self, S, aug):
+        """Casts / concatenations of the step inputs (part of the captured step).  aug: new_image is the
+        reference's augmentation of real_image_1 (eager_trainer.py:127-131) instead of the staged `in_new`."""
         B = self.args.batch_size
-        K.cast(S["in_new"], S["img3"][2 * B:])
+        if aug:
+            if self._aug_state is None:
+                rank = _dist().get_rank() if _dist() is not None else 0
+                self._aug_state = K.augment_state(int(getattr(self.args, "seed", 0)) * 7919 + 13 + rank, self.rt.device)
+            K.augment(S["in_img1"], S["img3"][2 * B:], S["aug_params"], state=self._aug_state)
+        else:
+            K.cast(S["in_new"], S["img3"][2 * B:])
         K.cast(S["in_img2"], S["img2"])
         K.cast(S["in_img1"], S["img3"][:B])
         S["aimg_t"][:B].copy_(S["img2"])
@@ -243,7 +252,7 @@ class EagerTrainer:
         S["acond_t"][B:].copy_(S["cond1"])
         torch.add(S["acond_t"], 1.0, out=S["acond_in"]).mul_(0.5)
 
-    def _step_body(self, S, adj_on, batch_no):
+    def _step_body(self, S, adj_on, batch_no, aug=False):
         a, rt = self.args, self.rt
         B = a.batch_size
         G, D, A = self.generator, self.discriminator, self.adjuster
@@ -255,7 +264,7 @@ class EagerTrainer:
         self.Gd.zero_()
         loss.zero_()
         rt.begin_step()
-        self._prepare_inputs(S)
+        self._prepare_inputs(S, aug)
 
         # ---- forward: G, then the encoder on [real_image_1 ; fake ; new_image] (eager_trainer.py:134-137, 157-160)
         fake, (g_hctx, g_dctx, g_x4) = G.forward_ctx(S["noise"], S["cond2"], out=S["fake"])
@@ -381,13 +390,14 @@ class EagerTrainer:
             grp = (batch_no // (a.partition_interval + 1)) % 3
         return adj_on, grp
 
-    def _run_step(self, S, batch_no):
-        adj_on, grp = key = self._variant(batch_no)
+    def _run_step(self, S, batch_no, aug=False):
+        adj_on, grp = self._variant(batch_no)
+        key = (adj_on, grp, aug)
         use_graph = bool(getattr(self.args, "cuda_graph", True))
         if not use_graph or key not in self._seen:
             # first occurrence of a variant runs eagerly (it also warms up lazy state before capture)
             self._seen.add(key)
-            self._step_body(S, adj_on, batch_no)
+            self._step_body(S, adj_on, batch_no, aug)
             return
         g = self._graphs.get(key)
         if g is None:
@@ -397,7 +407,7 @@ class EagerTrainer:
                 self._pool = torch.cuda.graph_pool_handle()
             n0 = K.launch_count()
             with torch.cuda.graph(g, pool=self._pool):
-                self._step_body(S, adj_on, batch_no)
+                self._step_body(S, adj_on, batch_no, aug)
             K.note_capture(K.launch_count() - n0)
             self._graphs[key] = (g, S["adj"])
         g, adj = self._graphs[key]
@@ -410,9 +420,10 @@ class EagerTrainer:
         dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
     def _train_step(self, batch_no, iterator, noise=None, new_image=None):
-        """eager_trainer.py:115-169.  `noise` / `new_image` may be injected for reproducible runs;
-        by default noise ~ N(0,1) is drawn on the device and new_image = real_image_1 (the
-        reference's unseeded augmentation, eager_trainer.py:127-131, is a later-round row)."""
+        """eager_trainer.py:115-169.  `noise` / `new_image` may be injected for reproducible runs; by default
+        noise ~ N(0,1) is drawn on the device and new_image is the reference's augmentation of real_image_1
+        (eager_trainer.py:127-131: flip / brightness / contrast / hue / Gaussian noise, csrc/augment.cu) with
+        device-side Philox draws; `augment: false` in the config makes new_image = real_image_1."""
         a = self.args
         try:
             real_image_1, real_cond_1 = iterator.get_next()
@@ -432,7 +443,11 @@ class EagerTrainer:
         self._to_static(S["in_img2"], real_image_2)
         self._to_static(S["cond1"], real_cond_1)
         self._to_static(S["cond2"], real_cond_2)
-        self._to_static(S["in_new"], real_image_1 if new_image is None else new_image)
+        # new_image: injected, else the reference's augmentation of real_image_1 (config key `augment`, default
+        # on as in the reference), else real_image_1 itself
+        aug = new_image is None and bool(getattr(a, "augment", True))
+        if not aug:
+            self._to_static(S["in_new"], real_image_1 if new_image is None else new_image)
         if noise is None:
             if self._noise_gen is None:
                 self._noise_gen = torch.Generator(device=self.rt.device)
@@ -442,7 +457,7 @@ class EagerTrainer:
         else:
             self._to_static(S["noise"], noise)
         adj_on, _ = self._variant(batch_no)
-        self._run_step(S, batch_no)
+        self._run_step(S, batch_no, aug)
         B = a.batch_size
         losses = self._read_back(S["loss"].clone())
         fake_image = S["fake"]

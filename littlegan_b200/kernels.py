@@ -374,3 +374,28 @@ def fid_finalize(S1, S2, shift, mu, sigma, n):
     _cuda(S1, S2, shift, mu, sigma)
     check(_lib.load().lg_fid_finalize(_p(S1), _p(S2), _p(shift), _p(mu), _p(sigma), n, S1.numel(), _st()),
           "lg_fid_finalize")
+
+
+# ------------------------------------------------------------------------------------ augmentation
+AUG_MAX_BRIGHTNESS, AUG_CONTRAST, AUG_MAX_HUE, AUG_NOISE_STD = 0.02, (0.75, 1.003), 0.03, 0.1 * 0.2
+
+
+def augment_state(seed, device):
+    """{seed, step} of the augmentation's Philox streams, on the device (the step advances inside the launches)."""
+    return torch.tensor([int(seed), 0], dtype=torch.int64, device=device)
+
+
+def augment(x, out, params, state=None, noise=None, draw=True):
+    """new_image of eager_trainer.py:127-131: x [N,H,W,3] fp32 -> out (same shape, fp32 or bf16).
+    params: float32 [4 + 4 N] scratch (draw=False: [0:3] and the flip flags at [7::4] hold the caller's draws).
+    noise: None = N(0, 0.02) from Philox(state), else a [N,H,W,3] fp32 tensor added as is."""
+    _cuda(x, out, params, state, noise)
+    N, H, W, C = x.shape
+    if C != 3 or x.dtype != torch.float32:
+        raise _lib.LittleGANError("augment: needs an fp32 RGB batch")
+    lib = _lib.load()
+    check(lib.lg_augment_prepare(_p(x), N, H, W, _p(state), _p(params), AUG_MAX_BRIGHTNESS, AUG_CONTRAST[0],
+                                 AUG_CONTRAST[1], AUG_MAX_HUE, int(draw), _st()), "lg_augment_prepare")
+    check(lib.lg_augment_apply(_p(x), _p(params), _p(noise), _p(state), AUG_NOISE_STD, _p(out), N, H, W, dt(out),
+                               _st()), "lg_augment_apply")
+    return out

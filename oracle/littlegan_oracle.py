@@ -377,3 +377,40 @@ def synthetic_batch(args, batch, seed=0, dtype=torch.float32):
     i1, c1, i2, c2 = img(), lab(), img(), lab()
     noise = torch.randn(batch, args.noise_dim, generator=g).to(dtype)
     return i1, c1, i2, c2, noise
+
+
+# --------------------------------------------------------------------------- #
+# input augmentation (eager_trainer.py:127-131), random draws injected
+# --------------------------------------------------------------------------- #
+def adjust_hue(x, delta):
+    """tf.image.adjust_hue on [..., 3] RGB: rotate the hue by `delta` turns keeping each pixel's max and min
+    (TF's fused AdjustHue kernel works on (hue, v_min, v_max), which is defined for any value range - the
+    reference feeds images in [-1, 1]).  Per-pixel Python-free restatement of the hexcone model."""
+    r, g, b = x[..., 0], x[..., 1], x[..., 2]
+    vmax = torch.maximum(r, torch.maximum(g, b))
+    vmin = torch.minimum(r, torch.minimum(g, b))
+    rng = vmax - vmin
+    safe = torch.where(rng > 0, rng, torch.ones_like(rng))
+    h = torch.where(r == vmax, (g - b) / safe,
+                    torch.where(g == vmax, 2.0 + (b - r) / safe, 4.0 + (r - g) / safe))
+    h = torch.remainder(h + 6.0 * delta, 6.0)
+    xm = vmin + rng * (1.0 - torch.abs(torch.remainder(h, 2.0) - 1.0))
+    sec = torch.clamp(torch.floor(h), 0, 5).long()
+    table = [(vmax, xm, vmin), (xm, vmax, vmin), (vmin, vmax, xm), (vmin, xm, vmax), (xm, vmin, vmax), (vmax, vmin, xm)]
+    out = torch.stack([torch.stack([table[k][c] for k in range(6)], -1).gather(-1, sec[..., None])[..., 0]
+                       for c in range(3)], -1)
+    return torch.where((rng > 0)[..., None], out, x)
+
+
+def augment(x, flips, db, fc, dh, noise):
+    """new_image of eager_trainer.py:127-131 with the draws given: flips [N] (1 = flip left-right, per image:
+    tf.image.random_flip_left_right), db brightness delta (random_brightness(0.02): one scalar per batch), fc
+    contrast factor (random_contrast(0.75, 1.003): (x - mean_HW) * fc + mean_HW per image and channel), dh hue
+    delta in turns (random_hue(x, 0.03, -0.03): max_delta 0.03 - the third argument is the seed), noise
+    [N,H,W,3] = 0.1 * N(0, 0.2) already scaled."""
+    x = torch.where(flips.reshape(-1, 1, 1, 1) > 0.5, x.flip(2), x)
+    x = x + db
+    mean = x.mean(dim=(1, 2), keepdim=True)
+    x = (x - mean) * fc + mean
+    x = adjust_hue(x, dh)
+    return x + noise

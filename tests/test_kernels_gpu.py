@@ -656,3 +656,67 @@ def test_rowdeconv_rgb_stride2(N, Hb):
     assert rel_err(out, ref) < 1e-2
     ref_stats = torch.stack([ref.reshape(N, -1).sum(1), (ref.reshape(N, -1) ** 2).sum(1)], 1)
     assert float(((stats.cpu() - ref_stats).abs() / ref_stats.abs().max()).max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# input augmentation of the train step (eager_trainer.py:127-131)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N,H", [(5, 128), (3, 32)])
+def test_augment_matches_oracle_with_injected_draws(N, H, dtype):
+    from littlegan_b200 import kernels as K
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(N, H, H, 3, generator=g) * 2 - 1
+    flips = (torch.rand(N, generator=g) < 0.5).float()
+    flips[0], flips[1] = 1.0, 0.0
+    db, fc, dh = 0.013, 0.81, -0.027
+    noise = torch.randn(N, H, H, 3, generator=g) * 0.02
+    ref = O.augment(x.double(), flips.double(), db, fc, dh, noise.double())
+    params = torch.zeros(4 + 4 * N)
+    params[0], params[1], params[2] = db, fc, dh
+    params[7::4] = flips
+    out = torch.empty(N, H, H, 3, dtype=dtype, device="cuda")
+    K.augment(x.cuda(), out, params.cuda(), state=None, noise=noise.cuda(), draw=False)
+    torch.cuda.synchronize()
+    # a pixel whose hue sits on a sector boundary may land on either side of it; the map is continuous there
+    assert rel_err(out, ref) < (2e-6 if dtype == torch.float32 else 5e-3)
+    assert float((out.double().cpu() - ref).abs().max()) < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+def test_augment_draws_and_noise_statistics():
+    from littlegan_b200 import kernels as K
+    N, H = 64, 128
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(N, H, H, 3, generator=g) * 2 - 1).cuda()
+    state = K.augment_state(1234, "cuda")
+    params = torch.zeros(4 + 4 * N, device="cuda")
+    out = torch.empty(N, H, H, 3, device="cuda")
+    seen, flips_all = [], []
+    for step in range(6):
+        K.augment(x, out, params, state=state)
+        p = params.cpu()
+        db, fc, dh = float(p[0]), float(p[1]), float(p[2])
+        assert -0.02 <= db < 0.02 and 0.75 <= fc < 1.003 and -0.03 <= dh < 0.03
+        assert int(state[1]) == step + 1
+        flips = p[7::4]
+        assert set(flips.tolist()) <= {0.0, 1.0}
+        flips_all.append(flips)
+        seen.append((db, fc, dh))
+        # the noise is what remains after the deterministic chain with the drawn parameters
+        det = O.augment(x.double().cpu(), flips.double(), db, fc, dh, torch.zeros(N, H, H, 3, dtype=torch.float64))
+        nz = out.double().cpu() - det
+        assert abs(float(nz.mean())) < 2e-4 and abs(float(nz.std()) - 0.02) < 4e-4
+        assert abs(float((nz ** 4).mean() / nz.var() ** 2) - 3.0) < 0.05          # Gaussian kurtosis
+        per_img = nz.reshape(N, -1)
+        assert float(torch.corrcoef(per_img[:8, :4096])[0, 1:].abs().max()) < 0.08   # independent across images
+    assert len(set(seen)) == 6
+    frac = float(torch.cat(flips_all).mean())
+    assert 0.38 < frac < 0.62
+    # the streams are functions of (seed, step): the same state reproduces the same batch
+    state2 = K.augment_state(1234, "cuda")
+    out2 = torch.empty_like(out)
+    K.augment(x, out2, torch.zeros_like(params), state=state2)
+    state3 = K.augment_state(1234, "cuda")
+    out3 = torch.empty_like(out)
+    K.augment(x, out3, torch.zeros_like(params), state=state3)
+    assert torch.equal(out2, out3) and not torch.equal(out2, out)

@@ -182,3 +182,28 @@ def test_fid_oracle_is_numpy_scipy():
     tr = np.sqrt(np.clip(np.linalg.eigvalsh(root @ sig2 @ root), 0, None)).sum()
     alt = ((mu - mu2) ** 2).sum() + np.trace(sigma) + np.trace(sig2) - 2 * tr
     assert abs(alt - d) < 1e-8 * abs(d)
+
+
+def test_augment_restatement_against_colorsys_and_definitions():
+    """oracle.augment (eager_trainer.py:127-131): the hue rotation against Python's colorsys on [0,1] pixels and
+    its invariance under x -> 2x - 1 (the reference feeds [-1,1] images); flip / brightness / contrast by definition."""
+    import colorsys
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(40, 3, generator=g, dtype=torch.float64)
+    for d in (0.03, -0.03, 0.31, -0.77):
+        y = O.adjust_hue(x, d)
+        for i in range(x.shape[0]):
+            h, s, v = colorsys.rgb_to_hsv(*x[i].tolist())
+            want = colorsys.hsv_to_rgb((h + d) % 1.0, s, v)
+            assert max(abs(a - b) for a, b in zip(want, y[i].tolist())) < 1e-12
+        assert float((O.adjust_hue(2 * x - 1, d) - (2 * y - 1)).abs().max()) < 1e-12
+    grey = torch.full((2, 3), 0.4, dtype=torch.float64)
+    assert torch.equal(O.adjust_hue(grey, 0.2), grey)
+    img = torch.rand(3, 4, 6, 3, generator=g, dtype=torch.float64) * 2 - 1
+    flips = torch.tensor([1.0, 0.0, 1.0], dtype=torch.float64)
+    zero = torch.zeros_like(img)
+    out = O.augment(img, flips, 0.01, 0.9, 0.0, zero)
+    for n in range(3):
+        src = img[n].flip(1) if flips[n] > 0.5 else img[n]
+        m = (src + 0.01).mean(dim=(0, 1), keepdim=True)
+        assert float((out[n] - (((src + 0.01) - m) * 0.9 + m)).abs().max()) < 1e-14

@@ -289,3 +289,32 @@ def test_upload_pinned_chunks_roundtrip():
     assert torch.equal(y.cpu(), torch.from_numpy(x))
     small = upload(x[:1], torch.device("cuda"))
     assert torch.equal(small.cpu(), torch.from_numpy(x[:1]))
+
+
+def test_train_step_with_device_augmentation():
+    """`augment: true` (the reference's behaviour): new_image is drawn on the device inside the captured step -
+    a different image every replay, the same sequence for the same seed."""
+    from littlegan_b200.eager_trainer import EagerTrainer
+    oargs = small_args()
+    runs = []
+    for rep in range(2):
+        pargs = product_args(oargs, dtype="fp32", cuda_graph=True, augment=True, seed=7)
+        gen, disc, adj = build_product(pargs, 0)
+        trainer = EagerTrainer(pargs, gen, disc, adj, None)
+        i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=5)
+        imgs, losses = [], []
+        for b in range(11, 16):
+            res = trainer._train_step(b, _ListIterator([(i1, c1), (i2, c2)]), noise=noise)
+            B = pargs.batch_size
+            imgs.append(trainer._static["img3"][2 * B:].float().cpu().clone())
+            losses.append([float(res[3]), float(res[4]), float(res[5])])
+        assert all(torch.isfinite(torch.tensor(l)).all() for l in losses)
+        for a, b in zip(imgs, imgs[1:]):
+            assert not torch.equal(a, b)
+        d = (imgs[0] - i1).abs()
+        flipped = (imgs[0] - i1.flip(2)).abs()
+        per = torch.minimum(d.reshape(4, -1).mean(1), flipped.reshape(4, -1).mean(1))
+        assert float(per.max()) < 0.3 and float(per.min()) > 1e-3     # an augmented copy, not the image itself
+        runs.append((imgs, losses))
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert torch.equal(a, b)

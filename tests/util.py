@@ -32,6 +32,7 @@ def product_args(oargs, **over):
     d = {k: getattr(oargs, k) for k in keys}
     d["attr"] = list(range(oargs.cond_dim))
     d["image_dim"] = oargs.init_dim * 16
+    d["augment"] = False          # oracle comparisons: new_image = real_image_1 unless a test injects one
     d.update(over)
     return Arg.from_dict(**d)
 
