@@ -116,8 +116,10 @@ class EagerTrainer:
         self._chain_streams = {}
         self._rb, self._rb_count = None, 0
         self._aug_state = None
+        self.test_noise = self.test_cond = self.test_image = None
         if getattr(args, "result_dir", None) and getattr(args, "init_dirs", False):
             self._init_dir()
+            self._restore_latest()
 
     # ------------------------------------------------------------------ parameter arenas
     def _build_arenas(self):
@@ -486,10 +488,71 @@ class EagerTrainer:
         return [LossValue(dev[i], slot, self._rb_count, i) for i in range(3)]
 
     # ------------------------------------------------------------------ epoch loop (host glue)
+    def _ckpt_dir(self):
+        a = self.args
+        d = os.path.join(a.result_dir, "checkpoint") if getattr(a, "result_dir", None) else None
+        return d if d and os.path.isdir(d) else None
+
+    def _restore_latest(self):
+        """eager_trainer.py:37-43: with `restore`, load the checkpoint status.json names and resume at its epoch."""
+        d = self._ckpt_dir()
+        if not d or not getattr(self.args, "restore", False):
+            return False
+        status = os.path.join(d, "status.json")
+        if not os.path.isfile(status):
+            return False
+        with open(status) as f:
+            st = json.load(f)
+        ck = os.path.join(d, st.get("latest", ""))
+        if not os.path.isfile(ck):
+            return False
+        print("Loading Checkpoint...")
+        self.load_checkpoint(ck)
+        self.global_epoch = int(st["epoch"])
+        return True
+
+    def _write_status(self, name):
+        with open(os.path.join(self._ckpt_dir(), "status.json"), "w") as f:
+            json.dump({"epoch": self.global_epoch, "latest": name}, f)
+
+    def _interrupted(self, signum, f_name):
+        """eager_trainer.py:171-178: SIGINT saves a checkpoint + status.json and exits."""
+        if self._ckpt_dir():
+            torch.cuda.synchronize()
+            self.save_checkpoint(os.path.join(self._ckpt_dir(), "interrupt.pt"))
+            self._write_status("interrupt.pt")
+            print("\n Checkpoint has been saved")
+        print(signum, f_name)
+        import sys
+        sys.exit(1)
+
+    def _init_test_data(self):
+        """eager_trainer.py:65-83: the fixed (noise, cond, image) triple of the periodic `predict` dumps - re-used
+        from test_data_<env>.npz with `reuse`, else the first batch of the dataset (saved there when possible)."""
+        a = self.args
+        npz = os.path.join(getattr(a, "test_data_dir", "") or "", "test_data_%s.npz" % getattr(a, "env", "sample"))
+        if os.path.isfile(npz) and getattr(a, "reuse", False):
+            data = np.load(npz)
+            self.test_noise, self.test_cond, self.test_image = data["n"], data["c"], data["i"]
+            return
+        print("No reuse test data, generating...")
+        image, cond = self.dataset.get_new_iterator().get_next()
+        to_np = lambda t: t.detach().float().cpu().numpy() if torch.is_tensor(t) else np.asarray(t, np.float32)
+        self.test_image, self.test_cond = to_np(image), to_np(cond)
+        self.test_noise = np.random.default_rng(int(getattr(a, "seed", 0))).standard_normal(
+            (self.test_cond.shape[0], a.noise_dim)).astype(np.float32)
+        if os.path.isdir(os.path.dirname(npz)):
+            np.savez_compressed(npz, n=self.test_noise, c=self.test_cond, i=self.test_image)
+
     def train(self):
         """eager_trainer.py:180-229 (loss scalars are read back every `log_every` steps only)."""
         a = self.args
         log_every = int(getattr(a, "log_every", 50))
+        import signal
+        import threading
+        if threading.current_thread() is threading.main_thread():
+            signal.signal(signal.SIGINT, self._interrupted)
+        dump = bool(getattr(a, "result_dir", None)) and os.path.isdir(os.path.join(a.result_dir, "test"))
         for e in range(self.global_epoch, a.epoch + 1):
             print("Experiment:", a.exp_name, "Epoch:", e, "Starting...")
             self.global_epoch = e
@@ -509,10 +572,20 @@ class EagerTrainer:
                         save_image(result[1], os.path.join(a.result_dir, "train", "gen", "%d-%d.jpg" % (e, b)))
                         if result[2] is not None:
                             save_image(result[2], os.path.join(a.result_dir, "train", "adj", "%d-%d.jpg" % (e, b)))
+                if dump and b % a.freq_test == 0:
+                    if self.test_image is None:
+                        self._init_test_data()
+                    r = a.result_dir
+                    self.predict(self.test_noise, self.test_cond, self.test_image,
+                                 os.path.join(r, "test", "gen", "%d-%d.jpg" % (e, b)),
+                                 os.path.join(r, "test", "disc", "%d-%d.json" % (e, b)),
+                                 os.path.join(r, "test", "adj", "%d-%d.jpg" % (e, b)))
             torch.cuda.synchronize()
             print("Time usage:", time.time() - start_time, "s")
-            if getattr(a, "result_dir", None) and os.path.isdir(os.path.join(a.result_dir, "checkpoint")):
-                self.save_checkpoint(os.path.join(a.result_dir, "checkpoint", "%d.pt" % e))
+            if self._ckpt_dir():
+                self.global_epoch = e + 1                      # a restored run continues with the next epoch
+                self.save_checkpoint(os.path.join(self._ckpt_dir(), "%d.pt" % e))
+                self._write_status("%d.pt" % e)
 
     def _init_dir(self):
         a = self.args

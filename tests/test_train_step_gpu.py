@@ -318,3 +318,37 @@ def test_train_step_with_device_augmentation():
         runs.append((imgs, losses))
     for a, b in zip(runs[0][0], runs[1][0]):
         assert torch.equal(a, b)
+
+
+def test_train_loop_checkpoints_and_resumes(tmp_path):
+    """train(): epoch loop, periodic image / predict dumps, one checkpoint + status.json per epoch; a new trainer
+    with `restore` continues from it (eager_trainer.py:37-43, 180-229)."""
+    from littlegan_b200.dataset import SyntheticCelebA
+    from littlegan_b200.eager_trainer import EagerTrainer
+    oargs = small_args()
+
+    def make(epoch):
+        pargs = product_args(oargs, dtype="fp32", cuda_graph=True, epoch=epoch, freq_gen=2, freq_test=3, restore=True,
+                             reuse=False, init_dirs=True, all_result_dir=str(tmp_path), exp_name="exp",
+                             test_data_dir=str(tmp_path), log_every=2)
+        pargs.result_dir = os.path.join(str(tmp_path), "exp")
+        gen, disc, adj = build_product(pargs, 0)
+        data = SyntheticCelebA(pargs, batches=8, seed=3, pool=2)      # a step draws two batches
+        return EagerTrainer(pargs, gen, disc, adj, data)
+
+    t1 = make(2)
+    assert t1.global_epoch == 1
+    t1.train()
+    r = t1.args.result_dir
+    assert os.path.isfile(os.path.join(r, "checkpoint", "2.pt"))
+    st = json.load(open(os.path.join(r, "checkpoint", "status.json")))
+    assert st == {"epoch": 3, "latest": "2.pt"}
+    assert os.path.isfile(os.path.join(r, "train", "gen", "1-2.jpg")) and os.path.isfile(os.path.join(r, "train", "gen", "2-4.jpg"))
+    assert os.path.isfile(os.path.join(r, "test", "disc", "1-3.json")) and os.path.isfile(os.path.join(r, "test", "adj", "2-3.jpg"))
+    t2 = make(3)
+    assert t2.global_epoch == 3
+    assert torch.equal(t2.P, t1.P) and torch.equal(t2.M, t1.M) and torch.equal(t2.V, t1.V)
+    for k in t1.adam_state:
+        assert torch.equal(t2.adam_state[k], t1.adam_state[k])
+    t2.train()
+    assert os.path.isfile(os.path.join(r, "checkpoint", "3.pt")) and not torch.equal(t2.P, t1.P)
