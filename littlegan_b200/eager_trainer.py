@@ -213,15 +213,16 @@ class EagerTrainer:
         S["cond1"] = rt.empty(B, a.cond_dim, dtype=f32)
         S["cond2"] = rt.empty(B, a.cond_dim, dtype=f32)
         S["noise"] = rt.empty(B, a.noise_dim, dtype=f32)
-        # One image buffer [real_image_1 ; fake_image ; new_image]: the adjuster's input is its first 2B
-        # images (eager_trainer.py:157), the discriminator's batch [fake ; new_image] its last 2B, so ONE encoder
-        # pass over the 3B images serves D(new_image), D(fake) AND the adjuster's encoder(real_image_1 ; fake):
-        # the adjuster shares D's encoder (model.py:119), nothing has been updated yet, and the norm is per
-        # sample - encoder(fake) is the same tensor in both.
+        # One image buffer [real_image_1 | new_image | fake_image] and ONE set of encoder maps over it serve
+        # D(new_image), D(fake) (the discriminator's batch is its last 2B images) AND the adjuster's
+        # encoder([real_image_1 ; fake], eager_trainer.py:157): the adjuster shares D's encoder (model.py:119),
+        # nothing has been updated yet and the norm is per sample, so encoder(fake) is the same tensor in both.
+        # The two real thirds come first so that their encoder pass is one contiguous 2B batch that can run while
+        # the generator is still producing `fake`.
         S["img3"] = rt.empty(3 * B, H, H, C)
-        S["aimg"] = S["img3"][:2 * B]                        # [real_image_1 ; fake_image]
-        S["dimg"] = S["img3"][B:]                            # [fake_image ; new_image]
-        S["fake"] = S["img3"][B:2 * B]
+        S["real1"] = S["img3"][:B]
+        S["dimg"] = S["img3"][B:]                            # [new_image ; fake_image]
+        S["fake"] = S["img3"][2 * B:]
         S["img2"] = rt.empty(B, H, H, C)
         S["aug_params"] = rt.empty(4 + 4 * B, dtype=f32)     # draws + per-image channel means of the augmentation
         S["aimg_t"] = rt.empty(2 * B, H, H, C)               # [real_image_2 ; real_image_1]
@@ -242,13 +243,13 @@ class EagerTrainer:
             if self._aug_state is None:
                 rank = _dist().get_rank() if _dist() is not None else 0
                 self._aug_state = K.augment_state(int(getattr(self.args, "seed", 0)) * 7919 + 13 + rank, self.rt.device)
-            K.augment(S["in_img1"], S["img3"][2 * B:], S["aug_params"], state=self._aug_state)
+            K.augment(S["in_img1"], S["img3"][B:2 * B], S["aug_params"], state=self._aug_state)
         else:
-            K.cast(S["in_new"], S["img3"][2 * B:])
+            K.cast(S["in_new"], S["img3"][B:2 * B])
         K.cast(S["in_img2"], S["img2"])
-        K.cast(S["in_img1"], S["img3"][:B])
+        K.cast(S["in_img1"], S["real1"])
         S["aimg_t"][:B].copy_(S["img2"])
-        S["aimg_t"][B:].copy_(S["aimg"][:B])
+        S["aimg_t"][B:].copy_(S["real1"])
         # eager_trainer.py:155-156
         S["acond_t"][:B].copy_(S["cond2"])
         S["acond_t"][B:].copy_(S["cond1"])
@@ -268,10 +269,27 @@ class EagerTrainer:
         rt.begin_step()
         self._prepare_inputs(S, aug)
 
-        # ---- forward: G, then the encoder on [real_image_1 ; fake ; new_image] (eager_trainer.py:134-137, 157-160)
+        # ---- forward: G, and the encoder on [real_image_1 | new_image | fake] (eager_trainer.py:134-137, 157-160).
+        # The real part of that batch does not depend on G: its encoder pass runs on a side stream while the
+        # (small-batch, GPU-underfilling) generator forward produces `fake`; the fake third follows on this stream.
+        main = torch.cuda.current_stream()
+        off = B if adj_on else 0                                  # where D's batch [new_image ; fake] starts
+        enc_in = S["img3"] if adj_on else S["dimg"]
+        n_real = enc_in.shape[0] - B
+        sliced = (bool(getattr(a, "overlap_chains", True)) and bool(getattr(a, "overlap_encoder", True))
+                  and E.EncoderPass.sliceable(rt, D.encoder, enc_in))
+        if sliced:
+            ep = E.EncoderPass(rt, D.encoder, enc_in)
+            sR = self._chain_stream("R", main)
+            with torch.cuda.stream(sR):
+                ep.run(0, n_real)
         fake, (g_hctx, g_dctx, g_x4) = G.forward_ctx(S["noise"], S["cond2"], out=S["fake"])
-        off = B if adj_on else 0                                  # where D's batch [fake ; new_image] starts
-        outs3, ectx3 = E.encoder_forward(rt, D.encoder, S["img3"] if adj_on else S["dimg"])
+        if sliced:
+            ep.run(n_real, n_real + B)
+            main.wait_stream(sR)
+            outs3, ectx3 = ep.result()
+        else:
+            outs3, ectx3 = E.encoder_forward(rt, D.encoder, enc_in)
         outs = [o[off:] for o in outs3]
         ectx = [(x[off:], z[off:], st[off:], None if xp is None else xp[off:]) for (x, z, st, xp) in ectx3]
 
@@ -283,24 +301,24 @@ class EagerTrainer:
         # stream), and the tensors chains share stay referenced until the join below.
         # The adjuster sub-step (eager_trainer.py:152-164) is the longest chain: it forks first, on a
         # high-priority stream, and the other chains fill in around it.
-        main = torch.cuda.current_stream()
         sA = self._chain_stream("A", main, high=True) if adj_on else None
         if adj_on:
             with torch.cuda.stream(sA):
-                self._adjuster_chain(S, batch_no, [o[:2 * B] for o in outs3])
+                # the adjuster's batch is [real_image_1 ; fake]: rows [:B] and [2B:] of the encoder maps
+                self._adjuster_chain(S, batch_no, [(o[:B], o[2 * B:]) for o in outs3])
 
-        pr, c = E.disc_heads_forward(rt, D, outs[3])              # rows [:B] fake, [B:] new_image
+        pr, c = E.disc_heads_forward(rt, D, outs[3])              # rows [:B] new_image, [B:] fake
 
         # ---- losses + gradients w.r.t. the logits (eager_trainer.py:139-140)
         dl_pr_d = rt.empty(2 * B, 1, dtype=f32)
         dl_c_d = rt.zeros(2 * B, a.cond_dim, dtype=f32)          # fake half: no D-loss term on fake_c
         dl_pr_g = rt.empty(B, 1, dtype=f32)
         dl_c_g = rt.empty(B, a.cond_dim, dtype=f32)
-        K.bce_sigmoid_multi([(c[B:], S["cond1"], 2.0, l_disc, dl_c_d[B:]),
-                             (pr[B:], soft(1.0), 1.0, l_disc, dl_pr_d[B:]),
-                             (pr[:B], soft(0.0), 1.0, l_disc, dl_pr_d[:B]),
-                             (pr[:B], soft(1.0), 1.0, l_gen, dl_pr_g),
-                             (c[:B], S["cond2"], 1.0, l_gen, dl_c_g)])
+        K.bce_sigmoid_multi([(c[:B], S["cond1"], 2.0, l_disc, dl_c_d[:B]),
+                             (pr[:B], soft(1.0), 1.0, l_disc, dl_pr_d[:B]),
+                             (pr[B:], soft(0.0), 1.0, l_disc, dl_pr_d[B:]),
+                             (pr[B:], soft(1.0), 1.0, l_gen, dl_pr_g),
+                             (c[B:], S["cond2"], 1.0, l_gen, dl_c_g)])
 
         # ---- disc_tape.gradient(disc_loss, D weights): both halves, no input gradient (:145)
         sD = self._chain_stream("D", main)
@@ -310,8 +328,8 @@ class EagerTrainer:
             self._reduce_async("Discriminator", batch_no)    # overlaps with the G backward + adjuster step
 
         # ---- gen_tape.gradient(gen_loss, G weights): dgrad-only through D(fake), then G (:149)
-        ectx_f = [(x[:B], z[:B], st[:B], None) for (x, z, st, _) in ectx]
-        g4 = E.disc_heads_backward(rt, D, outs[3][:B], dl_pr_g, dl_c_g, wgrad=False)
+        ectx_f = [(x[B:], z[B:], st[B:], None) for (x, z, st, _) in ectx]
+        g4 = E.disc_heads_backward(rt, D, outs[3][B:], dl_pr_g, dl_c_g, wgrad=False)
         g_img = E.encoder_backward(rt, D.encoder, ectx_f, g4, wgrad=False, input_grad=True)
         dpre = torch.empty_like(fake)
         K.l1_tanh_bwd(fake, S["img2"], g_img, dpre, a.l1_lambda, l_gen)
@@ -355,7 +373,7 @@ class EagerTrainer:
         D, A = self.discriminator, self.adjuster
         f32 = torch.float32
         l_adj = S["loss"][2:3]
-        adj, (a_hctx, a_dctx, a_x4) = A.forward_ctx(S["aimg"], S["acond_in"], enc=enc)
+        adj, (a_hctx, a_dctx, a_x4) = A.forward_ctx(None, S["acond_in"], enc=enc)
         outs2, ectx2 = E.encoder_forward(rt, D.encoder, adj)
         apr, ac = E.disc_heads_forward(rt, D, outs2[3])
         dl_pr_a = rt.empty(2 * B, 1, dtype=f32)

@@ -228,6 +228,59 @@ def encoder_forward(rt, enc, x):
     return outs, ctx
 
 
+def _norm_act_fwd(z, stats, norm, skip, out, a1, a2):
+    """IN + activation (+ additive skip) of a batch.  `skip` may be a tuple of tensors that together cover the
+    batch along N (the train step keeps the encoder maps of [real_image_1 | ... | fake] in one buffer where the
+    adjuster's batch [real_image_1 ; fake] is not contiguous): one launch per piece - the norm is per sample."""
+    if not isinstance(skip, (tuple, list)):
+        K.instnorm_act_fwd(z, stats, norm.gamma, norm.beta, skip, out, norm.epsilon, a1, a2)
+        return
+    lo = 0
+    for sk in skip:
+        hi = lo + sk.shape[0]
+        K.instnorm_act_fwd(z[lo:hi], stats[lo:hi], norm.gamma, norm.beta, sk, out[lo:hi], norm.epsilon, a1, a2)
+        lo = hi
+    assert lo == z.shape[0], "skip pieces must cover the batch"
+
+
+class EncoderPass:
+    """encoder_forward over one batch buffer, run in slices: the norm is per sample, so the slices of a batch are
+    independent passes that may be issued at different times and on different streams (the train step starts the
+    slice that holds the real images while the generator is still producing the fake ones).  All outputs are
+    allocated up front on the constructing stream; run(lo, hi) fills rows [lo, hi) on the CURRENT stream;
+    result() is encoder_forward's (outs, ctx) over the whole batch."""
+
+    def __init__(self, rt, enc, x):
+        self.rt, self.enc, self.x = rt, enc, x
+        N, H, W, _ = x.shape
+        self.stats = rt.zeros(4, N, 2)
+        self.z, self.a = [], []
+        for i in range(4):
+            H, W = H // 2, W // 2
+            self.z.append(rt.empty(N, H, W, enc.convs[i].filters))
+            self.a.append(rt.empty(N, H, W, enc.convs[i].filters))
+
+    @staticmethod
+    def sliceable(rt, enc, x):
+        """False when layer 1 needs a channel-padded copy of the whole image batch (kept in ctx for its wgrad)."""
+        N, Hb, Wb, A = x.shape
+        return A >= 16 or not rt.want_tc or rt.use_tc(K.OP_FPROP, N, Hb, Wb, A, enc.convs[0].filters, 2)
+
+    def run(self, lo, hi):
+        rt, enc = self.rt, self.enc
+        x = self.x[lo:hi]
+        for i in range(4):
+            conv, norm = enc.convs[i], enc.norms[i]
+            z, a, st = self.z[i][lo:hi], self.a[i][lo:hi], self.stats[i][lo:hi]
+            _fprop(rt, conv, x, conv.bias, z, st, 2)
+            K.instnorm_act_fwd(z, st, norm.gamma, norm.beta, None, a, norm.epsilon, 1.0, rt.alpha)
+            x = a
+
+    def result(self):
+        xs = [self.x] + self.a[:3]
+        return self.a, [(xs[i], self.z[i], self.stats[i], None) for i in range(4)]
+
+
 def _norm_act_bwd(rt, g, z, stats, norm, red, conv, wgrad, dy_ready):
     """IN + LeakyReLU backward of one conv layer -> dz; with `wgrad` also d(gamma), d(beta), d(bias)."""
     dz = torch.empty_like(z)
@@ -300,7 +353,7 @@ def decoder_forward(rt, dec, x, skips_after=(None, None, None)):
             K.conv2d_dgrad(x, conv.kernel, conv.bias, z, stats[i], 2, K.ACT_NONE, conv.wpack, tc)
         a = torch.empty_like(z)
         skip = skips_after[i] if i < 3 else None
-        K.instnorm_act_fwd(z, stats[i], norm.gamma, norm.beta, skip, a, norm.epsilon, 1.0, rt.alpha)
+        _norm_act_fwd(z, stats[i], norm, skip, a, 1.0, rt.alpha)
         ctx.append((x, z, stats[i]))
         x = a
     return x, ctx
@@ -404,7 +457,7 @@ def head_forward(rt, dense, norm, xin, out_shape, skip=None):
     stats = rt.zeros(N, 2)
     K.rowstats(h, stats, rt.alpha)
     out = rt.empty(*out_shape)
-    K.instnorm_act_fwd(h, stats, norm.gamma, norm.beta, skip, out, norm.epsilon, rt.alpha, 1.0)
+    _norm_act_fwd(h, stats, norm, skip, out, rt.alpha, 1.0)
     return out, (xin, h, stats)
 
 

@@ -306,7 +306,7 @@ def test_train_step_with_device_augmentation():
         for b in range(11, 16):
             res = trainer._train_step(b, _ListIterator([(i1, c1), (i2, c2)]), noise=noise)
             B = pargs.batch_size
-            imgs.append(trainer._static["img3"][2 * B:].float().cpu().clone())
+            imgs.append(trainer._static["img3"][B:2 * B].float().cpu().clone())
             losses.append([float(res[3]), float(res[4]), float(res[5])])
         assert all(torch.isfinite(torch.tensor(l)).all() for l in losses)
         for a, b in zip(imgs, imgs[1:]):
