@@ -20,6 +20,30 @@ def test_arg_layering(tmp_path):
     b = Arg.from_dict()
     assert b.cond_dim == 7 and b.noise_dim == 93 and b.conv_filter == [384, 256, 128, 64, 32]
     assert b.dtype == "bf16" and b.cuda_graph is True
+    assert b.augment is True                     # the reference always augments new_image (eager_trainer.py:127-131)
+    assert product_args(small_args()).augment is False and product_args(small_args(), augment=True).augment is True
+
+
+def test_loss_value_host_protocol():
+    """LossValue without a device: the ring-slot generation decides between the pinned copy and the fallback."""
+    from littlegan_b200.eager_trainer import LossValue
+
+    class _Ev:
+        def __init__(self):
+            self.waits = 0
+
+        def synchronize(self):
+            self.waits += 1
+
+    host, ev, gen = torch.tensor([1.5, -2.25, 0.125]), _Ev(), [7]
+    dev = torch.tensor([1.5, -2.25, 0.125])
+    v = LossValue(dev[1], (host, ev, gen), 7, 1)
+    assert float(v) == -2.25 and ev.waits == 1 and v.item() == -2.25 and "%.2f" % v.numpy() == "-2.25"
+    assert format(v, ".3f") == "-2.250" and float(v.cpu()) == -2.25
+    host[1] = 99.0
+    gen[0] = 8                                     # the slot now belongs to a later step
+    waits = ev.waits
+    assert float(v) == -2.25 and ev.waits == waits   # read from the step's own device scalar, no event wait
 
 
 def test_builders_surface_and_weight_order():
