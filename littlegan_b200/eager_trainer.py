@@ -263,16 +263,20 @@ class EagerTrainer:
         loss = S["loss"]
         l_gen, l_disc, l_adj = loss[0:1], loss[1:2], loss[2:3]
 
-        E.refresh_packs(rt, self._conv_layers())
-        self.Gd.zero_()
-        loss.zero_()
+        # ---- prologue: the input staging / zeroing (stream P) runs beside the weight packing (this stream); the
+        # generator forward needs only the latter
+        main = torch.cuda.current_stream()
+        sP = self._chain_stream("P", main)
+        with torch.cuda.stream(sP):
+            self.Gd.zero_()
+            loss.zero_()
+            self._prepare_inputs(S, aug)
         rt.begin_step()
-        self._prepare_inputs(S, aug)
+        E.refresh_packs(rt, self._conv_layers())
 
         # ---- forward: G, and the encoder on [real_image_1 | new_image | fake] (eager_trainer.py:134-137, 157-160).
         # The real part of that batch does not depend on G: its encoder pass runs on a side stream while the
         # (small-batch, GPU-underfilling) generator forward produces `fake`; the fake third follows on this stream.
-        main = torch.cuda.current_stream()
         off = B if adj_on else 0                                  # where D's batch [new_image ; fake] starts
         enc_in = S["img3"] if adj_on else S["dimg"]
         n_real = enc_in.shape[0] - B
@@ -281,9 +285,11 @@ class EagerTrainer:
         if sliced:
             ep = E.EncoderPass(rt, D.encoder, enc_in)
             sR = self._chain_stream("R", main)
+            sR.wait_stream(sP)
             with torch.cuda.stream(sR):
                 ep.run(0, n_real)
         fake, (g_hctx, g_dctx, g_x4) = G.forward_ctx(S["noise"], S["cond2"], out=S["fake"])
+        main.wait_stream(sP)
         if sliced:
             ep.run(n_real, n_real + B)
             main.wait_stream(sR)
