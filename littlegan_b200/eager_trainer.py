@@ -340,8 +340,9 @@ class EagerTrainer:
         dpre = torch.empty_like(fake)
         K.l1_tanh_bwd(fake, S["img2"], g_img, dpre, a.l1_lambda, l_gen)
         g = E.generator_tail_backward(rt, G.decoder, G.conv, g_dctx, g_x4, dpre, wgrad=True)
+        self._reduce_async("Generator", batch_no, part=(4, 22))     # decoder + final conv: under the dense backward
         E.head_backward(rt, G.dense, G.norm, g_hctx, g)
-        self._reduce_async("Generator", batch_no)
+        self._reduce_async("Generator", batch_no, part=(0, 4))
 
         main.wait_stream(sD)
         if adj_on:
@@ -394,16 +395,23 @@ class EagerTrainer:
         S["adj"] = adj
         self._reduce_async("Adjuster", batch_no)
 
-    def _reduce_async(self, name, batch_no):
+    def _reduce_async(self, name, batch_no, part=None):
         """Data parallel: average this optimiser's (active range of the) flat gradient arena over the
         ranks on a side stream, so that NCCL runs under the remaining backward work; the ranges of
-        the three optimisers are disjoint and the main stream joins before the first Adam."""
+        the three optimisers are disjoint and the main stream joins before the first Adam.
+        part = (first, last+1) tensor indices of the optimiser: reduce only that bucket of the range (the
+        generator's decoder gradients are complete while its dense-layer gradients are still being computed)."""
         dist = _dist()
         if dist is None:
             return
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream()
         lo, hi = self._range(name, batch_no)
+        if part is not None:
+            offs = self._offsets[name]
+            lo, hi = max(lo, offs[part[0]]), min(hi, offs[part[1]])
+            if lo >= hi:
+                return
         self._comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._comm_stream):
             dist.all_reduce(self.Gd[lo:hi], op=dist.ReduceOp.AVG)
