@@ -272,6 +272,10 @@ int lg_augment_apply(const float* x, const float* params, const float* noise, vo
 
 /* ---- casts ------------------------------------------------------------------------------- */
 int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+/* data_rescale (utils.py:51-52, applied by dataset.py:29 to every decoded image): dst[i] = src[i] / 127.5 - 1 for
+ * n decoded image bytes; dst fp32 or bf16 (dst_dtype).  Both pointers 16-byte aligned.  Replaces the host-side
+ * tf.cast + tf.divide + tf.subtract of the input pipeline: the batch crosses PCIe as bytes. */
+int lg_u8_rescale(const void* src, void* dst, int64_t n, int dst_dtype, void* stream);
 
 /* ---- FID statistics (fid.py:169-188: np.mean / np.cov in fp64) ----------------------------- */
 

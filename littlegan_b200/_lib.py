@@ -61,6 +61,7 @@ SIGNATURES = {
     "lg_augment_prepare": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
     "lg_augment_apply": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "lg_cast": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    "lg_u8_rescale": (_i, [_vp, _vp, _i64, _i, _vp]),
     "lg_fid_accumulate": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lg_fid_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
 }

@@ -406,6 +406,27 @@ __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = from_f<D>(to_f(s[i]));
 }
 
+// data_rescale of utils.py:51-52 on decoded image bytes: y = x / 127.5 - 1 (fp32 division, then the subtraction,
+// each rounded once as TF's two ops are), 16 pixels-bytes per thread
+template <typename D>
+__global__ void u8_rescale_kernel(const uint8_t* __restrict__ s, D* __restrict__ d, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nv = n >> 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(s) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float o[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) o[b] = __fsub_rn(__fdiv_rn((float)((w[q] >> (8 * b)) & 0xffu), 127.5f), 1.0f);
+      stv<D, 4>(d + i * 16 + q * 4, o);
+    }
+  }
+  for (int64_t i = (nv << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    d[i] = from_f<D>(__fsub_rn(__fdiv_rn((float)s[i], 127.5f), 1.0f));
+}
+
 // dst[row][0..Cp) = src[row][0..C) followed by zeros (3-channel images -> 16-channel TMA-able rows)
 template <typename T>
 __global__ void pad_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t rows, int C, int Cp) {
@@ -767,6 +788,21 @@ extern "C" int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int
   else if (src_dtype == LG_BF16 && dst_dtype == LG_F32) cast_kernel<bf16, float><<<gsz, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
   else if (src_dtype == LG_F32 && dst_dtype == LG_F32) cast_kernel<float, float><<<gsz, 256, 0, st>>>((const float*)src, (float*)dst, n);
   else cast_kernel<bf16, bf16><<<gsz, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_u8_rescale(const void* src, void* dst, int64_t n, int dst_dtype, void* stream) {
+  LG_REQUIRE(src && dst && n > 0, "bad arguments");
+  LG_REQUIRE(dst_dtype == LG_F32 || dst_dtype == LG_BF16, "dst_dtype must be LG_F32 or LG_BF16");
+  LG_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+             "src and dst must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t need = ((n + 15) / 16 + 255) / 256;
+  int64_t cap = (int64_t)lg_num_sms() * 8;
+  int gsz = (int)(need < cap ? need : cap);
+  if (dst_dtype == LG_F32) u8_rescale_kernel<float><<<gsz, 256, 0, st>>>((const uint8_t*)src, (float*)dst, n);
+  else u8_rescale_kernel<bf16><<<gsz, 256, 0, st>>>((const uint8_t*)src, (bf16*)dst, n);
   LG_LAUNCH_CHECK();
   return LG_OK;
 }

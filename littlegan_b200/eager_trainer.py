@@ -16,7 +16,7 @@ import torch
 
 from . import engine as E
 from . import kernels as K
-from .utils import save_image, soft, upload
+from .utils import data_rescale, save_image, soft, upload
 
 
 class OutOfRangeError(Exception):
@@ -451,6 +451,10 @@ class EagerTrainer:
     def _to_static(self, dst, src):
         if isinstance(src, np.ndarray):
             src = torch.from_numpy(src)
+        if src.dtype == torch.uint8:
+            # decoded image bytes (dataset.CelebA): data_rescale (utils.py:51-52) runs on the device
+            K.u8_rescale(src.to(dst.device, non_blocking=True).contiguous(), dst)
+            return
         dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
     def _train_step(self, batch_no, iterator, noise=None, new_image=None):
@@ -569,6 +573,8 @@ class EagerTrainer:
             return
         print("No reuse test data, generating...")
         image, cond = self.dataset.get_new_iterator().get_next()
+        if torch.is_tensor(image) and image.dtype == torch.uint8:      # decoded bytes from dataset.CelebA
+            image = data_rescale(image.float())
         to_np = lambda t: t.detach().float().cpu().numpy() if torch.is_tensor(t) else np.asarray(t, np.float32)
         self.test_image, self.test_cond = to_np(image), to_np(cond)
         self.test_noise = np.random.default_rng(int(getattr(a, "seed", 0))).standard_normal(

@@ -363,6 +363,15 @@ def cast(src, dst):
     return dst
 
 
+def u8_rescale(src, dst):
+    """data_rescale (utils.py:51-52) of decoded image bytes on the device: dst = src / 127.5 - 1."""
+    _cuda(src, dst)
+    if src.dtype != torch.uint8 or src.numel() != dst.numel() or not (src.is_contiguous() and dst.is_contiguous()):
+        raise _lib.LittleGANError("u8_rescale: needs a contiguous uint8 source and a destination of the same size")
+    check(_lib.load().lg_u8_rescale(_p(src), _p(dst), src.numel(), dt(dst), _st()), "lg_u8_rescale")
+    return dst
+
+
 # -------------------------------------------------------------------------------------------- FID
 def fid_accumulate(X, shift, S1, S2):
     _cuda(X, shift, S1, S2)

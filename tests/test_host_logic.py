@@ -107,3 +107,74 @@ def test_instance_norm_only_reference_mode():
         InstanceNormalization(axis=3)
     n = InstanceNormalization()
     assert n.epsilon == 1e-3 and tuple(n.gamma.shape) == (1,) and float(n.gamma) == 1.0 and float(n.beta) == 0.0
+
+
+def _write_celeba(tmp_path, n, dim, attrs=6, ext="png", seed=0):
+    """n lossless images + an attribute list in the reference's `<name> a0 a1 ...` form."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    imgs = rng.integers(0, 256, (n, dim, dim, 3), dtype=np.uint8)
+    labs = rng.integers(0, 2, (n, attrs)) * 2 - 1
+    d = tmp_path / "img"
+    d.mkdir()
+    lines = []
+    for i in range(n):
+        name = "%06d.%s" % (i + 1, ext)
+        Image.fromarray(imgs[i], "RGB").save(str(d / name))
+        lines.append(name + " " + " ".join(str(int(v)) for v in labs[i]))
+    (tmp_path / "list.txt").write_text("\n".join(lines) + "\n")
+    return imgs, labs
+
+
+def test_celeba_pipeline_batches_shuffle_and_labels(tmp_path):
+    """dataset.py:8-48: file/attribute pairing, attr filter, soft labels, batch-then-shuffle, short last batch,
+    one pass per iterator; bytes out by default, the reference's fp32 tensors with as_float."""
+    import numpy as np
+    from littlegan_b200.dataset import ALL_LABEL, CelebA
+    from littlegan_b200.eager_trainer import OutOfRangeError
+    from littlegan_b200.utils import soft
+    imgs, labs = _write_celeba(tmp_path, 22, 32)
+    a = Arg.from_dict(batch_size=4, init_dim=2, image_dim=32, attr=[1, 4, 5], image_path=str(tmp_path / "img"),
+                      attr_path=str(tmp_path / "list.txt"), image_ext="png", threads=3, prefetch_batch=1)
+    ds = CelebA(a, seed=3, pin=False)
+    assert ds.batches == 5 and ds.label == [ALL_LABEL[1], ALL_LABEL[4], ALL_LABEL[5]]
+    seen = []
+    for epoch in range(2):
+        it = ds.get_new_iterator()
+        order = []
+        while True:
+            try:
+                image, cond = it.get_next()
+            except OutOfRangeError:
+                break
+            assert image.dtype == torch.uint8 and image.shape[1:] == (32, 32, 3) and cond.dtype == torch.float32
+            lo = int(np.flatnonzero((imgs.reshape(22, -1) == image[0].numpy().reshape(-1)).all(1))[0])
+            assert lo % 4 == 0                                   # batches are formed before the shuffle
+            n = image.shape[0]
+            assert n == (2 if lo == 20 else 4)                   # tf.data keeps the short last batch
+            assert np.array_equal(image.numpy(), imgs[lo:lo + n])
+            want = soft(torch.tensor(labs[lo:lo + n][:, [1, 4, 5]], dtype=torch.float32))
+            assert torch.equal(cond, want)
+            order.append(lo)
+        assert sorted(order) == [0, 4, 8, 12, 16, 20]
+        seen.append(order)
+    assert seen[0] != seen[1]                                    # a new shuffle per epoch
+    f = CelebA(a, seed=3, pin=False, as_float=True).get_new_iterator().get_next()[0]
+    assert f.dtype == torch.float32 and float(f.min()) >= -1 and float(f.max()) <= 1
+    o1 = CelebA(a, seed=9, pin=False).get_new_iterator()
+    o2 = CelebA(a, seed=9, pin=False).get_new_iterator()
+    for _ in range(6):
+        assert torch.equal(o1.get_next()[0], o2.get_next()[0])
+
+
+def test_celeba_rejects_wrong_size_and_short_attr_list(tmp_path):
+    from littlegan_b200.dataset import CelebA
+    _write_celeba(tmp_path, 4, 16, attrs=40)
+    a = Arg.from_dict(batch_size=2, init_dim=2, image_dim=32, attr=None, image_path=str(tmp_path / "img"),
+                      attr_path=str(tmp_path / "list.txt"), image_ext="png", threads=1)
+    with pytest.raises(ValueError):
+        CelebA(a, pin=False).get_new_iterator().get_next()       # 16x16 files, image_dim 32 (tf set_shape)
+    (tmp_path / "list.txt").write_text("000001.png" + " 1" * 40 + "\n")
+    with pytest.raises(ValueError):
+        CelebA(a, pin=False)

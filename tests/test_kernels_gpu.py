@@ -720,3 +720,23 @@ def test_augment_draws_and_noise_statistics():
     out3 = torch.empty_like(out)
     K.augment(x, out3, torch.zeros_like(params), state=state3)
     assert torch.equal(out2, out3) and not torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 4099, 2 * 128 * 128 * 3])
+def test_u8_rescale_is_bit_exact(n):
+    """data_rescale (utils.py:51-52): x / 127.5 - 1 in fp32, two roundings - bit-exact against NumPy; the bf16
+    form is that value rounded once more.  Sizes cover the scalar tail and the 16-byte vector body."""
+    from littlegan_b200 import kernels as K
+    g = torch.Generator().manual_seed(n)
+    x = torch.randint(0, 256, (n,), generator=g, dtype=torch.uint8)
+    if n >= 256:
+        x[:256] = torch.arange(256, dtype=torch.uint8)           # every byte value
+    want = (x.numpy().astype(np.float32) / np.float32(127.5)) - np.float32(1)
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    K.u8_rescale(x.cuda(), out)
+    assert np.array_equal(out.cpu().numpy(), want)
+    outb = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    K.u8_rescale(x.cuda(), outb)
+    assert torch.equal(outb.cpu(), torch.from_numpy(want).to(torch.bfloat16))
+    with pytest.raises(Exception):
+        K.u8_rescale(x.cuda().float(), out)

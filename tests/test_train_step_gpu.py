@@ -352,3 +352,30 @@ def test_train_loop_checkpoints_and_resumes(tmp_path):
         assert torch.equal(t2.adam_state[k], t1.adam_state[k])
     t2.train()
     assert os.path.isfile(os.path.join(r, "checkpoint", "3.pt")) and not torch.equal(t2.P, t1.P)
+
+
+def test_train_step_from_decoded_bytes(tmp_path):
+    """dataset.CelebA -> DevicePrefetcher -> _train_step: uint8 batches are rescaled on the device and give the
+    same step as the reference's host-side data_rescale of the same files."""
+    from littlegan_b200.dataset import CelebA, DevicePrefetcher
+    from littlegan_b200.utils import data_rescale
+    from tests.test_host_logic import _write_celeba
+    oargs = small_args()
+    _write_celeba(tmp_path, 8, 32, attrs=5)
+    extra = dict(image_path=str(tmp_path / "img"), attr_path=str(tmp_path / "list.txt"), image_ext="png",
+                 threads=2, prefetch_batch=1)
+    runs = []
+    for mode in ("bytes", "float"):
+        pargs, gen, disc, adj, trainer, W = _setup(oargs, "fp32")
+        for k, v in extra.items():
+            setattr(pargs, k, v)
+        ds = CelebA(pargs, seed=1, as_float=(mode == "float"))
+        it = ds.get_new_iterator()
+        if mode == "bytes":
+            it = DevicePrefetcher(it, depth=2)
+        noise = torch.randn(4, oargs.noise_dim, generator=torch.Generator().manual_seed(2))
+        res = trainer._train_step(11, it, noise=noise)
+        assert res[0] is True
+        runs.append([float(res[3]), float(res[4]), float(res[5])] + [res[1].float().cpu()])
+        assert trainer._train_step(12, it, noise=noise) == (None,)       # 8 files = 2 batches = one step
+    assert runs[0][:3] == runs[1][:3] and torch.equal(runs[0][3], runs[1][3])
