@@ -277,6 +277,27 @@ int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype,
  * tf.cast + tf.divide + tf.subtract of the input pipeline: the batch crosses PCIe as bytes. */
 int lg_u8_rescale(const void* src, void* dst, int64_t n, int dst_dtype, void* stream);
 
+/* ---- Inception-2015 pool_3 forward (fid.py:36-106: create_inception_graph / get_activations) -- */
+
+/* One conv + folded batch-norm (+ ReLU) unit of the graph, NHWC.  x: N x H x W pixels of x_stride channels, the unit
+ * reads channels [x_off, x_off + Cin).  W fp32 [kh,kw,Cin,Cout] (TF HWIO).  y: N x Ho x Wo pixels of y_stride
+ * channels, the unit writes channels [y_off, y_off + Cout) - the slice of the block's concat output - with
+ * Ho = (H + 2 ph - kh) / stride + 1.  y = relu(scale[co] * conv + shift[co]); scale = gamma / sqrt(var + eps),
+ * shift = beta - mean * scale.  dtype: storage type of x and y (LG_F32 / LG_BF16), accumulation fp32. */
+int lg_conv2d_bn_relu(const void* x, const float* W, const float* scale, const float* shift, void* y, int N, int H,
+                      int Wd, int Cin, int x_stride, int x_off, int kh, int kw, int stride, int ph, int pw, int Cout,
+                      int y_stride, int y_off, int relu, int dtype, void* stream);
+/* k x k pooling with zero padding `pad` into a channel slice.  mode 0: max; 1: mean over the in-bounds taps (TF
+ * AvgPool SAME); 2: mean with the padding counted. */
+int lg_pool2d(const void* x, void* y, int N, int H, int W, int C, int x_stride, int x_off, int k, int stride, int pad,
+              int mode, int y_stride, int y_off, int dtype, void* stream);
+/* pool_3: y fp32 [N,C] = mean over the HW positions of x [N,HW,C]. */
+int lg_global_avgpool(const void* x, float* y, int N, int HW, int C, int dtype, void* stream);
+/* The graph's input stage: TF-1.x ResizeBilinear (align_corners = false) of x [N,H,W,C] (uint8 if src_is_u8, else
+ * fp32, values 0..255) to [N,Ho,Wo,C], then (v - sub) * mul. */
+int lg_resize_bilinear_norm(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, float sub, float mul,
+                            int src_is_u8, int dtype, void* stream);
+
 /* ---- FID statistics (fid.py:169-188: np.mean / np.cov in fp64) ----------------------------- */
 
 /* X [n,d] fp32 features.  S1 double[d] += sum_r (x_r - shift); S2 double[d,d], UPPER triangle

@@ -1,0 +1,153 @@
+// Inception-2015 pool_3 forward for the FID statistics pass (reference fid.py:36-106): the pieces around the
+// convolution GEMMs - TF-1.x bilinear resize + input normalisation, 3x3 max / average pools that write straight into
+// a channel slice of the block's concat output, the final 8x8 mean - and the C-ABI entry points of the family.
+// All of them are HBM-bound gathers: one thread per output element with the channel index fastest, so a warp reads
+// and writes contiguous channel runs.
+#include "common.cuh"
+#include "internal.h"
+
+namespace {
+
+// TF-1.x ResizeBilinear (align_corners = false, no half-pixel centres): src = dst * in / out, then (v - sub) * mul
+template <typename S, typename T>
+__global__ void resize_bilinear_kernel(const S* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Ho,
+                                       int Wo, float sy, float sx, float sub, float mul) {
+  const int64_t total = (int64_t)N * Ho * Wo * C;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % C);
+    int64_t t = e / C;
+    const int ox = (int)(t % Wo); t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const float fy = oy * sy, fx = ox * sx;
+    const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float wy = fy - y0, wx = fx - x0;
+    const S* base = x + (int64_t)n * H * W * C + c;
+    const float v00 = (float)base[((int64_t)y0 * W + x0) * C], v01 = (float)base[((int64_t)y0 * W + x1) * C];
+    const float v10 = (float)base[((int64_t)y1 * W + x0) * C], v11 = (float)base[((int64_t)y1 * W + x1) * C];
+    const float top = v00 + (v01 - v00) * wx, bot = v10 + (v11 - v10) * wx;
+    y[e] = from_f<T>((top + (bot - top) * wy - sub) * mul);
+  }
+}
+
+// mode 0: max; 1: average over the in-bounds taps only (the 2015 graph's AvgPool with SAME padding);
+// 2: average with the padding counted (divisor k*k)
+template <typename T>
+__global__ void pool2d_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xs, int k,
+                              int s, int pad, int Ho, int Wo, int mode, int ys) {
+  const int64_t total = (int64_t)N * Ho * Wo * C;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % C);
+    int64_t t = e / C;
+    const int ox = (int)(t % Wo); t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float acc = mode == 0 ? -INFINITY : 0.f;
+    int cnt = 0;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * s - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * s - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        const float v = to_f(x[(((int64_t)n * H + iy) * W + ix) * xs + c]);
+        acc = mode == 0 ? fmaxf(acc, v) : acc + v;
+        ++cnt;
+      }
+    }
+    if (mode == 1) acc /= (float)cnt;
+    else if (mode == 2) acc /= (float)(k * k);
+    y[(((int64_t)n * Ho + oy) * Wo + ox) * ys + c] = from_f<T>(acc);
+  }
+}
+
+// pool_3: mean over the HW positions of the last map, fp32 out
+template <typename T>
+__global__ void global_avgpool_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
+  const int64_t total = (int64_t)N * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int n = (int)(e / C);
+    const T* p = x + (int64_t)n * HW * C + c;
+    float acc = 0.f;
+    for (int i = 0; i < HW; ++i) acc += to_f(p[(int64_t)i * C]);
+    y[e] = acc / (float)HW;
+  }
+}
+
+inline int grid_for(int64_t total) {
+  int64_t need = (total + 255) / 256, cap = (int64_t)lg_num_sms() * 16;
+  return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+}  // namespace
+
+extern "C" int lg_conv2d_bn_relu(const void* x, const float* W, const float* scale, const float* shift, void* y, int N,
+                                 int H, int Wd, int Cin, int x_stride, int x_off, int kh, int kw, int stride, int ph,
+                                 int pw, int Cout, int y_stride, int y_off, int relu, int dtype, void* stream) {
+  LG_REQUIRE(N > 0 && H > 0 && Wd > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && ph >= 0 && pw >= 0,
+             "invalid geometry");
+  LG_REQUIRE(H + 2 * ph >= kh && Wd + 2 * pw >= kw, "kernel larger than the padded input");
+  LG_REQUIRE(x_off >= 0 && x_off + Cin <= x_stride && y_off >= 0 && y_off + Cout <= y_stride, "channel slice out of range");
+  LG_REQUIRE(dtype == LG_F32 || dtype == LG_BF16, "dtype must be LG_F32 or LG_BF16");
+  LG_REQUIRE(x && W && scale && shift && y, "null pointer");
+  const int64_t M = (int64_t)N * ((H + 2 * ph - kh) / stride + 1) * ((Wd + 2 * pw - kw) / stride + 1);
+  LG_REQUIRE(M < (1ll << 31) && (int64_t)kh * kw * Cin < (1ll << 31), "problem too large");
+  lg_simt_conv_bn(x, W, scale, shift, y, N, H, Wd, Cin, x_stride, x_off, kh, kw, stride, ph, pw, Cout, y_stride, y_off,
+                  relu, dtype, (cudaStream_t)stream);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_pool2d(const void* x, void* y, int N, int H, int W, int C, int x_stride, int x_off, int k, int stride,
+                         int pad, int mode, int y_stride, int y_off, int dtype, void* stream) {
+  LG_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && pad < k, "invalid geometry");
+  LG_REQUIRE(H + 2 * pad >= k && W + 2 * pad >= k, "window larger than the padded input");
+  LG_REQUIRE(mode >= 0 && mode <= 2, "mode: 0 max, 1 average over valid taps, 2 average incl. padding");
+  LG_REQUIRE(x_off >= 0 && x_off + C <= x_stride && y_off >= 0 && y_off + C <= y_stride, "channel slice out of range");
+  LG_REQUIRE(dtype == LG_F32 || dtype == LG_BF16, "dtype must be LG_F32 or LG_BF16");
+  LG_REQUIRE(x && y, "null pointer");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int g = grid_for((int64_t)N * Ho * Wo * C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LG_BF16)
+    pool2d_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x + x_off, (bf16*)y + y_off, N, H, W, C, x_stride, k, stride, pad,
+                                           Ho, Wo, mode, y_stride);
+  else
+    pool2d_kernel<float><<<g, 256, 0, st>>>((const float*)x + x_off, (float*)y + y_off, N, H, W, C, x_stride, k, stride,
+                                            pad, Ho, Wo, mode, y_stride);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_global_avgpool(const void* x, float* y, int N, int HW, int C, int dtype, void* stream) {
+  LG_REQUIRE(x && y && N > 0 && HW > 0 && C > 0, "bad arguments");
+  LG_REQUIRE(dtype == LG_F32 || dtype == LG_BF16, "dtype must be LG_F32 or LG_BF16");
+  const int g = grid_for((int64_t)N * C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LG_BF16) global_avgpool_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, y, N, HW, C);
+  else global_avgpool_kernel<float><<<g, 256, 0, st>>>((const float*)x, y, N, HW, C);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_resize_bilinear_norm(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, float sub,
+                                       float mul, int src_is_u8, int dtype, void* stream) {
+  LG_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, "bad arguments");
+  LG_REQUIRE(dtype == LG_F32 || dtype == LG_BF16, "dtype must be LG_F32 or LG_BF16");
+  const int g = grid_for((int64_t)N * Ho * Wo * C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  if (src_is_u8) {
+    if (dtype == LG_BF16) resize_bilinear_kernel<uint8_t, bf16><<<g, 256, 0, st>>>((const uint8_t*)x, (bf16*)y, N, H, W, C, Ho, Wo, sy, sx, sub, mul);
+    else resize_bilinear_kernel<uint8_t, float><<<g, 256, 0, st>>>((const uint8_t*)x, (float*)y, N, H, W, C, Ho, Wo, sy, sx, sub, mul);
+  } else {
+    if (dtype == LG_BF16) resize_bilinear_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)x, (bf16*)y, N, H, W, C, Ho, Wo, sy, sx, sub, mul);
+    else resize_bilinear_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, Ho, Wo, sy, sx, sub, mul);
+  }
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}

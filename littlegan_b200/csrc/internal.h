@@ -12,6 +12,9 @@ int lg_simt_wgrad(const void* big, const void* small, float* dW, int N, int Hb, 
                   int s, int dtype, cudaStream_t st);
 int lg_simt_dense(const void* A, const float* Bm, const float* bias, void* C, int M, int N, int K, int tA,
                   int tB, int acc, int a_dtype, int c_dtype, cudaStream_t st);
+int lg_simt_conv_bn(const void* x, const float* W, const float* scale, const float* shift, void* y, int N, int H,
+                    int Wd, int Cin, int xs, int xo, int kh, int kw, int s, int ph, int pw, int Cout, int ys, int yo,
+                    int relu, int dtype, cudaStream_t st);
 
 // tcgen05 / TMA path (tc_conv.cu).  Return LG_ERR_UNSUPPORTED when the geometry is not covered.
 // `nb` (may be NULL): fuse the InstanceNorm-backward reduction of the layer below into the epilogue.

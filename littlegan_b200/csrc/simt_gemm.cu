@@ -276,6 +276,49 @@ struct DenseProb {
   __device__ int sample_of(int) const { return 0; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// general conv + folded batch-norm + ReLU (Inception-2015 pool_3 forward, fid.py:36-106): any kh x kw, stride,
+// zero padding; reads a channel slice of an NHWC tensor, writes a channel slice of the block's concat output.
+//   y[m=(n,i,j)][co] = relu(scale[co] * sum_k=(ky,kx,c) x[n, s*i+ky-ph, s*j+kx-pw, c] * W[k][co] + shift[co])
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct ConvBnProb {
+  static constexpr bool A_KFAST = true, B_KFAST = false, HAS_STATS = false;
+  const T* x; const float* W; const float* scale; const float* shift; T* y; double* stats;
+  int M, N, K;                 // M = Nimg*Ho*Wo, N = Cout, K = kh*kw*Cin
+  int H, Wd, Cin, xs, Ho, Wo, kw, s, ph, pw, ys, relu;
+  struct MCtx { int n, y0, x0; bool ok; };
+  struct NCtx { int n; };
+  struct KCtx { int ky, kx, c, k; };
+  __device__ void set_slice(int) {}
+  __device__ int k_begin() const { return 0; }
+  __device__ int k_end() const { return K; }
+  __device__ MCtx prep_m(int m) const {
+    MCtx c; c.ok = m < M;
+    int j = m % Wo, t = m / Wo, i = t % Ho; c.n = t / Ho;
+    c.y0 = s * i - ph; c.x0 = s * j - pw; return c;
+  }
+  __device__ NCtx prep_n(int n) const { return NCtx{n}; }
+  __device__ KCtx prep_k(int k) const {
+    KCtx c; c.k = k; int tap = k / Cin; c.c = k - tap * Cin; c.ky = tap / kw; c.kx = tap - kw * c.ky; return c;
+  }
+  __device__ float load_a(const MCtx& m, const KCtx& k) const {
+    int yy = m.y0 + k.ky, xx = m.x0 + k.kx;
+    if (!m.ok || yy < 0 || yy >= H || xx < 0 || xx >= Wd) return 0.f;
+    return to_f(x[(((int64_t)m.n * H + yy) * Wd + xx) * xs + k.c]);
+  }
+  __device__ float load_b(const KCtx& k, const NCtx& n) const {
+    return n.n < N ? W[(int64_t)k.k * N + n.n] : 0.f;
+  }
+  __device__ float store(int m, int n, float v) const {
+    v = fmaf(v, scale[n], shift[n]);
+    if (relu) v = fmaxf(v, 0.f);
+    y[(int64_t)m * ys + n] = from_f<T>(v);
+    return v;
+  }
+  __device__ int sample_of(int) const { return 0; }
+};
+
 template <class P>
 int launch(P p, int zslices, cudaStream_t st) {
   dim3 grid((p.M + TM - 1) / TM, (p.N + TN - 1) / TN, zslices);
@@ -348,6 +391,25 @@ int lg_simt_wgrad(const void* big, const void* small, float* dW, int N, int Hb, 
                   int s, int dtype, cudaStream_t st) {
   return dtype == LG_BF16 ? simt_wgrad_t<bf16>(big, small, dW, N, Hb, Wb, A, B, s, st)
                           : simt_wgrad_t<float>(big, small, dW, N, Hb, Wb, A, B, s, st);
+}
+
+template <typename T>
+static int simt_conv_bn_t(const void* x, const float* W, const float* scale, const float* shift, void* y, int N,
+                          int H, int Wd, int Cin, int xs, int xo, int kh, int kw, int s, int ph, int pw, int Cout,
+                          int ys, int yo, int relu, cudaStream_t st) {
+  ConvBnProb<T> p;
+  p.x = (const T*)x + xo; p.W = W; p.scale = scale; p.shift = shift; p.y = (T*)y + yo; p.stats = nullptr;
+  p.H = H; p.Wd = Wd; p.Cin = Cin; p.xs = xs; p.kw = kw; p.s = s; p.ph = ph; p.pw = pw; p.ys = ys; p.relu = relu;
+  p.Ho = (H + 2 * ph - kh) / s + 1; p.Wo = (Wd + 2 * pw - kw) / s + 1;
+  p.M = N * p.Ho * p.Wo; p.N = Cout; p.K = kh * kw * Cin;
+  return launch(p, 1, st);
+}
+int lg_simt_conv_bn(const void* x, const float* W, const float* scale, const float* shift, void* y, int N, int H,
+                    int Wd, int Cin, int xs, int xo, int kh, int kw, int s, int ph, int pw, int Cout, int ys, int yo,
+                    int relu, int dtype, cudaStream_t st) {
+  return dtype == LG_BF16
+             ? simt_conv_bn_t<bf16>(x, W, scale, shift, y, N, H, Wd, Cin, xs, xo, kh, kw, s, ph, pw, Cout, ys, yo, relu, st)
+             : simt_conv_bn_t<float>(x, W, scale, shift, y, N, H, Wd, Cin, xs, xo, kh, kw, s, ph, pw, Cout, ys, yo, relu, st);
 }
 
 template <typename TA, typename TC, bool TRA, bool TRB>

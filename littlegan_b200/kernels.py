@@ -408,3 +408,52 @@ def augment(x, out, params, state=None, noise=None, draw=True):
     check(lib.lg_augment_apply(_p(x), _p(params), _p(noise), _p(state), AUG_NOISE_STD, _p(out), N, H, W, dt(out),
                                _st()), "lg_augment_apply")
     return out
+
+
+# ------------------------------------------------------------------- Inception pool_3 forward (FID)
+POOL_MAX, POOL_AVG_VALID, POOL_AVG_PADDED = 0, 1, 2
+
+
+def conv2d_bn_relu(x, W, scale, shift, y, y_off, stride=1, pad=(0, 0), x_off=0, cin=None, relu=True):
+    """One conv + folded-BN + ReLU unit: x [N,H,W,Cx] (channels [x_off, x_off+cin)), W fp32 [kh,kw,cin,cout] ->
+    channels [y_off, y_off+cout) of y [N,Ho,Wo,Cy]."""
+    _cuda(x, W, scale, shift, y)
+    N, H, Wd, Cx = x.shape
+    kh, kw, ci, co = W.shape
+    cin = Cx - x_off if cin is None else cin
+    Ho, Wo = (H + 2 * pad[0] - kh) // stride + 1, (Wd + 2 * pad[1] - kw) // stride + 1
+    if ci != cin or tuple(y.shape[:3]) != (N, Ho, Wo) or x.dtype != y.dtype or W.dtype != torch.float32:
+        raise _lib.LittleGANError("conv2d_bn_relu: shapes / dtypes do not match the geometry")
+    check(_lib.load().lg_conv2d_bn_relu(_p(x), _p(W), _p(scale), _p(shift), _p(y), N, H, Wd, cin, Cx, x_off, kh, kw,
+                                        stride, pad[0], pad[1], co, y.shape[3], y_off, int(relu), dt(x), _st()),
+          "lg_conv2d_bn_relu")
+    return y
+
+
+def pool2d(x, y, y_off, k, stride, pad, mode):
+    _cuda(x, y)
+    N, H, Wd, C = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (Wd + 2 * pad - k) // stride + 1
+    if tuple(y.shape[:3]) != (N, Ho, Wo) or x.dtype != y.dtype:
+        raise _lib.LittleGANError("pool2d: output shape / dtype does not match the geometry")
+    check(_lib.load().lg_pool2d(_p(x), _p(y), N, H, Wd, C, C, 0, k, stride, pad, mode, y.shape[3], y_off, dt(x), _st()),
+          "lg_pool2d")
+    return y
+
+
+def global_avgpool(x, y):
+    _cuda(x, y)
+    N, H, Wd, C = x.shape
+    check(_lib.load().lg_global_avgpool(_p(x), _p(y), N, H * Wd, C, dt(x), _st()), "lg_global_avgpool")
+    return y
+
+
+def resize_bilinear_norm(x, y, sub, mul):
+    """TF-1.x ResizeBilinear of x [N,H,W,C] (uint8 or fp32, 0..255) to y's spatial size, then (v - sub) * mul."""
+    _cuda(x, y)
+    if x.dtype not in (torch.uint8, torch.float32):
+        raise _lib.LittleGANError("resize_bilinear_norm: source must be uint8 or fp32")
+    N, H, Wd, C = x.shape
+    check(_lib.load().lg_resize_bilinear_norm(_p(x), _p(y), N, H, Wd, C, y.shape[1], y.shape[2], sub, mul,
+                                              int(x.dtype == torch.uint8), dt(y), _st()), "lg_resize_bilinear_norm")
+    return y

@@ -1,0 +1,145 @@
+"""Inception-2015 pool_3 forward (fid.py:36-106) against the CPU oracle, through the C-ABI.  -m gpu."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import inception_oracle as IO
+from tests.util import rel_err, tol
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, dtype=torch.float32, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g, dtype=torch.float64) * scale).to(dtype)
+
+
+# (N, H, W, Cin, Cout, (kh,kw), stride, (ph,pw))
+UNIT_GEOMS = [
+    (2, 31, 31, 3, 32, (3, 3), 2, (0, 0)),      # Conv2d_1a: RGB in, stride 2, VALID, odd size
+    (2, 17, 17, 24, 40, (1, 7), 1, (0, 3)),     # 1x7
+    (2, 17, 17, 24, 40, (7, 1), 1, (3, 0)),     # 7x1
+    (3, 9, 9, 48, 64, (5, 5), 1, (2, 2)),       # 5x5 SAME
+    (1, 8, 8, 80, 70, (1, 1), 1, (0, 0)),       # 1x1, Cout not a multiple of the tile
+    (2, 9, 11, 16, 24, (3, 3), 2, (0, 0)),      # non-square map
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("geom", UNIT_GEOMS)
+def test_conv_bn_relu_unit(geom, dtype):
+    """One unit reading a channel slice and writing a channel slice of a wider concat buffer."""
+    from littlegan_b200 import kernels as K
+    N, H, W_, Cin, Cout, (kh, kw), s, (ph, pw) = geom
+    x_off, y_off, Cx, Cy = 8, 16, Cin + 16, Cout + 24
+    x = _rand((N, H, W_, Cx), 1, dtype)
+    Wt = _rand((kh, kw, Cin, Cout), 2, torch.float32, 0.2)
+    scale = _rand((Cout,), 3).abs() + 0.5
+    shift = _rand((Cout,), 4)
+    xs = x[..., x_off:x_off + Cin].double().permute(0, 3, 1, 2)
+    ref = F.conv2d(xs, Wt.double().permute(3, 2, 0, 1), None, stride=s, padding=(ph, pw))
+    ref = F.relu(ref * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]).permute(0, 2, 3, 1)
+    y = torch.full((N, ref.shape[1], ref.shape[2], Cy), 7.0, dtype=dtype, device="cuda")
+    K.conv2d_bn_relu(x.cuda(), Wt.cuda(), scale.cuda(), shift.cuda(), y, y_off, stride=s, pad=(ph, pw), x_off=x_off,
+                     cin=Cin)
+    assert rel_err(y[..., y_off:y_off + Cout], ref) < tol(dtype)
+    keep = torch.cat([y[..., :y_off], y[..., y_off + Cout:]], -1)
+    assert bool((keep == 7.0).all())                       # the rest of the concat buffer is untouched
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [(3, 2, 0, 0), (3, 1, 1, 0), (3, 1, 1, 1), (3, 1, 1, 2)])
+def test_pool2d_modes(cfg, dtype):
+    from littlegan_b200 import kernels as K
+    k, s, p, mode = cfg
+    x = _rand((2, 17, 15, 24), 5, dtype)
+    xc = x.double().permute(0, 3, 1, 2)
+    if mode == 0:
+        ref = F.max_pool2d(xc, k, stride=s, padding=p)
+    else:
+        ref = F.avg_pool2d(xc, k, stride=s, padding=p, count_include_pad=(mode == 2))
+    ref = ref.permute(0, 2, 3, 1)
+    y = torch.zeros(2, ref.shape[1], ref.shape[2], 40, dtype=dtype, device="cuda")
+    K.pool2d(x.cuda(), y, 8, k, s, p, mode)
+    assert rel_err(y[..., 8:32], ref) < (1e-6 if dtype == torch.float32 else 1e-2)
+    assert float(y[..., :8].abs().max()) == 0 and float(y[..., 32:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("src", ["u8", "f32"])
+def test_resize_bilinear_tf1_and_normalise(src):
+    from littlegan_b200 import kernels as K
+    g = torch.Generator().manual_seed(6)
+    img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
+    ref = (IO.resize_bilinear_tf1(img.double(), 299, 299) - 128.0) / 128.0
+    x = img.cuda() if src == "u8" else img.float().cuda()
+    y = torch.empty(2, 299, 299, 3, dtype=torch.float32, device="cuda")
+    K.resize_bilinear_norm(x, y, 128.0, 1.0 / 128.0)
+    assert float((y.double().cpu() - ref).abs().max()) < 1e-5
+    # an up-scale whose source coordinates hit the last row / column clamp
+    small = torch.randint(0, 256, (1, 5, 7, 3), generator=g, dtype=torch.uint8)
+    ref2 = IO.resize_bilinear_tf1(small.double(), 11, 13)
+    y2 = torch.empty(1, 11, 13, 3, dtype=torch.float32, device="cuda")
+    K.resize_bilinear_norm(small.cuda(), y2, 0.0, 1.0)
+    assert float((y2.double().cpu() - ref2).abs().max()) < 1e-4
+
+
+def test_global_avgpool():
+    from littlegan_b200 import kernels as K
+    x = _rand((3, 8, 8, 2048), 7)
+    y = torch.empty(3, 2048, dtype=torch.float32, device="cuda")
+    K.global_avgpool(x.cuda(), y)
+    assert rel_err(y, x.double().mean(dim=(1, 2))) < 1e-6
+
+
+@pytest.mark.parametrize("variant", ["fid", "torchvision"])
+def test_pool3_features_match_oracle_fp32(variant):
+    """Every unit's activation and pool_3 within 1e-4 (max-norm relative) of the fp64 oracle on identical weights."""
+    from littlegan_b200.inception import InceptionPool3
+    W = IO.random_weights(seed=1)
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
+    ora = IO.InceptionOracle(W, variant=variant, dtype=torch.float64)
+    want = ora(img.double())
+    net = InceptionPool3(weights=W, dtype="fp32", fid_variant=(variant == "fid"))
+    net.taps = {}
+    got = net(img.numpy())
+    assert got.shape == (2, 2048) and got.dtype == torch.float32 and got.is_cuda
+    worst = 0.0
+    assert set(ora.taps) == set(net.taps)
+    for name, ref in ora.taps.items():
+        e = rel_err(net.taps[name], ref)
+        worst = max(worst, e)
+        assert e < 1e-4, (name, e)
+    assert rel_err(got, want) < 1e-4
+    print("worst unit error %.2e, pool_3 %.2e" % (worst, rel_err(got, want)))
+
+
+def test_pool3_features_bf16_storage():
+    from littlegan_b200.inception import InceptionPool3
+    W = IO.random_weights(seed=2)
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
+    want = IO.InceptionOracle(W, dtype=torch.float64)(img.double())
+    got = InceptionPool3(weights=W, dtype="bf16")(img)
+    # 20 units deep with every activation rounded to bf16: errors accumulate beyond the per-layer 2e-2
+    assert rel_err(got, want) < 6e-2
+    d = (got.double().cpu() - want).norm() / want.norm()
+    assert float(d) < 2e-2
+
+
+def test_fid_statistics_through_the_inception_session():
+    """fid.calculate_activation_statistics(images, sess=InceptionPool3) == np.mean / np.cov of the oracle features
+    (fid.py:169-188), including the dropped N % batch tail (fid.py:89-94)."""
+    from littlegan_b200 import fid
+    from littlegan_b200.inception import InceptionPool3
+    from oracle import fid_oracle
+    W = IO.random_weights(seed=5)
+    g = torch.Generator().manual_seed(8)
+    imgs = torch.randint(0, 256, (7, 64, 64, 3), generator=g, dtype=torch.uint8).numpy()
+    net = InceptionPool3(weights=W)
+    mu, sigma = fid.calculate_activation_statistics(imgs, net, batch_size=3)
+    feats = IO.InceptionOracle(W, dtype=torch.float64)(torch.from_numpy(imgs[:6]).double()).numpy()
+    mu_ref, sigma_ref = fid_oracle.activation_statistics(feats)
+    assert np.abs(mu - mu_ref).max() < 1e-4 * np.abs(mu_ref).max()
+    assert np.abs(sigma - sigma_ref).max() < 1e-3 * np.abs(sigma_ref).max()

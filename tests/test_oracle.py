@@ -207,3 +207,45 @@ def test_augment_restatement_against_colorsys_and_definitions():
         src = img[n].flip(1) if flips[n] > 0.5 else img[n]
         m = (src + 0.01).mean(dim=(0, 1), keepdim=True)
         assert float((out[n] - (((src + 0.01) - m) * 0.9 + m)).abs().max()) < 1e-14
+
+
+def test_inception_oracle_wiring_matches_torchvision():
+    """The Inception oracle is pinned against torchvision's inception_v3 (same published architecture) with
+    identical weights; the FID variant then changes only the three documented pooling details."""
+    import pytest
+    torchvision = pytest.importorskip("torchvision")
+    from oracle import inception_oracle as IO
+    m = torchvision.models.inception_v3(weights=None, aux_logits=False, transform_input=False, init_weights=False).eval()
+    W = IO.random_weights(seed=1)
+    g = torch.Generator().manual_seed(0)
+    sd = m.state_dict()
+    for name, p in W.items():
+        p["gamma"] = torch.rand(p["beta"].shape, generator=g) * 0.5 + 0.75
+        sd[name + ".conv.weight"].copy_(p["W"].permute(3, 2, 0, 1))
+        sd[name + ".bn.weight"].copy_(p["gamma"])
+        sd[name + ".bn.bias"].copy_(p["beta"])
+        sd[name + ".bn.running_mean"].copy_(p["mean"])
+        sd[name + ".bn.running_var"].copy_(p["var"])
+    assert len(W) == 94 and sum(k.endswith("conv.weight") for k in sd) == 94
+    m.load_state_dict(sd)
+    x = torch.randn(1, 3, 299, 299, generator=g)
+    got = {}
+    m.avgpool.register_forward_hook(lambda mod, i, o: got.__setitem__("pool", o.flatten(1)))
+    with torch.no_grad():
+        m(x)
+        f = IO.InceptionOracle(W, variant="torchvision", dtype=torch.float32).features(x)
+        f_fid = IO.InceptionOracle(W, variant="fid", dtype=torch.float32).features(x)
+    assert f.shape == (1, 2048)
+    assert float((f - got["pool"]).abs().max() / got["pool"].abs().max()) < 1e-5
+    assert float((f - f_fid).abs().max()) > 1e-2          # max pool in Mixed_7c, pad-excluding averages
+
+
+def test_inception_resize_is_tf1_bilinear():
+    """TF-1.x ResizeBilinear (align_corners=False): src = dst * in/out; identity at equal size, exact 2x up-sample
+    values, last row/column clamped."""
+    from oracle import inception_oracle as IO
+    x = torch.arange(12, dtype=torch.float64).reshape(1, 3, 4, 1)
+    assert torch.equal(IO.resize_bilinear_tf1(x, 3, 4), x)
+    y = IO.resize_bilinear_tf1(x, 6, 8)
+    assert torch.allclose(y[0, 0, :, 0], torch.tensor([0, 0.5, 1, 1.5, 2, 2.5, 3, 3], dtype=torch.float64))
+    assert torch.allclose(y[0, :, 0, 0], torch.tensor([0, 2, 4, 6, 8, 8], dtype=torch.float64))
