@@ -284,9 +284,14 @@ int lg_u8_rescale(const void* src, void* dst, int64_t n, int dst_dtype, void* st
  * channels, the unit writes channels [y_off, y_off + Cout) - the slice of the block's concat output - with
  * Ho = (H + 2 ph - kh) / stride + 1.  y = relu(scale[co] * conv + shift[co]); scale = gamma / sqrt(var + eps),
  * shift = beta - mean * scale.  dtype: storage type of x and y (LG_F32 / LG_BF16), accumulation fp32. */
-int lg_conv2d_bn_relu(const void* x, const float* W, const float* scale, const float* shift, void* y, int N, int H,
-                      int Wd, int Cin, int x_stride, int x_off, int kh, int kw, int stride, int ph, int pw, int Cout,
-                      int y_stride, int y_off, int relu, int dtype, void* stream);
+int lg_conv2d_bn_relu(const void* x, const float* W, const void* wpack, const float* scale, const float* shift, void* y,
+                      int N, int H, int Wd, int Cin, int x_stride, int x_off, int kh, int kw, int stride, int ph, int pw,
+                      int Cout, int y_stride, int y_off, int relu, int dtype, void* stream);
+/* bf16 tensor-core operand of a unit's kernel (W fp32 [kh,kw,Cin,Cout] -> wpack), made once per weight set.  With W or
+ * wpack NULL: the size of wpack in bytes, 0 when the geometry has no tensor-core form (Cin % 8 or Cout % 16 != 0; such
+ * units run the SIMT path of lg_conv2d_bn_relu from W).  lg_conv2d_bn_relu takes the tcgen05 path when dtype is
+ * LG_BF16, wpack is given and the channel strides / offsets are multiples of 8; otherwise W is required. */
+int lg_pack_conv_bn_weights(const float* W, void* wpack, int Cin, int kh, int kw, int Cout, void* stream);
 /* k x k pooling with zero padding `pad` into a channel slice.  mode 0: max; 1: mean over the in-bounds taps (TF
  * AvgPool SAME); 2: mean with the padding counted. */
 int lg_pool2d(const void* x, void* y, int N, int H, int W, int C, int x_stride, int x_off, int k, int stride, int pad,

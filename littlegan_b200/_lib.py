@@ -62,7 +62,8 @@ SIGNATURES = {
     "lg_augment_apply": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "lg_cast": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "lg_u8_rescale": (_i, [_vp, _vp, _i64, _i, _vp]),
-    "lg_conv2d_bn_relu": (_i, [_vp] * 5 + [_i] * 16 + [_vp]),
+    "lg_conv2d_bn_relu": (_i, [_vp] * 6 + [_i] * 16 + [_vp]),
+    "lg_pack_conv_bn_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "lg_pool2d": (_i, [_vp, _vp] + [_i] * 13 + [_vp]),
     "lg_global_avgpool": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "lg_resize_bilinear_norm": (_i, [_vp, _vp] + [_i] * 6 + [_f, _f, _i, _i, _vp]),

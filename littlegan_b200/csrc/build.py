@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "simt_gemm.cu", "elementwise.cu", "fid.cu", "tc_conv.cu", "tc_wgrad.cu", "tc_deconv_small.cu", "tc_conv_cin3.cu", "tc_dgrad4.cu", "heads.cu", "tc_rowconv.cu", "tc_rowdeconv.cu", "tc_rowdgrad.cu", "tc_rowwgrad.cu", "augment.cu", "inception.cu"]
+SOURCES = ["api.cu", "simt_gemm.cu", "elementwise.cu", "fid.cu", "tc_conv.cu", "tc_wgrad.cu", "tc_deconv_small.cu", "tc_conv_cin3.cu", "tc_dgrad4.cu", "heads.cu", "tc_rowconv.cu", "tc_rowdeconv.cu", "tc_rowdgrad.cu", "tc_rowwgrad.cu", "augment.cu", "inception.cu", "tc_convbn.cu"]
 HEADERS = ["common.cuh", "internal.h", "tc_ptx.cuh", "tc_host.cuh", "norm_bwd.cuh", os.path.join(ROOT, "include", "littlegan_b200.h")]
 LIB = os.path.join(os.path.dirname(HERE), "liblittlegan_b200.so")
 STAMP = LIB + ".stamp"

@@ -85,19 +85,37 @@ inline int grid_for(int64_t total) {
 
 }  // namespace
 
-extern "C" int lg_conv2d_bn_relu(const void* x, const float* W, const float* scale, const float* shift, void* y, int N,
-                                 int H, int Wd, int Cin, int x_stride, int x_off, int kh, int kw, int stride, int ph,
-                                 int pw, int Cout, int y_stride, int y_off, int relu, int dtype, void* stream) {
+extern "C" int lg_pack_conv_bn_weights(const float* W, void* wpack, int Cin, int kh, int kw, int Cout, void* stream) {
+  LG_REQUIRE(Cin > 0 && kh > 0 && kw > 0 && Cout > 0, "invalid geometry");
+  if (W == nullptr || wpack == nullptr) return (int)lg_tc_convbn_pack_bytes(Cin, kh, kw, Cout);
+  int r = lg_tc_convbn_pack(W, wpack, Cin, kh, kw, Cout, (cudaStream_t)stream);
+  if (r != LG_OK) { lg_set_error("%s: geometry has no tensor-core form", __func__); return r; }
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_conv2d_bn_relu(const void* x, const float* W, const void* wpack, const float* scale, const float* shift,
+                                 void* y, int N, int H, int Wd, int Cin, int x_stride, int x_off, int kh, int kw,
+                                 int stride, int ph, int pw, int Cout, int y_stride, int y_off, int relu, int dtype,
+                                 void* stream) {
   LG_REQUIRE(N > 0 && H > 0 && Wd > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && ph >= 0 && pw >= 0,
              "invalid geometry");
   LG_REQUIRE(H + 2 * ph >= kh && Wd + 2 * pw >= kw, "kernel larger than the padded input");
   LG_REQUIRE(x_off >= 0 && x_off + Cin <= x_stride && y_off >= 0 && y_off + Cout <= y_stride, "channel slice out of range");
   LG_REQUIRE(dtype == LG_F32 || dtype == LG_BF16, "dtype must be LG_F32 or LG_BF16");
-  LG_REQUIRE(x && W && scale && shift && y, "null pointer");
+  LG_REQUIRE(x && (W || wpack) && scale && shift && y, "null pointer");
   const int64_t M = (int64_t)N * ((H + 2 * ph - kh) / stride + 1) * ((Wd + 2 * pw - kw) / stride + 1);
-  LG_REQUIRE(M < (1ll << 31) && (int64_t)kh * kw * Cin < (1ll << 31), "problem too large");
-  lg_simt_conv_bn(x, W, scale, shift, y, N, H, Wd, Cin, x_stride, x_off, kh, kw, stride, ph, pw, Cout, y_stride, y_off,
-                  relu, dtype, (cudaStream_t)stream);
+  LG_REQUIRE(M < (1ll << 31) - 128 && (int64_t)kh * kw * Cin < (1ll << 31), "problem too large");
+  if (dtype == LG_BF16 && wpack != nullptr &&
+      lg_tc_convbn_supported(Cin, x_stride, x_off, kh, kw, Cout, y_stride, y_off) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(wpack)) & 15) == 0) {
+    lg_tc_convbn(x, wpack, scale, shift, y, N, H, Wd, Cin, x_stride, x_off, kh, kw, stride, ph, pw, Cout, y_stride, y_off,
+                 relu, (cudaStream_t)stream);
+  } else {
+    LG_REQUIRE(W != nullptr, "this geometry / dtype runs the fp32-accumulate SIMT path and needs the fp32 kernel W");
+    lg_simt_conv_bn(x, W, scale, shift, y, N, H, Wd, Cin, x_stride, x_off, kh, kw, stride, ph, pw, Cout, y_stride, y_off,
+                    relu, dtype, (cudaStream_t)stream);
+  }
   LG_LAUNCH_CHECK();
   return LG_OK;
 }

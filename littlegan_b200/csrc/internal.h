@@ -15,6 +15,13 @@ int lg_simt_dense(const void* A, const float* Bm, const float* bias, void* C, in
 int lg_simt_conv_bn(const void* x, const float* W, const float* scale, const float* shift, void* y, int N, int H,
                     int Wd, int Cin, int xs, int xo, int kh, int kw, int s, int ph, int pw, int Cout, int ys, int yo,
                     int relu, int dtype, cudaStream_t st);
+// tcgen05 conv + BN + ReLU unit (tc_convbn.cu): bf16 maps, Cin % 8 == 0, Cout % 16 == 0
+int lg_tc_convbn_supported(int Cin, int x_stride, int x_off, int kh, int kw, int Cout, int y_stride, int y_off);
+int64_t lg_tc_convbn_pack_bytes(int Cin, int kh, int kw, int Cout);
+int lg_tc_convbn_pack(const float* W, void* wpack, int Cin, int kh, int kw, int Cout, cudaStream_t st);
+int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const float* shift, void* y, int N, int H, int Wd,
+                 int Cin, int xs, int xo, int kh, int kw, int s, int ph, int pw, int Cout, int ys, int yo, int relu,
+                 cudaStream_t st);
 
 // tcgen05 / TMA path (tc_conv.cu).  Return LG_ERR_UNSUPPORTED when the geometry is not covered.
 // `nb` (may be NULL): fuse the InstanceNorm-backward reduction of the layer below into the epilogue.

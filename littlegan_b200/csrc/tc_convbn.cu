@@ -1,0 +1,269 @@
+// General conv + folded batch-norm + ReLU unit of the Inception-2015 pool_3 graph (fid.py:36-106) on tcgen05:
+// an implicit GEMM  y[pos][co] = sum_k patch[pos][k] * W[k][co]  with  k = (ky, kx, c), any kh x kw / stride / padding /
+// odd map sizes (299, 149, 147, 73, 71, 35, 17, 8 do not tile into TMA boxes, so the patch matrix is gathered).
+//
+//   * 8 builder warps gather the A operand: thread (m, half) owns output position m of the 128-position tile and
+//     fetches 16-byte runs (8 channels of one tap - channel counts are multiples of 8) straight from the NHWC map into
+//     the no-swizzle K-major core-matrix layout [k-chunk of 8][position][16 B]; out-of-image taps and the K / M tails
+//     are zero runs.  The same threads copy the stage's weight block, prepacked on the host side of the ABI in exactly
+//     its shared-memory image, so both operands land with plain 16-byte stores + one proxy fence.
+//   * one elected thread issues 128 x Ncols x 16 tcgen05.mma over a 3-4 stage mbarrier ring into one of two TMEM
+//     accumulators (Ncols <= 256, Cout > 256 is split into equal column tiles);
+//   * 4 epilogue warps read the accumulator (tcgen05.ld), apply scale / shift / ReLU and write bf16 rows into the
+//     unit's channel slice of the block's concat buffer - while the next tile's MMAs run into the other accumulator.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "internal.h"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int KC = 64;                      // k per stage: 8 chunks of 8
+constexpr int PLANE = 128 * 16;             // one k-chunk plane of A: 128 positions x 16 B
+constexpr int A_STAGE = (KC / 8) * PLANE;   // 16 KB
+constexpr int BUILDERS = 256;
+constexpr int THREADS = BUILDERS + 32 + 128;
+constexpr int MAX_STAGES = 4;
+
+struct CBParams {
+  const bf16* x; const bf16* wpack; const float* scale; const float* shift; bf16* y;
+  int H, W, Cin, xs, Ho, Wo, kw, s, ph, pw, ys, relu;
+  int M, K, Cout, Ncols, n_tiles, m_tiles, KS, stages, b_stage;   // b_stage = Ncols * KC * 2 bytes
+};
+
+__global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.stages * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * p.b_stage);
+  uint64_t* full = bars;                      // [MAX_STAGES] builders -> MMA   (256 arrivals)
+  uint64_t* empty = bars + MAX_STAGES;        // [MAX_STAGES] MMA -> builders
+  uint64_t* tfull = bars + 2 * MAX_STAGES;    // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;               // [2] epilogue -> MMA            (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sscale = reinterpret_cast<float*>(tmem_slot + 4);
+  float* sshift = sscale + p.Cout;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.Ncols) tmem_cols <<= 1;
+
+  for (int e = threadIdx.x; e < p.Cout; e += THREADS) { sscale[e] = p.scale[e]; sshift[e] = p.shift[e]; }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_STAGES; ++i) { tc::mbar_init(&full[i], BUILDERS); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, tmem_cols);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ builders
+    const int m = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int b_vecs = p.b_stage >> 4;                         // uint4 per weight stage (<= 2048)
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+      const int gm = mt * 128 + m;
+      const bool row_ok = gm < p.M;
+      int n = 0, y0 = 0, x0 = 0;
+      if (row_ok) {
+        const int hw = p.Ho * p.Wo;
+        n = gm / hw;
+        const int r = gm - n * hw, oy = r / p.Wo, ox = r - oy * p.Wo;
+        y0 = p.s * oy - p.ph; x0 = p.s * ox - p.pw;
+      }
+      const bf16* ximg = p.x + (int64_t)n * p.H * p.W * p.xs;
+      const uint4* wsrc = reinterpret_cast<const uint4*>(p.wpack) + (int64_t)nt * p.KS * b_vecs;
+      for (int ks = 0; ks < p.KS; ++ks) {
+        // global loads first (in flight while the ring slot is still being read by the tensor core)
+        uint4 av[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = ks * KC + (half * 4 + q) * 8;
+          av[q] = make_uint4(0, 0, 0, 0);
+          if (row_ok && k < p.K) {
+            const int tap = k / p.Cin, c = k - tap * p.Cin;
+            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+            const int yy = y0 + ky, xx = x0 + kx;
+            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+              av[q] = __ldg(reinterpret_cast<const uint4*>(ximg + ((int64_t)yy * p.W + xx) * p.xs + c));
+          }
+        }
+        uint4 bv[8];
+        const uint4* wst = wsrc + (int64_t)ks * b_vecs;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = threadIdx.x + q * BUILDERS;
+          bv[q] = e < b_vecs ? __ldg(wst + e) : make_uint4(0, 0, 0, 0);
+        }
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* a_dst = sA + stage * A_STAGE + m * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(a_dst + (half * 4 + q) * PLANE) = av[q];
+        uint4* b_dst = reinterpret_cast<uint4*>(sB + stage * p.b_stage);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = threadIdx.x + q * BUILDERS;
+          if (e < b_vecs) b_dst[e] = bv[q];
+        }
+        tc::fence_proxy_async();                               // generic writes -> async (tensor core) proxy
+        tc::mbar_arrive(&full[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc(128, p.Ncols, 0, 0);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        tc::mbar_wait(&tempty[acc], aphase ^ 1);
+        tc::fence_after_sync();
+        for (int ks = 0; ks < p.KS; ++ks) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(sA + stage * A_STAGE);
+          const uint32_t sb = tc::smem_u32(sB + stage * p.b_stage);
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint64_t da = tc::make_sdesc(sa + kk * 2 * PLANE, PLANE, 128, 0u);       // LBO = plane, SBO = 8 rows
+            const uint64_t db = tc::make_sdesc(sb + kk * 256, 128, (KC / 8) * 128, 0u);
+            tc::mma_bf16(tmem_base + acc * p.Ncols, da, db, idesc, (ks | kk) != 0);
+          }
+          tc::mma_commit(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0; uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+      const int gm = mt * 128 + row;
+      const int c0 = nt * p.Ncols;
+      bf16* orow = p.y + (int64_t)gm * p.ys + c0;
+      tc::mbar_wait(&tfull[acc], aphase);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Ncols);
+      for (int cb = 0; cb < p.Ncols; cb += 16) {
+        float v[16];
+        tc::tmem_ld16(taddr + cb, v);                          // warp-collective: every lane, also past the M tail
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          float a = fmaf(v[e], sscale[c0 + cb + e], sshift[c0 + cb + e]);
+          float b = fmaf(v[e + 1], sscale[c0 + cb + e + 1], sshift[c0 + cb + e + 1]);
+          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (gm < p.M) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + cb);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; aphase ^= 1; }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// W fp32 [K][Cout] -> per (column tile, k stage) the bf16 shared-memory image of the B operand:
+// no-swizzle K-major core matrices, byte offset (b>>3)*1024 + (k>>3)*128 + (b&7)*16 + (k&7)*2 inside a stage block
+__global__ void convbn_pack_kernel(const float* __restrict__ W, bf16* __restrict__ out, int K, int Cout, int Ncols,
+                                   int n_tiles, int KS) {
+  const int64_t total = (int64_t)n_tiles * KS * Ncols * KC;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int kl = (int)(e % KC);
+    int64_t t = e / KC;
+    const int b = (int)(t % Ncols); t /= Ncols;
+    const int ks = (int)(t % KS);
+    const int nt = (int)(t / KS);
+    const int k = ks * KC + kl;
+    const float v = k < K ? W[(int64_t)k * Cout + nt * Ncols + b] : 0.f;
+    const int64_t block = ((int64_t)nt * KS + ks) * Ncols * KC;
+    const int off = (b >> 3) * 512 + (kl >> 3) * 64 + (b & 7) * 8 + (kl & 7);      // in bf16 elements
+    out[block + off] = __float2bfloat16_rn(v);
+  }
+}
+
+struct Plan { int Ncols, n_tiles, KS; };
+inline bool plan(int Cin, int kh, int kw, int Cout, Plan* pl) {
+  if (Cin % 8 != 0 || Cout % 16 != 0) return false;
+  const int nt = (Cout + 255) / 256;
+  if (Cout % (16 * nt) != 0) return false;
+  pl->n_tiles = nt; pl->Ncols = Cout / nt; pl->KS = (kh * kw * Cin + KC - 1) / KC;
+  return true;
+}
+
+}  // namespace
+
+int lg_tc_convbn_supported(int Cin, int x_stride, int x_off, int kh, int kw, int Cout, int y_stride, int y_off) {
+  Plan pl;
+  return plan(Cin, kh, kw, Cout, &pl) && x_stride % 8 == 0 && x_off % 8 == 0 && y_stride % 8 == 0 && y_off % 8 == 0;
+}
+
+int64_t lg_tc_convbn_pack_bytes(int Cin, int kh, int kw, int Cout) {
+  Plan pl;
+  if (!plan(Cin, kh, kw, Cout, &pl)) return 0;
+  return (int64_t)pl.n_tiles * pl.KS * pl.Ncols * KC * 2;
+}
+
+int lg_tc_convbn_pack(const float* W, void* wpack, int Cin, int kh, int kw, int Cout, cudaStream_t st) {
+  Plan pl;
+  if (!plan(Cin, kh, kw, Cout, &pl)) return LG_ERR_UNSUPPORTED;
+  const int64_t total = (int64_t)pl.n_tiles * pl.KS * pl.Ncols * KC;
+  int g = (int)((total + 255) / 256);
+  if (g > lg_num_sms() * 16) g = lg_num_sms() * 16;
+  convbn_pack_kernel<<<g, 256, 0, st>>>(W, (bf16*)wpack, kh * kw * Cin, Cout, pl.Ncols, pl.n_tiles, pl.KS);
+  return LG_OK;
+}
+
+int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const float* shift, void* y, int N, int H, int Wd,
+                 int Cin, int xs, int xo, int kh, int kw, int s, int ph, int pw, int Cout, int ys, int yo, int relu,
+                 cudaStream_t st) {
+  Plan pl;
+  if (!plan(Cin, kh, kw, Cout, &pl)) return LG_ERR_UNSUPPORTED;
+  CBParams p;
+  p.x = (const bf16*)x + xo; p.wpack = (const bf16*)wpack; p.scale = scale; p.shift = shift; p.y = (bf16*)y + yo;
+  p.H = H; p.W = Wd; p.Cin = Cin; p.xs = xs; p.kw = kw; p.s = s; p.ph = ph; p.pw = pw; p.ys = ys; p.relu = relu;
+  p.Ho = (H + 2 * ph - kh) / s + 1; p.Wo = (Wd + 2 * pw - kw) / s + 1;
+  p.M = N * p.Ho * p.Wo; p.K = kh * kw * Cin; p.Cout = Cout;
+  p.Ncols = pl.Ncols; p.n_tiles = pl.n_tiles; p.KS = pl.KS; p.m_tiles = (p.M + 127) / 128;
+  p.b_stage = pl.Ncols * KC * 2;
+  int stages = (200 * 1024) / (A_STAGE + p.b_stage);
+  p.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+  const size_t shm = (size_t)p.stages * (A_STAGE + p.b_stage) + 1024 + 256 + 2 * (size_t)Cout * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(convbn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = lg_even_grid(tiles, lg_num_sms());
+  convbn_kernel<<<grid, THREADS, shm, st>>>(p);
+  return LG_OK;
+}

@@ -142,7 +142,10 @@ class InceptionPool3:
             if p.get("gamma") is not None:
                 scale = scale * p["gamma"].double()
             shift = p["beta"].double() - p["mean"].double() * scale
-            self.params[u["name"]] = tuple(t.to(self.device, torch.float32).contiguous() for t in (W, scale, shift))
+            W, scale, shift = (t.to(self.device, torch.float32).contiguous() for t in (W, scale, shift))
+            # bf16 mode: the unit's kernel as the tensor-core operand, packed once (None: SIMT path, e.g. the RGB stem)
+            wpack = K.pack_conv_bn_weights(W) if self.act_dtype == torch.bfloat16 else None
+            self.params[u["name"]] = (W, scale, shift, wpack)
         self.taps = None                      # set to a dict to keep every unit's output (layer-parity tests)
 
     # ------------------------------------------------------------------ executor
@@ -150,11 +153,11 @@ class InceptionPool3:
         return torch.empty(n, h, w, c, dtype=self.act_dtype, device=self.device)
 
     def _run_conv(self, u, x, y=None, y_off=0):
-        W, scale, shift = self.params[u["name"]]
+        W, scale, shift, wpack = self.params[u["name"]]
         if y is None:
             ho, wo = _out_hw(x.shape[1], x.shape[2], u["k"], u["s"], u["p"])
             y = self._new(x.shape[0], ho, wo, u["cout"])
-        K.conv2d_bn_relu(x, W, scale, shift, y, y_off, stride=u["s"], pad=u["p"])
+        K.conv2d_bn_relu(x, W, scale, shift, y, y_off, stride=u["s"], pad=u["p"], wpack=wpack)
         if self.taps is not None:
             self.taps[u["name"]] = y[..., y_off:y_off + u["cout"]]
         return y

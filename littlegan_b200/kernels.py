@@ -414,18 +414,32 @@ def augment(x, out, params, state=None, noise=None, draw=True):
 POOL_MAX, POOL_AVG_VALID, POOL_AVG_PADDED = 0, 1, 2
 
 
-def conv2d_bn_relu(x, W, scale, shift, y, y_off, stride=1, pad=(0, 0), x_off=0, cin=None, relu=True):
+def pack_conv_bn_weights(W):
+    """bf16 tensor-core operand of a unit's kernel W [kh,kw,cin,cout] (fp32, CUDA), or None when the geometry has no
+    tensor-core form."""
+    _cuda(W)
+    kh, kw, ci, co = W.shape
+    lib = _lib.load()
+    nbytes = lib.lg_pack_conv_bn_weights(None, None, ci, kh, kw, co, None)
+    if nbytes <= 0:
+        return None
+    wpack = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    check(lib.lg_pack_conv_bn_weights(_p(W), _p(wpack), ci, kh, kw, co, _st()), "lg_pack_conv_bn_weights")
+    return wpack
+
+
+def conv2d_bn_relu(x, W, scale, shift, y, y_off, stride=1, pad=(0, 0), x_off=0, cin=None, relu=True, wpack=None):
     """One conv + folded-BN + ReLU unit: x [N,H,W,Cx] (channels [x_off, x_off+cin)), W fp32 [kh,kw,cin,cout] ->
-    channels [y_off, y_off+cout) of y [N,Ho,Wo,Cy]."""
-    _cuda(x, W, scale, shift, y)
+    channels [y_off, y_off+cout) of y [N,Ho,Wo,Cy].  bf16 maps with `wpack` run on the tensor cores."""
+    _cuda(x, W, scale, shift, y, wpack)
     N, H, Wd, Cx = x.shape
     kh, kw, ci, co = W.shape
     cin = Cx - x_off if cin is None else cin
     Ho, Wo = (H + 2 * pad[0] - kh) // stride + 1, (Wd + 2 * pad[1] - kw) // stride + 1
     if ci != cin or tuple(y.shape[:3]) != (N, Ho, Wo) or x.dtype != y.dtype or W.dtype != torch.float32:
         raise _lib.LittleGANError("conv2d_bn_relu: shapes / dtypes do not match the geometry")
-    check(_lib.load().lg_conv2d_bn_relu(_p(x), _p(W), _p(scale), _p(shift), _p(y), N, H, Wd, cin, Cx, x_off, kh, kw,
-                                        stride, pad[0], pad[1], co, y.shape[3], y_off, int(relu), dt(x), _st()),
+    check(_lib.load().lg_conv2d_bn_relu(_p(x), _p(W), _p(wpack), _p(scale), _p(shift), _p(y), N, H, Wd, cin, Cx, x_off,
+                                        kh, kw, stride, pad[0], pad[1], co, y.shape[3], y_off, int(relu), dt(x), _st()),
           "lg_conv2d_bn_relu")
     return y
 

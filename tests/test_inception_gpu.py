@@ -17,32 +17,44 @@ def _rand(shape, seed, dtype=torch.float32, scale=1.0):
 
 # (N, H, W, Cin, Cout, (kh,kw), stride, (ph,pw))
 UNIT_GEOMS = [
-    (2, 31, 31, 3, 32, (3, 3), 2, (0, 0)),      # Conv2d_1a: RGB in, stride 2, VALID, odd size
-    (2, 17, 17, 24, 40, (1, 7), 1, (0, 3)),     # 1x7
-    (2, 17, 17, 24, 40, (7, 1), 1, (3, 0)),     # 7x1
+    (2, 31, 31, 3, 32, (3, 3), 2, (0, 0)),      # Conv2d_1a: RGB in, stride 2, VALID, odd size (SIMT in every mode)
+    (2, 17, 17, 24, 48, (1, 7), 1, (0, 3)),     # 1x7
+    (2, 17, 17, 24, 48, (7, 1), 1, (3, 0)),     # 7x1
     (3, 9, 9, 48, 64, (5, 5), 1, (2, 2)),       # 5x5 SAME
-    (1, 8, 8, 80, 70, (1, 1), 1, (0, 0)),       # 1x1, Cout not a multiple of the tile
-    (2, 9, 11, 16, 24, (3, 3), 2, (0, 0)),      # non-square map
+    (1, 8, 8, 80, 80, (1, 1), 1, (0, 0)),       # 1x1, K = 80 (K tail inside a 64-wide stage)
+    (2, 9, 11, 16, 32, (3, 3), 2, (0, 0)),      # non-square map, stride 2
+    (2, 8, 8, 448, 384, (3, 3), 1, (1, 1)),     # Mixed_7 dbl_2: K = 4032 (63 stages), Cout split into 2 column tiles
+    (1, 35, 35, 64, 96, (3, 3), 1, (1, 1)),     # Mixed_5: 1225 positions = 10 tiles, M tail of 73 rows
+    (3, 8, 8, 128, 320, (1, 1), 1, (0, 0)),     # Cout 320 = 2 x 160 columns
+    (2, 17, 17, 40, 24, (3, 3), 1, (1, 1)),     # Cout % 16 != 0: no tensor-core form, SIMT also in bf16
 ]
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16-tc"])
 @pytest.mark.parametrize("geom", UNIT_GEOMS)
-def test_conv_bn_relu_unit(geom, dtype):
-    """One unit reading a channel slice and writing a channel slice of a wider concat buffer."""
+def test_conv_bn_relu_unit(geom, mode):
+    """One unit reading a channel slice and writing a channel slice of a wider concat buffer; bf16 maps on the SIMT
+    path (from W) and on the tcgen05 path (from the packed operand)."""
     from littlegan_b200 import kernels as K
+    dtype = torch.float32 if mode == "fp32" else torch.bfloat16
     N, H, W_, Cin, Cout, (kh, kw), s, (ph, pw) = geom
     x_off, y_off, Cx, Cy = 8, 16, Cin + 16, Cout + 24
     x = _rand((N, H, W_, Cx), 1, dtype)
     Wt = _rand((kh, kw, Cin, Cout), 2, torch.float32, 0.2)
     scale = _rand((Cout,), 3).abs() + 0.5
     shift = _rand((Cout,), 4)
+    wpack = None
+    if mode == "bf16-tc":
+        wpack = K.pack_conv_bn_weights(Wt.cuda())
+        assert (wpack is not None) == (Cin % 8 == 0 and Cout % 16 == 0)
+        Wt = Wt.to(torch.bfloat16).float()                # the tensor-core operand is W rounded to bf16
     xs = x[..., x_off:x_off + Cin].double().permute(0, 3, 1, 2)
     ref = F.conv2d(xs, Wt.double().permute(3, 2, 0, 1), None, stride=s, padding=(ph, pw))
     ref = F.relu(ref * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]).permute(0, 2, 3, 1)
     y = torch.full((N, ref.shape[1], ref.shape[2], Cy), 7.0, dtype=dtype, device="cuda")
     K.conv2d_bn_relu(x.cuda(), Wt.cuda(), scale.cuda(), shift.cuda(), y, y_off, stride=s, pad=(ph, pw), x_off=x_off,
-                     cin=Cin)
+                     cin=Cin, wpack=wpack)
+    torch.cuda.synchronize()
     assert rel_err(y[..., y_off:y_off + Cout], ref) < tol(dtype)
     keep = torch.cat([y[..., :y_off], y[..., y_off + Cout:]], -1)
     assert bool((keep == 7.0).all())                       # the rest of the concat buffer is untouched
@@ -75,7 +87,8 @@ def test_resize_bilinear_tf1_and_normalise(src):
     x = img.cuda() if src == "u8" else img.float().cuda()
     y = torch.empty(2, 299, 299, 3, dtype=torch.float32, device="cuda")
     K.resize_bilinear_norm(x, y, 128.0, 1.0 / 128.0)
-    assert float((y.double().cpu() - ref).abs().max()) < 1e-5
+    # the kernel computes source coordinates in fp32 as TF's op does (dst * float(in/out)); the oracle in fp64
+    assert float((y.double().cpu() - ref).abs().max()) < 1e-4
     # an up-scale whose source coordinates hit the last row / column clamp
     small = torch.randint(0, 256, (1, 5, 7, 3), generator=g, dtype=torch.uint8)
     ref2 = IO.resize_bilinear_tf1(small.double(), 11, 13)
@@ -121,7 +134,9 @@ def test_pool3_features_bf16_storage():
     g = torch.Generator().manual_seed(4)
     img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
     want = IO.InceptionOracle(W, dtype=torch.float64)(img.double())
-    got = InceptionPool3(weights=W, dtype="bf16")(img)
+    net = InceptionPool3(weights=W, dtype="bf16")
+    assert sum(p[3] is not None for p in net.params.values()) == 93          # all but the RGB stem unit on tcgen05
+    got = net(img)
     # 20 units deep with every activation rounded to bf16: errors accumulate beyond the per-layer 2e-2
     assert rel_err(got, want) < 6e-2
     d = (got.double().cpu() - want).norm() / want.norm()
