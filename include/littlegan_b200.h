@@ -299,9 +299,10 @@ int lg_pool2d(const void* x, void* y, int N, int H, int W, int C, int x_stride, 
 /* pool_3: y fp32 [N,C] = mean over the HW positions of x [N,HW,C]. */
 int lg_global_avgpool(const void* x, float* y, int N, int HW, int C, int dtype, void* stream);
 /* The graph's input stage: TF-1.x ResizeBilinear (align_corners = false) of x [N,H,W,C] (uint8 if src_is_u8, else
- * fp32, values 0..255) to [N,Ho,Wo,C], then (v - sub) * mul. */
-int lg_resize_bilinear_norm(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, float sub, float mul,
-                            int src_is_u8, int dtype, void* stream);
+ * fp32, values 0..255) to y [N,Ho,Wo,Cpad], then (v - sub) * mul; channels [C, Cpad) of y are zero (Cpad = 8 makes an
+ * RGB pixel one 16-byte run, the form the tensor-core conv unit reads). */
+int lg_resize_bilinear_norm(const void* x, void* y, int N, int H, int W, int C, int Cpad, int Ho, int Wo, float sub,
+                            float mul, int src_is_u8, int dtype, void* stream);
 
 /* ---- FID statistics (fid.py:169-188: np.mean / np.cov in fp64) ----------------------------- */
 

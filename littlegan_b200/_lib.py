@@ -66,7 +66,7 @@ SIGNATURES = {
     "lg_pack_conv_bn_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "lg_pool2d": (_i, [_vp, _vp] + [_i] * 13 + [_vp]),
     "lg_global_avgpool": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "lg_resize_bilinear_norm": (_i, [_vp, _vp] + [_i] * 6 + [_f, _f, _i, _i, _vp]),
+    "lg_resize_bilinear_norm": (_i, [_vp, _vp] + [_i] * 7 + [_f, _f, _i, _i, _vp]),
     "lg_fid_accumulate": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lg_fid_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
 }

@@ -8,15 +8,18 @@
 
 namespace {
 
-// TF-1.x ResizeBilinear (align_corners = false, no half-pixel centres): src = dst * in / out, then (v - sub) * mul
+// TF-1.x ResizeBilinear (align_corners = false, no half-pixel centres): src = dst * in / out, then (v - sub) * mul.
+// The output pixel has Cp >= C channels, the extra ones zero (RGB -> 8 channels = one 16-byte run per pixel, which
+// puts the first conv unit on the tensor-core path).
 template <typename S, typename T>
-__global__ void resize_bilinear_kernel(const S* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Ho,
-                                       int Wo, float sy, float sx, float sub, float mul) {
-  const int64_t total = (int64_t)N * Ho * Wo * C;
+__global__ void resize_bilinear_kernel(const S* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int Cp,
+                                       int Ho, int Wo, float sy, float sx, float sub, float mul) {
+  const int64_t total = (int64_t)N * Ho * Wo * Cp;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int c = (int)(e % C);
-    int64_t t = e / C;
+    const int c = (int)(e % Cp);
+    if (c >= C) { y[e] = from_f<T>(0.f); continue; }
+    int64_t t = e / Cp;
     const int ox = (int)(t % Wo); t /= Wo;
     const int oy = (int)(t % Ho);
     const int n = (int)(t / Ho);
@@ -61,6 +64,50 @@ __global__ void pool2d_kernel(const T* __restrict__ x, T* __restrict__ y, int N,
     if (mode == 1) acc /= (float)cnt;
     else if (mode == 2) acc /= (float)(k * k);
     y[(((int64_t)n * Ho + oy) * Wo + ox) * ys + c] = from_f<T>(acc);
+  }
+}
+
+// bf16 maps whose channel counts / slice offsets are multiples of 8: one thread per (output pixel, 8 channels),
+// 16-byte loads and stores (the scalar kernel above moves 2 bytes per instruction)
+__global__ void pool2d_vec8_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C8, int xs,
+                                   int k, int s, int pad, int Ho, int Wo, int mode, int ys) {
+  const int64_t total = (int64_t)N * Ho * Wo * C8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % C8) * 8;
+    int64_t t = e / C8;
+    const int ox = (int)(t % Wo); t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = mode == 0 ? -INFINITY : 0.f;
+    int cnt = 0;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * s - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * s - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + iy) * W + ix) * xs + c));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          if (mode == 0) { acc[2 * i] = fmaxf(acc[2 * i], f.x); acc[2 * i + 1] = fmaxf(acc[2 * i + 1], f.y); }
+          else { acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        }
+        ++cnt;
+      }
+    }
+    const float div = mode == 1 ? (float)cnt : (float)(k * k);
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      oh[i] = mode == 0 ? __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1])
+                        : __floats2bfloat162_rn(acc[2 * i] / div, acc[2 * i + 1] / div);
+    *reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + oy) * Wo + ox) * ys + c) = o;
   }
 }
 
@@ -131,7 +178,11 @@ extern "C" int lg_pool2d(const void* x, void* y, int N, int H, int W, int C, int
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int g = grid_for((int64_t)N * Ho * Wo * C);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == LG_BF16)
+  if (dtype == LG_BF16 && ((C | x_stride | x_off | y_stride | y_off) & 7) == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+    pool2d_vec8_kernel<<<grid_for((int64_t)N * Ho * Wo * (C / 8)), 256, 0, st>>>(
+        (const bf16*)x + x_off, (bf16*)y + y_off, N, H, W, C / 8, x_stride, k, stride, pad, Ho, Wo, mode, y_stride);
+  else if (dtype == LG_BF16)
     pool2d_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x + x_off, (bf16*)y + y_off, N, H, W, C, x_stride, k, stride, pad,
                                            Ho, Wo, mode, y_stride);
   else
@@ -152,19 +203,19 @@ extern "C" int lg_global_avgpool(const void* x, float* y, int N, int HW, int C, 
   return LG_OK;
 }
 
-extern "C" int lg_resize_bilinear_norm(const void* x, void* y, int N, int H, int W, int C, int Ho, int Wo, float sub,
-                                       float mul, int src_is_u8, int dtype, void* stream) {
-  LG_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, "bad arguments");
+extern "C" int lg_resize_bilinear_norm(const void* x, void* y, int N, int H, int W, int C, int Cpad, int Ho, int Wo,
+                                       float sub, float mul, int src_is_u8, int dtype, void* stream) {
+  LG_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && Cpad >= C && Ho > 0 && Wo > 0, "bad arguments");
   LG_REQUIRE(dtype == LG_F32 || dtype == LG_BF16, "dtype must be LG_F32 or LG_BF16");
-  const int g = grid_for((int64_t)N * Ho * Wo * C);
+  const int g = grid_for((int64_t)N * Ho * Wo * Cpad);
   cudaStream_t st = (cudaStream_t)stream;
   const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
   if (src_is_u8) {
-    if (dtype == LG_BF16) resize_bilinear_kernel<uint8_t, bf16><<<g, 256, 0, st>>>((const uint8_t*)x, (bf16*)y, N, H, W, C, Ho, Wo, sy, sx, sub, mul);
-    else resize_bilinear_kernel<uint8_t, float><<<g, 256, 0, st>>>((const uint8_t*)x, (float*)y, N, H, W, C, Ho, Wo, sy, sx, sub, mul);
+    if (dtype == LG_BF16) resize_bilinear_kernel<uint8_t, bf16><<<g, 256, 0, st>>>((const uint8_t*)x, (bf16*)y, N, H, W, C, Cpad, Ho, Wo, sy, sx, sub, mul);
+    else resize_bilinear_kernel<uint8_t, float><<<g, 256, 0, st>>>((const uint8_t*)x, (float*)y, N, H, W, C, Cpad, Ho, Wo, sy, sx, sub, mul);
   } else {
-    if (dtype == LG_BF16) resize_bilinear_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)x, (bf16*)y, N, H, W, C, Ho, Wo, sy, sx, sub, mul);
-    else resize_bilinear_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, Ho, Wo, sy, sx, sub, mul);
+    if (dtype == LG_BF16) resize_bilinear_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)x, (bf16*)y, N, H, W, C, Cpad, Ho, Wo, sy, sx, sub, mul);
+    else resize_bilinear_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, Cpad, Ho, Wo, sy, sx, sub, mul);
   }
   LG_LAUNCH_CHECK();
   return LG_OK;

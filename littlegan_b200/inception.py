@@ -132,6 +132,7 @@ class InceptionPool3:
         excl = fid_variant if avg_excludes_pad is None else avg_excludes_pad
         self.avg_mode = K.POOL_AVG_VALID if excl else K.POOL_AVG_PADDED
         weights = random_weights(seed) if weights is None else weights
+        self.in_pad = 8 if self.act_dtype == torch.bfloat16 else 3      # channels per pixel of the resized input
         self.params = {}
         for u in _units(self.prog):
             p = weights[u["name"]]
@@ -142,6 +143,9 @@ class InceptionPool3:
             if p.get("gamma") is not None:
                 scale = scale * p["gamma"].double()
             shift = p["beta"].double() - p["mean"].double() * scale
+            if self.act_dtype == torch.bfloat16 and u["cin"] % 8 != 0:
+                # the RGB stem: zero kernel rows for the zero channels the input stage pads each pixel with
+                W = torch.cat([W, W.new_zeros(W.shape[0], W.shape[1], self.in_pad - u["cin"], W.shape[3])], 2)
             W, scale, shift = (t.to(self.device, torch.float32).contiguous() for t in (W, scale, shift))
             # bf16 mode: the unit's kernel as the tensor-core operand, packed once (None: SIMT path, e.g. the RGB stem)
             wpack = K.pack_conv_bn_weights(W) if self.act_dtype == torch.bfloat16 else None
@@ -211,6 +215,8 @@ class InceptionPool3:
     @torch.no_grad()
     def features_from_normalised(self, x):
         """x [b,299,299,3] NHWC already resized and normalised -> pool_3 [b,2048] fp32."""
+        if x.shape[3] < self.in_pad:
+            x = torch.nn.functional.pad(x, (0, self.in_pad - x.shape[3])).contiguous()
         for st in self.prog:
             if isinstance(st, dict):
                 x = self._run_conv(st, x)
@@ -230,10 +236,10 @@ class InceptionPool3:
         if x.dtype != torch.uint8:
             x = x.to(torch.float32)
         x = x.contiguous()
-        y = self._new(x.shape[0], 299, 299, x.shape[3])
+        y = self._new(x.shape[0], 299, 299, max(self.in_pad, x.shape[3]))
         K.resize_bilinear_norm(x, y, 128.0, 1.0 / 128.0)
         if self.taps is not None:
-            self.taps["input"] = y
+            self.taps["input"] = y[..., :x.shape[3]]
         return y
 
     def __call__(self, images):

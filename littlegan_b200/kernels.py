@@ -463,11 +463,14 @@ def global_avgpool(x, y):
 
 
 def resize_bilinear_norm(x, y, sub, mul):
-    """TF-1.x ResizeBilinear of x [N,H,W,C] (uint8 or fp32, 0..255) to y's spatial size, then (v - sub) * mul."""
+    """TF-1.x ResizeBilinear of x [N,H,W,C] (uint8 or fp32, 0..255) to y's spatial size, then (v - sub) * mul; y may
+    have more channels than x (zero filled)."""
     _cuda(x, y)
     if x.dtype not in (torch.uint8, torch.float32):
         raise _lib.LittleGANError("resize_bilinear_norm: source must be uint8 or fp32")
     N, H, Wd, C = x.shape
-    check(_lib.load().lg_resize_bilinear_norm(_p(x), _p(y), N, H, Wd, C, y.shape[1], y.shape[2], sub, mul,
+    if y.shape[0] != N or y.shape[3] < C:
+        raise _lib.LittleGANError("resize_bilinear_norm: output batch / channels do not fit the source")
+    check(_lib.load().lg_resize_bilinear_norm(_p(x), _p(y), N, H, Wd, C, y.shape[3], y.shape[1], y.shape[2], sub, mul,
                                               int(x.dtype == torch.uint8), dt(y), _st()), "lg_resize_bilinear_norm")
     return y

@@ -89,6 +89,9 @@ def test_resize_bilinear_tf1_and_normalise(src):
     K.resize_bilinear_norm(x, y, 128.0, 1.0 / 128.0)
     # the kernel computes source coordinates in fp32 as TF's op does (dst * float(in/out)); the oracle in fp64
     assert float((y.double().cpu() - ref).abs().max()) < 1e-4
+    y8 = torch.full((2, 299, 299, 8), 5.0, dtype=torch.bfloat16, device="cuda")       # channel-padded bf16 form
+    K.resize_bilinear_norm(x, y8, 128.0, 1.0 / 128.0)
+    assert float(y8[..., 3:].abs().max()) == 0 and float((y8[..., :3].double().cpu() - ref).abs().max()) < 1e-2
     # an up-scale whose source coordinates hit the last row / column clamp
     small = torch.randint(0, 256, (1, 5, 7, 3), generator=g, dtype=torch.uint8)
     ref2 = IO.resize_bilinear_tf1(small.double(), 11, 13)
@@ -135,7 +138,7 @@ def test_pool3_features_bf16_storage():
     img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
     want = IO.InceptionOracle(W, dtype=torch.float64)(img.double())
     net = InceptionPool3(weights=W, dtype="bf16")
-    assert sum(p[3] is not None for p in net.params.values()) == 93          # all but the RGB stem unit on tcgen05
+    assert sum(p[3] is not None for p in net.params.values()) == 94          # every unit on tcgen05 (RGB stem padded to 8)
     got = net(img)
     # 20 units deep with every activation rounded to bf16: errors accumulate beyond the per-layer 2e-2
     assert rel_err(got, want) < 6e-2
