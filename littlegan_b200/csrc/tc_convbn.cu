@@ -3,11 +3,13 @@
 // odd map sizes (299, 149, 147, 73, 71, 35, 17, 8 do not tile into TMA boxes, so the patch matrix is gathered).
 //
 //   * 8 builder warps gather the A operand: thread (m, half) owns output position m of the 128-position tile and
-//     fetches 16-byte runs (8 channels of one tap - channel counts are multiples of 8) straight from the NHWC map into
-//     the no-swizzle K-major core-matrix layout [k-chunk of 8][position][16 B]; out-of-image taps and the K / M tails
-//     are zero runs.  The same threads copy the stage's weight block, prepacked on the host side of the ABI in exactly
-//     its shared-memory image, so both operands land with plain 16-byte stores + one proxy fence.
-//   * one elected thread issues 128 x Ncols x 16 tcgen05.mma over a 3-4 stage mbarrier ring into one of two TMEM
+//     copies 16-byte runs (8 channels of one tap - channel counts are multiples of 8) straight from the NHWC map into
+//     the no-swizzle K-major core-matrix layout [k-chunk of 8][position][16 B] with cp.async; out-of-image taps and the
+//     K / M tails use its zero-fill form.  The (ky, kx, c) walk is incremental (no divisions in the stage loop) and a
+//     thread arrives for a stage only after issuing three more, so four stages of gathers are in flight per thread.
+//     The stage's weight block, prepacked in exactly its shared-memory image, arrives by ONE bulk copy (TMA unit)
+//     that completes on the same full barrier.
+//   * one elected thread issues 128 x Ncols x 16 tcgen05.mma over a 4-6 stage mbarrier ring into one of two TMEM
 //     accumulators (Ncols <= 256, Cout > 256 is split into equal column tiles);
 //   * 4 epilogue warps read the accumulator (tcgen05.ld), apply scale / shift / ReLU and write bf16 rows into the
 //     unit's channel slice of the block's concat buffer - while the next tile's MMAs run into the other accumulator.
@@ -24,11 +26,24 @@ constexpr int PLANE = 128 * 16;             // one k-chunk plane of A: 128 posit
 constexpr int A_STAGE = (KC / 8) * PLANE;   // 16 KB
 constexpr int BUILDERS = 256;
 constexpr int THREADS = BUILDERS + 32 + 128;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
+constexpr int LAG = 3;                      // stages a builder thread runs ahead of its arrivals (< stages)
+
+__device__ __forceinline__ void cb_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// 1-D bulk copy global -> shared by the TMA unit, completing `bytes` on an mbarrier
+__device__ __forceinline__ void cb_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 struct CBParams {
   const bf16* x; const bf16* wpack; const float* scale; const float* shift; bf16* y;
-  int H, W, Cin, xs, Ho, Wo, kw, s, ph, pw, ys, relu;
+  int H, W, Cin, xs, Ho, Wo, kh, kw, s, ph, pw, ys, relu;
   int M, K, Cout, Ncols, n_tiles, m_tiles, KS, stages, b_stage;   // b_stage = Ncols * KC * 2 bytes
 };
 
@@ -38,7 +53,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.stages * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * p.b_stage);
-  uint64_t* full = bars;                      // [MAX_STAGES] builders -> MMA   (256 arrivals)
+  uint64_t* full = bars;                      // [MAX_STAGES] builders -> MMA   (256 arrivals + the weight block's bytes)
   uint64_t* empty = bars + MAX_STAGES;        // [MAX_STAGES] MMA -> builders
   uint64_t* tfull = bars + 2 * MAX_STAGES;    // [2] MMA -> epilogue
   uint64_t* tempty = tfull + 2;               // [2] epilogue -> MMA            (4 arrivals)
@@ -53,7 +68,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
 
   for (int e = threadIdx.x; e < p.Cout; e += THREADS) { sscale[e] = p.scale[e]; sshift[e] = p.shift[e]; }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_STAGES; ++i) { tc::mbar_init(&full[i], BUILDERS); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { tc::mbar_init(&full[i], BUILDERS + 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
     tc::fence_barrier_init();
   }
@@ -66,9 +81,13 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
 
   if (warp < 8) {
     // ------------------------------------------------------------------ builders
+    // Every copy is asynchronous: the A runs by cp.async (zero-fill form for padding and tails), the stage's weight
+    // block by one bulk copy that completes on the stage's full barrier.  A thread arrives for stage i only after it
+    // has issued stage i + LAG, so LAG + 1 stages of gathers are in flight per thread and no load latency is exposed.
     const int m = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int b_vecs = p.b_stage >> 4;                         // uint4 per weight stage (<= 2048)
-    int stage = 0; uint32_t phase = 0;
+    int stage = 0; uint32_t phase = 0;      // slot being filled
+    int astage = 0;                         // oldest slot this thread has not arrived for yet
+    int issued = 0;                         // stages issued so far (all tiles)
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
       const int gm = mt * 128 + m;
@@ -81,43 +100,45 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
         y0 = p.s * oy - p.ph; x0 = p.s * ox - p.pw;
       }
       const bf16* ximg = p.x + (int64_t)n * p.H * p.W * p.xs;
-      const uint4* wsrc = reinterpret_cast<const uint4*>(p.wpack) + (int64_t)nt * p.KS * b_vecs;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (int64_t)nt * p.KS * p.b_stage;
+      // (ky, kx, c) of this thread's first chunk of the stage, advanced by 64 k per stage without divisions
+      int c = half * 32, kx = 0, ky = 0;
+      while (c >= p.Cin) { c -= p.Cin; if (++kx == p.kw) { kx = 0; ++ky; } }
       for (int ks = 0; ks < p.KS; ++ks) {
-        // global loads first (in flight while the ring slot is still being read by the tensor core)
-        uint4 av[4];
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        if (threadIdx.x == 0) {
+          tc::mbar_expect_tx(&full[stage], (uint32_t)p.b_stage);
+          cb_bulk_load(tc::smem_u32(sB + stage * p.b_stage), wsrc + (int64_t)ks * p.b_stage, (uint32_t)p.b_stage,
+                       tc::smem_u32(&full[stage]));
+        }
+        const uint32_t a_dst = tc::smem_u32(sA + stage * A_STAGE + m * 16) + half * 4 * PLANE;
+        int cq = c, kxq = kx, kyq = ky;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int k = ks * KC + (half * 4 + q) * 8;
-          av[q] = make_uint4(0, 0, 0, 0);
-          if (row_ok && k < p.K) {
-            const int tap = k / p.Cin, c = k - tap * p.Cin;
-            const int ky = tap / p.kw, kx = tap - ky * p.kw;
-            const int yy = y0 + ky, xx = x0 + kx;
-            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-              av[q] = __ldg(reinterpret_cast<const uint4*>(ximg + ((int64_t)yy * p.W + xx) * p.xs + c));
-          }
+          const int yy = y0 + kyq, xx = x0 + kxq;
+          const bool ok = row_ok && kyq < p.kh && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+          const bf16* src = ok ? ximg + (yy * p.W + xx) * p.xs + cq : ximg;
+          cb_cp_async16(a_dst + q * PLANE, src, ok ? 16u : 0u);
+          cq += 8;
+          if (cq >= p.Cin) { cq -= p.Cin; if (++kxq == p.kw) { kxq = 0; ++kyq; } }
         }
-        uint4 bv[8];
-        const uint4* wst = wsrc + (int64_t)ks * b_vecs;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int e = threadIdx.x + q * BUILDERS;
-          bv[q] = e < b_vecs ? __ldg(wst + e) : make_uint4(0, 0, 0, 0);
-        }
-        tc::mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* a_dst = sA + stage * A_STAGE + m * 16;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(a_dst + (half * 4 + q) * PLANE) = av[q];
-        uint4* b_dst = reinterpret_cast<uint4*>(sB + stage * p.b_stage);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int e = threadIdx.x + q * BUILDERS;
-          if (e < b_vecs) b_dst[e] = bv[q];
-        }
-        tc::fence_proxy_async();                               // generic writes -> async (tensor core) proxy
-        tc::mbar_arrive(&full[stage]);
+        cb_cp_async_commit();
+        c += KC;
+        while (c >= p.Cin) { c -= p.Cin; if (++kx == p.kw) { kx = 0; ++ky; } }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++issued > LAG) {
+          cb_cp_async_wait<LAG>();
+          tc::fence_proxy_async();                             // generic-proxy writes -> async (tensor core) proxy
+          tc::mbar_arrive(&full[astage]);
+          if (++astage == p.stages) astage = 0;
+        }
       }
+    }
+    cb_cp_async_wait<0>();
+    tc::fence_proxy_async();
+    for (int r = issued < LAG ? issued : LAG; r > 0; --r) {
+      tc::mbar_arrive(&full[astage]);
+      if (++astage == p.stages) astage = 0;
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
@@ -249,12 +270,12 @@ int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const flo
   if (!plan(Cin, kh, kw, Cout, &pl)) return LG_ERR_UNSUPPORTED;
   CBParams p;
   p.x = (const bf16*)x + xo; p.wpack = (const bf16*)wpack; p.scale = scale; p.shift = shift; p.y = (bf16*)y + yo;
-  p.H = H; p.W = Wd; p.Cin = Cin; p.xs = xs; p.kw = kw; p.s = s; p.ph = ph; p.pw = pw; p.ys = ys; p.relu = relu;
+  p.H = H; p.W = Wd; p.Cin = Cin; p.xs = xs; p.kh = kh; p.kw = kw; p.s = s; p.ph = ph; p.pw = pw; p.ys = ys; p.relu = relu;
   p.Ho = (H + 2 * ph - kh) / s + 1; p.Wo = (Wd + 2 * pw - kw) / s + 1;
   p.M = N * p.Ho * p.Wo; p.K = kh * kw * Cin; p.Cout = Cout;
   p.Ncols = pl.Ncols; p.n_tiles = pl.n_tiles; p.KS = pl.KS; p.m_tiles = (p.M + 127) / 128;
   p.b_stage = pl.Ncols * KC * 2;
-  int stages = (200 * 1024) / (A_STAGE + p.b_stage);
+  int stages = (196 * 1024) / (A_STAGE + p.b_stage);
   p.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
   const size_t shm = (size_t)p.stages * (A_STAGE + p.b_stage) + 1024 + 256 + 2 * (size_t)Cout * sizeof(float);
   static bool attr_set = false;
