@@ -22,8 +22,8 @@
 namespace {
 
 constexpr int KC = 64;                      // k per stage: 8 chunks of 8
-constexpr int PLANE = 128 * 16;             // one k-chunk plane of A: 128 positions x 16 B
-constexpr int A_STAGE = (KC / 8) * PLANE;   // 16 KB
+constexpr int PLANE = 128 * 16 + 16;        // one k-chunk plane of A: 128 positions x 16 B, pitched against bank conflicts
+constexpr int A_STAGE = (KC / 8) * PLANE;   // ~16 KB
 constexpr int BUILDERS = 256;
 constexpr int THREADS = BUILDERS + 32 + 128;
 constexpr int MAX_STAGES = 6;
@@ -84,25 +84,32 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
     // Every copy is asynchronous: the A runs by cp.async (zero-fill form for padding and tails), the stage's weight
     // block by one bulk copy that completes on the stage's full barrier.  A thread arrives for stage i only after it
     // has issued stage i + LAG, so LAG + 1 stages of gathers are in flight per thread and no load latency is exposed.
-    const int m = threadIdx.x & 127, half = threadIdx.x >> 7;
+    // Lane mapping: the 8 chunks of a position are 8 consecutive lanes (channel / tap runs that are contiguous in
+    // memory), a warp covers 4 neighbouring positions - a warp-wide copy touches 4 full 128-byte lines instead of 32
+    // partial ones.  Planes are pitched 2048 + 16 bytes so that those 32 stores spread over all banks.
+    const int chunk = threadIdx.x & 7, prow = threadIdx.x >> 3;
     int stage = 0; uint32_t phase = 0;      // slot being filled
     int astage = 0;                         // oldest slot this thread has not arrived for yet
     int issued = 0;                         // stages issued so far (all tiles)
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
-      const int gm = mt * 128 + m;
-      const bool row_ok = gm < p.M;
-      int n = 0, y0 = 0, x0 = 0;
-      if (row_ok) {
-        const int hw = p.Ho * p.Wo;
-        n = gm / hw;
-        const int r = gm - n * hw, oy = r / p.Wo, ox = r - oy * p.Wo;
-        y0 = p.s * oy - p.ph; x0 = p.s * ox - p.pw;
+      int y0[4], x0[4];
+      const bf16* ximg[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gm = mt * 128 + prow + 32 * q;
+        y0[q] = -(1 << 28); x0[q] = 0; ximg[q] = p.x;          // rows past M: every tap is out of range
+        if (gm < p.M) {
+          const int hw = p.Ho * p.Wo;
+          const int n = gm / hw;
+          const int r = gm - n * hw, oy = r / p.Wo, ox = r - oy * p.Wo;
+          y0[q] = p.s * oy - p.ph; x0[q] = p.s * ox - p.pw;
+          ximg[q] = p.x + (int64_t)n * p.H * p.W * p.xs;
+        }
       }
-      const bf16* ximg = p.x + (int64_t)n * p.H * p.W * p.xs;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (int64_t)nt * p.KS * p.b_stage;
-      // (ky, kx, c) of this thread's first chunk of the stage, advanced by 64 k per stage without divisions
-      int c = half * 32, kx = 0, ky = 0;
+      // (ky, kx, c) of this thread's chunk of the stage, advanced by 64 k per stage without divisions
+      int c = chunk * 8, kx = 0, ky = 0;
       while (c >= p.Cin) { c -= p.Cin; if (++kx == p.kw) { kx = 0; ++ky; } }
       for (int ks = 0; ks < p.KS; ++ks) {
         tc::mbar_wait(&empty[stage], phase ^ 1);
@@ -111,16 +118,14 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
           cb_bulk_load(tc::smem_u32(sB + stage * p.b_stage), wsrc + (int64_t)ks * p.b_stage, (uint32_t)p.b_stage,
                        tc::smem_u32(&full[stage]));
         }
-        const uint32_t a_dst = tc::smem_u32(sA + stage * A_STAGE + m * 16) + half * 4 * PLANE;
-        int cq = c, kxq = kx, kyq = ky;
+        const uint32_t a_dst = tc::smem_u32(sA + stage * A_STAGE + chunk * PLANE + prow * 16);
+        const bool k_ok = ky < p.kh;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int yy = y0 + kyq, xx = x0 + kxq;
-          const bool ok = row_ok && kyq < p.kh && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-          const bf16* src = ok ? ximg + (yy * p.W + xx) * p.xs + cq : ximg;
-          cb_cp_async16(a_dst + q * PLANE, src, ok ? 16u : 0u);
-          cq += 8;
-          if (cq >= p.Cin) { cq -= p.Cin; if (++kxq == p.kw) { kxq = 0; ++kyq; } }
+          const int yy = y0[q] + ky, xx = x0[q] + kx;
+          const bool ok = k_ok && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+          const bf16* src = ok ? ximg[q] + (yy * p.W + xx) * p.xs + c : p.x;
+          cb_cp_async16(a_dst + q * 512, src, ok ? 16u : 0u);
         }
         cb_cp_async_commit();
         c += KC;
