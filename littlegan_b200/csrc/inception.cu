@@ -35,6 +35,43 @@ __global__ void resize_bilinear_kernel(const S* __restrict__ x, T* __restrict__ 
   }
 }
 
+// RGB -> 8-channel bf16 pixels: one thread per output pixel, one 16-byte store
+template <typename S>
+__global__ void resize_rgb8_kernel(const S* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int Ho, int Wo,
+                                   float sy, float sx, float sub, float mul) {
+  const int64_t total = (int64_t)N * Ho * Wo;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int ox = (int)(e % Wo);
+    int64_t t = e / Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const float fy = oy * sy, fx = ox * sx;
+    const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float wy = fy - y0, wx = fx - x0;
+    const S* base = x + (int64_t)n * H * W * 3;
+    const S* p00 = base + ((int64_t)y0 * W + x0) * 3;
+    const S* p01 = base + ((int64_t)y0 * W + x1) * 3;
+    const S* p10 = base + ((int64_t)y1 * W + x0) * 3;
+    const S* p11 = base + ((int64_t)y1 * W + x1) * 3;
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v00 = (float)p00[c], v01 = (float)p01[c], v10 = (float)p10[c], v11 = (float)p11[c];
+      const float top = v00 + (v01 - v00) * wx, bot = v10 + (v11 - v10) * wx;
+      o[c] = (top + (bot - top) * wy - sub) * mul;
+    }
+    uint4 pk;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+    h[0] = __floats2bfloat162_rn(o[0], o[1]);
+    h[1] = __floats2bfloat162_rn(o[2], 0.f);
+    h[2] = __floats2bfloat162_rn(0.f, 0.f);
+    h[3] = h[2];
+    reinterpret_cast<uint4*>(y)[e] = pk;
+  }
+}
+
 // mode 0: max; 1: average over the in-bounds taps only (the 2015 graph's AvgPool with SAME padding);
 // 2: average with the padding counted (divisor k*k)
 template <typename T>
@@ -210,7 +247,11 @@ extern "C" int lg_resize_bilinear_norm(const void* x, void* y, int N, int H, int
   const int g = grid_for((int64_t)N * Ho * Wo * Cpad);
   cudaStream_t st = (cudaStream_t)stream;
   const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
-  if (src_is_u8) {
+  if (dtype == LG_BF16 && C == 3 && Cpad == 8 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    const int g8 = grid_for((int64_t)N * Ho * Wo);
+    if (src_is_u8) resize_rgb8_kernel<uint8_t><<<g8, 256, 0, st>>>((const uint8_t*)x, (bf16*)y, N, H, W, Ho, Wo, sy, sx, sub, mul);
+    else resize_rgb8_kernel<float><<<g8, 256, 0, st>>>((const float*)x, (bf16*)y, N, H, W, Ho, Wo, sy, sx, sub, mul);
+  } else if (src_is_u8) {
     if (dtype == LG_BF16) resize_bilinear_kernel<uint8_t, bf16><<<g, 256, 0, st>>>((const uint8_t*)x, (bf16*)y, N, H, W, C, Cpad, Ho, Wo, sy, sx, sub, mul);
     else resize_bilinear_kernel<uint8_t, float><<<g, 256, 0, st>>>((const uint8_t*)x, (float*)y, N, H, W, C, Cpad, Ho, Wo, sy, sx, sub, mul);
   } else {

@@ -6,10 +6,11 @@
 //     copies 16-byte runs (8 channels of one tap - channel counts are multiples of 8) straight from the NHWC map into
 //     the no-swizzle K-major core-matrix layout [k-chunk of 8][position][16 B] with cp.async; out-of-image taps and the
 //     K / M tails use its zero-fill form.  The (ky, kx, c) walk is incremental (no divisions in the stage loop) and a
-//     thread arrives for a stage only after issuing three more, so four stages of gathers are in flight per thread.
+//     thread arrives for a stage only after issuing up to six more (ring size - 1), so the gathers of a whole ring are
+//     in flight per thread; when the next slot is not free yet it hands over everything issued before blocking.
 //     The stage's weight block, prepacked in exactly its shared-memory image, arrives by ONE bulk copy (TMA unit)
 //     that completes on the same full barrier.
-//   * one elected thread issues 128 x Ncols x 16 tcgen05.mma over a 4-6 stage mbarrier ring into one of two TMEM
+//   * one elected thread issues 128 x Ncols x 16 tcgen05.mma over a 4-8 stage mbarrier ring into one of two TMEM
 //     accumulators (Ncols <= 256, Cout > 256 is split into equal column tiles);
 //   * 4 epilogue warps read the accumulator (tcgen05.ld), apply scale / shift / ReLU and write bf16 rows into the
 //     unit's channel slice of the block's concat buffer - while the next tile's MMAs run into the other accumulator.
@@ -24,10 +25,12 @@ namespace {
 constexpr int KC = 64;                      // k per stage: 8 chunks of 8
 constexpr int PLANE = 128 * 16 + 16;        // one k-chunk plane of A: 128 positions x 16 B, pitched against bank conflicts
 constexpr int A_STAGE = (KC / 8) * PLANE;   // ~16 KB
-constexpr int BUILDERS = 256;
+constexpr int BUILDERS = 512;               // 16 gather warps
+constexpr int PPT = 1024 / BUILDERS;        // positions per builder thread per stage
 constexpr int THREADS = BUILDERS + 32 + 128;
-constexpr int MAX_STAGES = 6;
-constexpr int LAG = 3;                      // stages a builder thread runs ahead of its arrivals (< stages)
+constexpr int MMA_WARP = BUILDERS / 32;     // then 4 epilogue warps (warp & 3 = TMEM lane quarter)
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_LAG = 6;                  // stages a builder thread may run ahead of its arrivals (< stages)
 
 __device__ __forceinline__ void cb_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -35,6 +38,27 @@ __device__ __forceinline__ void cb_cp_async16(uint32_t dst, const void* src, uin
 __device__ __forceinline__ void cb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cb_cp_async_wait_dyn(int n) {   // at most n of this thread's groups still pending
+  switch (n) {
+    case 0: cb_cp_async_wait<0>(); break;
+    case 1: cb_cp_async_wait<1>(); break;
+    case 2: cb_cp_async_wait<2>(); break;
+    case 3: cb_cp_async_wait<3>(); break;
+    case 4: cb_cp_async_wait<4>(); break;
+    case 5: cb_cp_async_wait<5>(); break;
+    case 6: cb_cp_async_wait<6>(); break;
+    default: cb_cp_async_wait<7>(); break;
+  }
+}
+__device__ __forceinline__ int cb_div(int n, uint32_t mul, uint32_t shr) {   // n / d, (mul, shr) from fast_div
+  return mul ? (int)(__umulhi((uint32_t)n, mul) >> shr) : n;
+}
+__device__ __forceinline__ bool cb_mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking phase test
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // 1-D bulk copy global -> shared by the TMA unit, completing `bytes` on an mbarrier
 __device__ __forceinline__ void cb_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -45,6 +69,7 @@ struct CBParams {
   const bf16* x; const bf16* wpack; const float* scale; const float* shift; bf16* y;
   int H, W, Cin, xs, Ho, Wo, kh, kw, s, ph, pw, ys, relu;
   int M, K, Cout, Ncols, n_tiles, m_tiles, KS, stages, b_stage;   // b_stage = Ncols * KC * 2 bytes
+  uint32_t hw_mul, hw_shr, wo_mul, wo_shr;                         // n / (Ho*Wo) and r / Wo as multiply-high + shift
 };
 
 __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
@@ -53,7 +78,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.stages * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * p.b_stage);
-  uint64_t* full = bars;                      // [MAX_STAGES] builders -> MMA   (256 arrivals + the weight block's bytes)
+  uint64_t* full = bars;                      // [MAX_STAGES] builders -> MMA   (8 warp arrivals + the weight block's bytes)
   uint64_t* empty = bars + MAX_STAGES;        // [MAX_STAGES] MMA -> builders
   uint64_t* tfull = bars + 2 * MAX_STAGES;    // [2] MMA -> epilogue
   uint64_t* tempty = tfull + 2;               // [2] epilogue -> MMA            (4 arrivals)
@@ -68,43 +93,49 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
 
   for (int e = threadIdx.x; e < p.Cout; e += THREADS) { sscale[e] = p.scale[e]; sshift[e] = p.shift[e]; }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_STAGES; ++i) { tc::mbar_init(&full[i], BUILDERS + 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { tc::mbar_init(&full[i], BUILDERS / 32 + 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
     tc::fence_barrier_init();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, tmem_cols);
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
+  if (warp < MMA_WARP) {
     // ------------------------------------------------------------------ builders
     // Every copy is asynchronous: the A runs by cp.async (zero-fill form for padding and tails), the stage's weight
-    // block by one bulk copy that completes on the stage's full barrier.  A thread arrives for stage i only after it
-    // has issued stage i + LAG, so LAG + 1 stages of gathers are in flight per thread and no load latency is exposed.
+    // block by one bulk copy that completes on the stage's full barrier.  A warp arrives for stage i only after it has
+    // issued up to `lag` more stages, so no load latency is exposed while the ring has free slots.
     // Lane mapping: the 8 chunks of a position are 8 consecutive lanes (channel / tap runs that are contiguous in
     // memory), a warp covers 4 neighbouring positions - a warp-wide copy touches 4 full 128-byte lines instead of 32
     // partial ones.  Planes are pitched 2048 + 16 bytes so that those 32 stores spread over all banks.
+    // The stage loop is kept to a few dozen instructions per thread (16 warps of dependent integer chains would
+    // otherwise be the bound): per position a base pointer and two bit masks of the in-image ky / kx taps are made
+    // once per tile, a stage then needs one tap offset, two shifts and a select per copy.
     const int chunk = threadIdx.x & 7, prow = threadIdx.x >> 3;
     int stage = 0; uint32_t phase = 0;      // slot being filled
-    int astage = 0;                         // oldest slot this thread has not arrived for yet
-    int issued = 0;                         // stages issued so far (all tiles)
+    int astage = 0;                         // oldest slot this warp has not arrived for yet
+    int pending = 0;                        // stages issued but not yet arrived for
+    const int lag = p.stages - 1 < MAX_LAG ? p.stages - 1 : MAX_LAG;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
-      int y0[4], x0[4];
-      const bf16* ximg[4];
+      uint32_t vy[PPT], vx[PPT];                               // bit k set: tap row / column k is inside the image
+      const bf16* base[PPT];                                   // &x[n, y0, x0, 0] (may lie outside; used with valid taps)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int gm = mt * 128 + prow + 32 * q;
-        y0[q] = -(1 << 28); x0[q] = 0; ximg[q] = p.x;          // rows past M: every tap is out of range
+      for (int q = 0; q < PPT; ++q) {
+        const int gm = mt * 128 + prow + (BUILDERS / 8) * q;
+        vy[q] = 0; vx[q] = 0; base[q] = p.x;                   // rows past M: no tap is valid
         if (gm < p.M) {
-          const int hw = p.Ho * p.Wo;
-          const int n = gm / hw;
-          const int r = gm - n * hw, oy = r / p.Wo, ox = r - oy * p.Wo;
-          y0[q] = p.s * oy - p.ph; x0[q] = p.s * ox - p.pw;
-          ximg[q] = p.x + (int64_t)n * p.H * p.W * p.xs;
+          const int n = cb_div(gm, p.hw_mul, p.hw_shr);
+          const int r = gm - n * p.Ho * p.Wo;
+          const int oy = cb_div(r, p.wo_mul, p.wo_shr), ox = r - oy * p.Wo;
+          const int y0 = p.s * oy - p.ph, x0 = p.s * ox - p.pw;
+          for (int k = 0; k < p.kh; ++k) vy[q] |= (uint32_t)(y0 + k >= 0 && y0 + k < p.H) << k;
+          for (int k = 0; k < p.kw; ++k) vx[q] |= (uint32_t)(x0 + k >= 0 && x0 + k < p.W) << k;
+          base[q] = p.x + ((int64_t)(n * p.H + y0) * p.W + x0) * p.xs;
         }
       }
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (int64_t)nt * p.KS * p.b_stage;
@@ -112,40 +143,55 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
       int c = chunk * 8, kx = 0, ky = 0;
       while (c >= p.Cin) { c -= p.Cin; if (++kx == p.kw) { kx = 0; ++ky; } }
       for (int ks = 0; ks < p.KS; ++ks) {
-        tc::mbar_wait(&empty[stage], phase ^ 1);
+        // Slot not free yet = the tensor core is behind: hand over everything issued so far before blocking, so
+        // that the MMA issuer is never starved by the run-ahead.  (Warp-uniform decision: lane 0 arrives for all.)
+        if (!__all_sync(0xffffffffu, cb_mbar_test(&empty[stage], phase ^ 1))) {
+          if (pending) {
+            cb_cp_async_wait<0>();
+            tc::fence_proxy_async();
+            __syncwarp();
+            for (; pending > 0; --pending) {
+              if (lane == 0) tc::mbar_arrive(&full[astage]);
+              if (++astage == p.stages) astage = 0;
+            }
+          }
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+        }
         if (threadIdx.x == 0) {
           tc::mbar_expect_tx(&full[stage], (uint32_t)p.b_stage);
           cb_bulk_load(tc::smem_u32(sB + stage * p.b_stage), wsrc + (int64_t)ks * p.b_stage, (uint32_t)p.b_stage,
                        tc::smem_u32(&full[stage]));
         }
         const uint32_t a_dst = tc::smem_u32(sA + stage * A_STAGE + chunk * PLANE + prow * 16);
-        const bool k_ok = ky < p.kh;
+        const int tapoff = (ky * p.W + kx) * p.xs + c;        // ky >= kh (K tail): vy has no such bit
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int yy = y0[q] + ky, xx = x0[q] + kx;
-          const bool ok = k_ok && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-          const bf16* src = ok ? ximg[q] + (yy * p.W + xx) * p.xs + c : p.x;
-          cb_cp_async16(a_dst + q * 512, src, ok ? 16u : 0u);
+        for (int q = 0; q < PPT; ++q) {
+          const bool ok = ((vy[q] >> ky) & (vx[q] >> kx) & 1u) != 0;
+          const bf16* src = ok ? base[q] + tapoff : p.x;
+          cb_cp_async16(a_dst + q * (BUILDERS / 8) * 16, src, ok ? 16u : 0u);
         }
         cb_cp_async_commit();
         c += KC;
         while (c >= p.Cin) { c -= p.Cin; if (++kx == p.kw) { kx = 0; ++ky; } }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        if (++issued > LAG) {
-          cb_cp_async_wait<LAG>();
+        if (++pending > lag) {
+          cb_cp_async_wait_dyn(lag);
           tc::fence_proxy_async();                             // generic-proxy writes -> async (tensor core) proxy
-          tc::mbar_arrive(&full[astage]);
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&full[astage]);       // one arrival per warp: 9 per stage instead of 257
           if (++astage == p.stages) astage = 0;
+          --pending;
         }
       }
     }
     cb_cp_async_wait<0>();
     tc::fence_proxy_async();
-    for (int r = issued < LAG ? issued : LAG; r > 0; --r) {
-      tc::mbar_arrive(&full[astage]);
+    __syncwarp();
+    for (; pending > 0; --pending) {
+      if (lane == 0) tc::mbar_arrive(&full[astage]);
       if (++astage == p.stages) astage = 0;
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(128, p.Ncols, 0, 0);
@@ -211,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -234,6 +280,16 @@ __global__ void convbn_pack_kernel(const float* __restrict__ W, bf16* __restrict
     const int off = (b >> 3) * 512 + (kl >> 3) * 64 + (b & 7) * 8 + (kl & 7);      // in bf16 elements
     out[block + off] = __float2bfloat16_rn(v);
   }
+}
+
+// q = n / d for 0 <= n < 2^31 as (n * mul) >> (32 + shr)
+inline void fast_div(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  if (d == 1) { *mul = 0; *shr = 0; return; }                  // mul 0 = "divisor is 1" (handled in cb_div)
+  uint32_t l = 0;
+  while ((1u << l) < d) ++l;                                   // ceil(log2 d)
+  const uint64_t p2 = 1ull << (31 + l);
+  *mul = (uint32_t)((p2 + d - 1) / d);
+  *shr = l - 1;
 }
 
 struct Plan { int Ncols, n_tiles, KS; };
@@ -280,6 +336,8 @@ int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const flo
   p.M = N * p.Ho * p.Wo; p.K = kh * kw * Cin; p.Cout = Cout;
   p.Ncols = pl.Ncols; p.n_tiles = pl.n_tiles; p.KS = pl.KS; p.m_tiles = (p.M + 127) / 128;
   p.b_stage = pl.Ncols * KC * 2;
+  fast_div((uint32_t)(p.Ho * p.Wo), &p.hw_mul, &p.hw_shr);
+  fast_div((uint32_t)p.Wo, &p.wo_mul, &p.wo_shr);
   int stages = (196 * 1024) / (A_STAGE + p.b_stage);
   p.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
   const size_t shm = (size_t)p.stages * (A_STAGE + p.b_stage) + 1024 + 256 + 2 * (size_t)Cout * sizeof(float);
