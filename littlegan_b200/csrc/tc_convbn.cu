@@ -53,6 +53,11 @@ __device__ __forceinline__ void cb_cp_async_wait_dyn(int n) {   // at most n of 
 __device__ __forceinline__ int cb_div(int n, uint32_t mul, uint32_t shr) {   // n / d, (mul, shr) from fast_div
   return mul ? (int)(__umulhi((uint32_t)n, mul) >> shr) : n;
 }
+// bits k in [0, taps) with 0 <= o + k < size
+__device__ __forceinline__ uint32_t cb_tap_mask(int o, int taps, int size) {
+  const int lo = max(0, -o), hi = min(taps, size - o);
+  return hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+}
 __device__ __forceinline__ bool cb_mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking phase test
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -69,7 +74,8 @@ struct CBParams {
   const bf16* x; const bf16* wpack; const float* scale; const float* shift; bf16* y;
   int H, W, Cin, xs, Ho, Wo, kh, kw, s, ph, pw, ys, relu;
   int M, K, Cout, Ncols, n_tiles, m_tiles, KS, stages, b_stage;   // b_stage = Ncols * KC * 2 bytes
-  uint32_t hw_mul, hw_shr, wo_mul, wo_shr;                         // n / (Ho*Wo) and r / Wo as multiply-high + shift
+  int HoWo;
+  uint32_t hw_mul, hw_shr, wo_mul, wo_shr, nt_mul, nt_shr;         // / (Ho*Wo), / Wo, / n_tiles as multiply-high + shift
 };
 
 __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
@@ -120,8 +126,11 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
     int astage = 0;                         // oldest slot this warp has not arrived for yet
     int pending = 0;                        // stages issued but not yet arrived for
     const int lag = p.stages - 1 < MAX_LAG ? p.stages - 1 : MAX_LAG;
+    // (ky, kx, c) of this thread's chunk in the first stage of a tile
+    int c_first = chunk * 8, kx_first = 0, ky_first = 0;
+    while (c_first >= p.Cin) { c_first -= p.Cin; if (++kx_first == p.kw) { kx_first = 0; ++ky_first; } }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+      const int mt = p.n_tiles == 1 ? t : cb_div(t, p.nt_mul, p.nt_shr), nt = t - mt * p.n_tiles;
       uint32_t vy[PPT], vx[PPT];                               // bit k set: tap row / column k is inside the image
       const bf16* base[PPT];                                   // &x[n, y0, x0, 0] (may lie outside; used with valid taps)
 #pragma unroll
@@ -130,18 +139,16 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
         vy[q] = 0; vx[q] = 0; base[q] = p.x;                   // rows past M: no tap is valid
         if (gm < p.M) {
           const int n = cb_div(gm, p.hw_mul, p.hw_shr);
-          const int r = gm - n * p.Ho * p.Wo;
+          const int r = gm - n * p.HoWo;
           const int oy = cb_div(r, p.wo_mul, p.wo_shr), ox = r - oy * p.Wo;
           const int y0 = p.s * oy - p.ph, x0 = p.s * ox - p.pw;
-          for (int k = 0; k < p.kh; ++k) vy[q] |= (uint32_t)(y0 + k >= 0 && y0 + k < p.H) << k;
-          for (int k = 0; k < p.kw; ++k) vx[q] |= (uint32_t)(x0 + k >= 0 && x0 + k < p.W) << k;
+          vy[q] = cb_tap_mask(y0, p.kh, p.H);
+          vx[q] = cb_tap_mask(x0, p.kw, p.W);
           base[q] = p.x + ((int64_t)(n * p.H + y0) * p.W + x0) * p.xs;
         }
       }
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (int64_t)nt * p.KS * p.b_stage;
-      // (ky, kx, c) of this thread's chunk of the stage, advanced by 64 k per stage without divisions
-      int c = chunk * 8, kx = 0, ky = 0;
-      while (c >= p.Cin) { c -= p.Cin; if (++kx == p.kw) { kx = 0; ++ky; } }
+      int c = c_first, kx = kx_first, ky = ky_first;           // advanced by 64 k per stage without divisions
       for (int ks = 0; ks < p.KS; ++ks) {
         // Slot not free yet = the tensor core is behind: hand over everything issued so far before blocking, so
         // that the MMA issuer is never starved by the run-ahead.  (Warp-uniform decision: lane 0 arrives for all.)
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
     const int row = q * 32 + lane;
     int acc = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+      const int mt = p.n_tiles == 1 ? t : cb_div(t, p.nt_mul, p.nt_shr), nt = t - mt * p.n_tiles;
       const int gm = mt * 128 + row;
       const int c0 = nt * p.Ncols;
       bf16* orow = p.y + (int64_t)gm * p.ys + c0;
@@ -338,6 +345,8 @@ int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const flo
   p.b_stage = pl.Ncols * KC * 2;
   fast_div((uint32_t)(p.Ho * p.Wo), &p.hw_mul, &p.hw_shr);
   fast_div((uint32_t)p.Wo, &p.wo_mul, &p.wo_shr);
+  fast_div((uint32_t)p.n_tiles, &p.nt_mul, &p.nt_shr);
+  p.HoWo = p.Ho * p.Wo;
   int stages = (196 * 1024) / (A_STAGE + p.b_stage);
   p.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
   const size_t shm = (size_t)p.stages * (A_STAGE + p.b_stage) + 1024 + 256 + 2 * (size_t)Cout * sizeof(float);
