@@ -108,25 +108,24 @@ __global__ void pool2d_kernel(const T* __restrict__ x, T* __restrict__ y, int N,
 // 16-byte loads and stores (the scalar kernel above moves 2 bytes per instruction)
 __global__ void pool2d_vec8_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C8, int xs,
                                    int k, int s, int pad, int Ho, int Wo, int mode, int ys) {
-  const int64_t total = (int64_t)N * Ho * Wo * C8;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int c = (int)(e % C8) * 8;
-    int64_t t = e / C8;
-    const int ox = (int)(t % Wo); t /= Wo;
-    const int oy = (int)(t % Ho);
-    const int n = (int)(t / Ho);
+  // grid: x = blocks over (ox, c8) of one output row, y = oy, z = n  (no 64-bit divisions per element)
+  const int row_elems = Wo * C8;
+  const int oy = blockIdx.y, n = blockIdx.z;
+  const bf16* xin = x + (int64_t)n * H * W * xs;
+  bf16* yout = y + ((int64_t)n * Ho + oy) * Wo * ys;
+  const int iy0 = oy * s - pad;
+  const int ky_lo = max(0, -iy0), ky_hi = min(k, H - iy0);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < row_elems; e += gridDim.x * blockDim.x) {
+    const int ox = e / C8, c = (e - ox * C8) * 8;
+    const int ix0 = ox * s - pad;
+    const int kx_lo = max(0, -ix0), kx_hi = min(k, W - ix0);
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = mode == 0 ? -INFINITY : 0.f;
-    int cnt = 0;
-    for (int ky = 0; ky < k; ++ky) {
-      const int iy = oy * s - pad + ky;
-      if (iy < 0 || iy >= H) continue;
-      for (int kx = 0; kx < k; ++kx) {
-        const int ix = ox * s - pad + kx;
-        if (ix < 0 || ix >= W) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + iy) * W + ix) * xs + c));
+    for (int ky = ky_lo; ky < ky_hi; ++ky) {
+      const bf16* row = xin + ((int64_t)(iy0 + ky) * W + ix0) * xs + c;
+      for (int kx = kx_lo; kx < kx_hi; ++kx) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + kx * xs));
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -134,17 +133,16 @@ __global__ void pool2d_vec8_kernel(const bf16* __restrict__ x, bf16* __restrict_
           if (mode == 0) { acc[2 * i] = fmaxf(acc[2 * i], f.x); acc[2 * i + 1] = fmaxf(acc[2 * i + 1], f.y); }
           else { acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
         }
-        ++cnt;
       }
     }
-    const float div = mode == 1 ? (float)cnt : (float)(k * k);
+    const float div = mode == 1 ? (float)((ky_hi - ky_lo) * (kx_hi - kx_lo)) : (float)(k * k);
     uint4 o;
     __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       oh[i] = mode == 0 ? __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1])
                         : __floats2bfloat162_rn(acc[2 * i] / div, acc[2 * i + 1] / div);
-    *reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + oy) * Wo + ox) * ys + c) = o;
+    *reinterpret_cast<uint4*>(yout + ox * ys + c) = o;
   }
 }
 
@@ -217,8 +215,14 @@ extern "C" int lg_pool2d(const void* x, void* y, int N, int H, int W, int C, int
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == LG_BF16 && ((C | x_stride | x_off | y_stride | y_off) & 7) == 0 &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
-    pool2d_vec8_kernel<<<grid_for((int64_t)N * Ho * Wo * (C / 8)), 256, 0, st>>>(
-        (const bf16*)x + x_off, (bf16*)y + y_off, N, H, W, C / 8, x_stride, k, stride, pad, Ho, Wo, mode, y_stride);
+  {
+    LG_REQUIRE(Ho <= 65535 && N <= 65535, "map too tall / batch too large for the pooling grid");
+    const int row_elems = Wo * (C / 8);
+    const int threads = row_elems >= 256 ? 256 : ((row_elems + 31) / 32) * 32;
+    dim3 grid((row_elems + threads - 1) / threads, Ho, N);
+    pool2d_vec8_kernel<<<grid, threads, 0, st>>>((const bf16*)x + x_off, (bf16*)y + y_off, N, H, W, C / 8, x_stride, k,
+                                                 stride, pad, Ho, Wo, mode, y_stride);
+  }
   else if (dtype == LG_BF16)
     pool2d_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x + x_off, (bf16*)y + y_off, N, H, W, C, x_stride, k, stride, pad,
                                            Ho, Wo, mode, y_stride);
