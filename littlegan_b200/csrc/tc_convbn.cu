@@ -15,6 +15,7 @@
 //   * 4 epilogue warps read the accumulator (tcgen05.ld), apply scale / shift / ReLU and write bf16 rows into the
 //     unit's channel slice of the block's concat buffer - while the next tile's MMAs run into the other accumulator.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -75,6 +76,7 @@ struct CBParams {
   int H, W, Cin, xs, Ho, Wo, kh, kw, s, ph, pw, ys, relu;
   int M, K, Cout, Ncols, n_tiles, m_tiles, KS, stages, b_stage;   // b_stage = Ncols * KC * 2 bytes
   int HoWo;
+  int dbg;                                                         // LG_CONVBN_DBG knock-outs (profiling only): 1 no A copies, 2 no MMAs, 4 no epilogue, 8 no B copies
   uint32_t hw_mul, hw_shr, wo_mul, wo_shr, nt_mul, nt_shr;         // / (Ho*Wo), / Wo, / n_tiles as multiply-high + shift
 };
 
@@ -125,7 +127,9 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
     int stage = 0; uint32_t phase = 0;      // slot being filled
     int astage = 0;                         // oldest slot this warp has not arrived for yet
     int pending = 0;                        // stages issued but not yet arrived for
-    const int lag = p.stages - 1 < MAX_LAG ? p.stages - 1 : MAX_LAG;
+    // the ring must hold the lag + 1 stages in flight AND the stages the tensor core is still reading: with a lag of
+    // ring - 1 the two sides can only work in alternating bursts (measured: ~1000 cycles per stage of pure hand-shake)
+    const int lag = p.stages / 2 < MAX_LAG ? p.stages / 2 : MAX_LAG;
     // (ky, kx, c) of this thread's chunk in the first stage of a tile
     int c_first = chunk * 8, kx_first = 0, ky_first = 0;
     while (c_first >= p.Cin) { c_first -= p.Cin; if (++kx_first == p.kw) { kx_first = 0; ++ky_first; } }
@@ -152,19 +156,28 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
       for (int ks = 0; ks < p.KS; ++ks) {
         // Slot not free yet = the tensor core is behind: hand over everything issued so far before blocking, so
         // that the MMA issuer is never starved by the run-ahead.  (Warp-uniform decision: lane 0 arrives for all.)
-        if (!__all_sync(0xffffffffu, cb_mbar_test(&empty[stage], phase ^ 1))) {
+        bool slot_free;
+        if (p.dbg & 32) {                                      // lane 0 polls for the warp
+          slot_free = lane == 0 ? cb_mbar_test(&empty[stage], phase ^ 1) : true;
+          slot_free = __all_sync(0xffffffffu, slot_free);
+        } else {
+          slot_free = __all_sync(0xffffffffu, cb_mbar_test(&empty[stage], phase ^ 1));
+        }
+        if (!slot_free) {
           if (pending) {
             cb_cp_async_wait<0>();
-            tc::fence_proxy_async();
+            if (!(p.dbg & 16)) tc::fence_proxy_async();
             __syncwarp();
             for (; pending > 0; --pending) {
               if (lane == 0) tc::mbar_arrive(&full[astage]);
               if (++astage == p.stages) astage = 0;
             }
           }
-          tc::mbar_wait(&empty[stage], phase ^ 1);
+          if (p.dbg & 32) { if (lane == 0) tc::mbar_wait(&empty[stage], phase ^ 1); __syncwarp(); }
+          else tc::mbar_wait(&empty[stage], phase ^ 1);
         }
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && (p.dbg & 8)) tc::mbar_arrive(&full[stage]);
+        if (threadIdx.x == 0 && !(p.dbg & 8)) {
           tc::mbar_expect_tx(&full[stage], (uint32_t)p.b_stage);
           cb_bulk_load(tc::smem_u32(sB + stage * p.b_stage), wsrc + (int64_t)ks * p.b_stage, (uint32_t)p.b_stage,
                        tc::smem_u32(&full[stage]));
@@ -175,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
         for (int q = 0; q < PPT; ++q) {
           const bool ok = ((vy[q] >> ky) & (vx[q] >> kx) & 1u) != 0;
           const bf16* src = ok ? base[q] + tapoff : p.x;
-          cb_cp_async16(a_dst + q * (BUILDERS / 8) * 16, src, ok ? 16u : 0u);
+          if (!(p.dbg & 1)) cb_cp_async16(a_dst + q * (BUILDERS / 8) * 16, src, ok ? 16u : 0u);
         }
         cb_cp_async_commit();
         c += KC;
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if (++pending > lag) {
           cb_cp_async_wait_dyn(lag);
-          tc::fence_proxy_async();                             // generic-proxy writes -> async (tensor core) proxy
+          if (!(p.dbg & 16)) tc::fence_proxy_async();          // generic-proxy writes -> async (tensor core) proxy
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&full[astage]);       // one arrival per warp: 9 per stage instead of 257
           if (++astage == p.stages) astage = 0;
@@ -202,6 +215,8 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
     // ------------------------------------------------------------------ MMA issuer
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc(128, p.Ncols, 0, 0);
+      const uint64_t desc_a0 = tc::make_sdesc(tc::smem_u32(sA), PLANE, 128, 0u);             // LBO = plane, SBO = 8 rows
+      const uint64_t desc_b0 = tc::make_sdesc(tc::smem_u32(sB), 128, (KC / 8) * 128, 0u);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t aphase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         tc::mbar_wait(&tempty[acc], aphase ^ 1);
@@ -209,13 +224,14 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
         for (int ks = 0; ks < p.KS; ++ks) {
           tc::mbar_wait(&full[stage], phase);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(sA + stage * A_STAGE);
-          const uint32_t sb = tc::smem_u32(sB + stage * p.b_stage);
+          // descriptors = ring-slot-0 descriptor + (byte offset >> 4): the address field is the low 14 bits
+          const uint64_t da0 = desc_a0 + (uint64_t)((stage * A_STAGE) >> 4);
+          const uint64_t db0 = desc_b0 + (uint64_t)((stage * p.b_stage) >> 4);
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk) {
-            const uint64_t da = tc::make_sdesc(sa + kk * 2 * PLANE, PLANE, 128, 0u);       // LBO = plane, SBO = 8 rows
-            const uint64_t db = tc::make_sdesc(sb + kk * 256, 128, (KC / 8) * 128, 0u);
-            tc::mma_bf16(tmem_base + acc * p.Ncols, da, db, idesc, (ks | kk) != 0);
+            const uint64_t da = da0 + (uint64_t)((kk * 2 * PLANE) >> 4);
+            const uint64_t db = db0 + (uint64_t)((kk * 256) >> 4);
+            if (!(p.dbg & 2)) tc::mma_bf16(tmem_base + acc * p.Ncols, da, db, idesc, (ks | kk) != 0);
           }
           tc::mma_commit(&empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
       tc::mbar_wait(&tfull[acc], aphase);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Ncols);
-      for (int cb = 0; cb < p.Ncols; cb += 16) {
+      for (int cb = 0; cb < ((p.dbg & 4) ? 0 : p.Ncols); cb += 16) {
         float v[16];
         tc::tmem_ld16(taddr + cb, v);                          // warp-collective: every lane, also past the M tail
         uint32_t pk[8];
@@ -347,6 +363,8 @@ int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const flo
   fast_div((uint32_t)p.Wo, &p.wo_mul, &p.wo_shr);
   fast_div((uint32_t)p.n_tiles, &p.nt_mul, &p.nt_shr);
   p.HoWo = p.Ho * p.Wo;
+  static const int dbg_env = getenv("LG_CONVBN_DBG") ? atoi(getenv("LG_CONVBN_DBG")) : 0;
+  p.dbg = dbg_env;
   int stages = (196 * 1024) / (A_STAGE + p.b_stage);
   p.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
   const size_t shm = (size_t)p.stages * (A_STAGE + p.b_stage) + 1024 + 256 + 2 * (size_t)Cout * sizeof(float);
