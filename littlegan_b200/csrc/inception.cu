@@ -188,7 +188,7 @@ extern "C" int lg_conv2d_bn_relu(const void* x, const float* W, const void* wpac
   LG_REQUIRE(x && (W || wpack) && scale && shift && y, "null pointer");
   const int64_t M = (int64_t)N * ((H + 2 * ph - kh) / stride + 1) * ((Wd + 2 * pw - kw) / stride + 1);
   LG_REQUIRE(M < (1ll << 31) - 128 && (int64_t)kh * kw * Cin < (1ll << 31), "problem too large");
-  if (dtype == LG_BF16 && wpack != nullptr &&
+  if (dtype == LG_BF16 && wpack != nullptr && (int64_t)N * H * Wd * x_stride < (1ll << 31) &&   // 32-bit element offsets
       lg_tc_convbn_supported(Cin, x_stride, x_off, kh, kw, Cout, y_stride, y_off) &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(wpack)) & 15) == 0) {
     lg_tc_convbn(x, wpack, scale, shift, y, N, H, Wd, Cin, x_stride, x_off, kh, kw, stride, ph, pw, Cout, y_stride, y_off,

@@ -27,11 +27,13 @@ constexpr int KC = 64;                      // k per stage: 8 chunks of 8
 constexpr int PLANE = 128 * 16 + 16;        // one k-chunk plane of A: 128 positions x 16 B, pitched against bank conflicts
 constexpr int A_STAGE = (KC / 8) * PLANE;   // ~16 KB
 constexpr int BUILDERS = 512;               // 16 gather warps
-constexpr int PPT = 1024 / BUILDERS;        // positions per builder thread per stage
+constexpr int GROUPS = 4;                   // independent builder groups (different ring items in flight)
+constexpr int GROUP_THREADS = BUILDERS / GROUPS;
+constexpr int PPT = 1024 / GROUP_THREADS;   // positions per builder thread per item
+static_assert(PPT == 8, "the tile setup deals one position to each of the 8 chunk lanes");
 constexpr int THREADS = BUILDERS + 32 + 128;
 constexpr int MMA_WARP = BUILDERS / 32;     // then 4 epilogue warps (warp & 3 = TMEM lane quarter)
 constexpr int MAX_STAGES = 8;
-constexpr int MAX_LAG = 6;                  // stages a builder thread may run ahead of its arrivals (< stages)
 
 __device__ __forceinline__ void cb_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -77,7 +79,9 @@ struct CBParams {
   int M, K, Cout, Ncols, n_tiles, m_tiles, KS, stages, b_stage;   // b_stage = Ncols * KC * 2 bytes
   int HoWo;
   int dbg;                                                         // LG_CONVBN_DBG knock-outs (profiling only): 1 no A copies, 2 no MMAs, 4 no epilogue, 8 no B copies
+  int run;                                                         // consecutive ring items per builder group
   uint32_t hw_mul, hw_shr, wo_mul, wo_shr, nt_mul, nt_shr;         // / (Ho*Wo), / Wo, / n_tiles as multiply-high + shift
+  uint32_t ks_mul, ks_shr, ci_mul, ci_shr, kw_mul, kw_shr;         // / KS, / Cin, / kw
 };
 
 __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.stages * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * p.b_stage);
-  uint64_t* full = bars;                      // [MAX_STAGES] builders -> MMA   (8 warp arrivals + the weight block's bytes)
+  uint64_t* full = bars;                      // [MAX_STAGES] builders -> MMA   (the 4 warps of one builder group + the weight block's bytes)
   uint64_t* empty = bars + MAX_STAGES;        // [MAX_STAGES] MMA -> builders
   uint64_t* tfull = bars + 2 * MAX_STAGES;    // [2] MMA -> epilogue
   uint64_t* tempty = tfull + 2;               // [2] epilogue -> MMA            (4 arrivals)
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
 
   for (int e = threadIdx.x; e < p.Cout; e += THREADS) { sscale[e] = p.scale[e]; sshift[e] = p.shift[e]; }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_STAGES; ++i) { tc::mbar_init(&full[i], BUILDERS / 32 + 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { tc::mbar_init(&full[i], GROUP_THREADS / 32 + 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
     tc::fence_barrier_init();
   }
@@ -114,102 +118,103 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
 
   if (warp < MMA_WARP) {
     // ------------------------------------------------------------------ builders
-    // Every copy is asynchronous: the A runs by cp.async (zero-fill form for padding and tails), the stage's weight
-    // block by one bulk copy that completes on the stage's full barrier.  A warp arrives for stage i only after it has
-    // issued up to `lag` more stages, so no load latency is exposed while the ring has free slots.
+    // The ring items (tile, k stage) are dealt to GROUPS independent groups of 4 warps: one pass of the stage loop is a
+    // chain of long-latency synchronisation instructions (barrier test, vote, cp.async wait, proxy fence, arrive:
+    // ~1000 cycles measured with every copy and MMA knocked out), so the groups work on different items at the same
+    // time instead of all warps stepping through every stage together (item i goes to group i % GROUPS).
+    // Every copy is asynchronous: the A runs by cp.async (zero-fill form for padding and tails), the item's weight
+    // block by one bulk copy that completes on the item's full barrier.
     // Lane mapping: the 8 chunks of a position are 8 consecutive lanes (channel / tap runs that are contiguous in
     // memory), a warp covers 4 neighbouring positions - a warp-wide copy touches 4 full 128-byte lines instead of 32
     // partial ones.  Planes are pitched 2048 + 16 bytes so that those 32 stores spread over all banks.
-    // The stage loop is kept to a few dozen instructions per thread (16 warps of dependent integer chains would
-    // otherwise be the bound): per position a base pointer and two bit masks of the in-image ky / kx taps are made
-    // once per tile, a stage then needs one tap offset, two shifts and a select per copy.
-    const int chunk = threadIdx.x & 7, prow = threadIdx.x >> 3;
-    int stage = 0; uint32_t phase = 0;      // slot being filled
-    int astage = 0;                         // oldest slot this warp has not arrived for yet
-    int pending = 0;                        // stages issued but not yet arrived for
-    // the ring must hold the lag + 1 stages in flight AND the stages the tensor core is still reading: with a lag of
-    // ring - 1 the two sides can only work in alternating bursts (measured: ~1000 cycles per stage of pure hand-shake)
-    const int lag = p.stages / 2 < MAX_LAG ? p.stages / 2 : MAX_LAG;
-    // (ky, kx, c) of this thread's chunk in the first stage of a tile
-    int c_first = chunk * 8, kx_first = 0, ky_first = 0;
-    while (c_first >= p.Cin) { c_first -= p.Cin; if (++kx_first == p.kw) { kx_first = 0; ++ky_first; } }
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = p.n_tiles == 1 ? t : cb_div(t, p.nt_mul, p.nt_shr), nt = t - mt * p.n_tiles;
-      uint32_t vy[PPT], vx[PPT];                               // bit k set: tap row / column k is inside the image
-      const bf16* base[PPT];                                   // &x[n, y0, x0, 0] (may lie outside; used with valid taps)
-#pragma unroll
-      for (int q = 0; q < PPT; ++q) {
-        const int gm = mt * 128 + prow + (BUILDERS / 8) * q;
-        vy[q] = 0; vx[q] = 0; base[q] = p.x;                   // rows past M: no tap is valid
-        if (gm < p.M) {
-          const int n = cb_div(gm, p.hw_mul, p.hw_shr);
-          const int r = gm - n * p.HoWo;
-          const int oy = cb_div(r, p.wo_mul, p.wo_shr), ox = r - oy * p.Wo;
-          const int y0 = p.s * oy - p.ph, x0 = p.s * ox - p.pw;
-          vy[q] = cb_tap_mask(y0, p.kh, p.H);
-          vx[q] = cb_tap_mask(x0, p.kw, p.W);
-          base[q] = p.x + ((int64_t)(n * p.H + y0) * p.W + x0) * p.xs;
-        }
-      }
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (int64_t)nt * p.KS * p.b_stage;
-      int c = c_first, kx = kx_first, ky = ky_first;           // advanced by 64 k per stage without divisions
-      for (int ks = 0; ks < p.KS; ++ks) {
-        // Slot not free yet = the tensor core is behind: hand over everything issued so far before blocking, so
-        // that the MMA issuer is never starved by the run-ahead.  (Warp-uniform decision: lane 0 arrives for all.)
-        bool slot_free;
-        if (p.dbg & 32) {                                      // lane 0 polls for the warp
-          slot_free = lane == 0 ? cb_mbar_test(&empty[stage], phase ^ 1) : true;
-          slot_free = __all_sync(0xffffffffu, slot_free);
-        } else {
-          slot_free = __all_sync(0xffffffffu, cb_mbar_test(&empty[stage], phase ^ 1));
-        }
-        if (!slot_free) {
-          if (pending) {
-            cb_cp_async_wait<0>();
-            if (!(p.dbg & 16)) tc::fence_proxy_async();
-            __syncwarp();
-            for (; pending > 0; --pending) {
-              if (lane == 0) tc::mbar_arrive(&full[astage]);
-              if (++astage == p.stages) astage = 0;
+    const int group = threadIdx.x / GROUP_THREADS, gtid = threadIdx.x - group * GROUP_THREADS;
+    const int chunk = gtid & 7, prow = gtid >> 3;               // prow: 0 .. GROUP_THREADS/8 - 1
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_items = my_tiles * p.KS;
+    const int smask = p.stages - 1, sshift_ = p.stages == 8 ? 3 : 2;      // ring sizes are 4 or 8
+    uint32_t vyx[PPT];                                         // bits 0-7: in-image tap rows, bits 8-15: tap columns
+    const bf16* base[PPT];                                     // &x[n, y0, x0, 0] (may lie outside; used with valid taps)
+    int cur_tile = -1;
+    const uint8_t* wsrc = nullptr;
+    int astage = 0, pending = 0;                               // oldest item this warp has not arrived for yet
+    for (int blk = group; blk * p.run < total_items; blk += GROUPS) {
+      const int item_end = min(total_items, (blk + 1) * p.run);
+      for (int item = blk * p.run; item < item_end; ++item) {
+        const int tl = cb_div(item, p.ks_mul, p.ks_shr), ks = item - tl * p.KS;
+        const int stage = item & smask;
+        const uint32_t phase = (uint32_t)(item >> sshift_) & 1u;
+        if (tl != cur_tile) {
+          cur_tile = tl;
+          const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+          const int mt = p.n_tiles == 1 ? t : cb_div(t, p.nt_mul, p.nt_shr), nt = t - mt * p.n_tiles;
+          wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (int64_t)nt * p.KS * p.b_stage;
+          // the 8 chunk lanes of a position row need the same 8 positions: lane `chunk` sets up position `chunk`,
+          // the values travel by shuffles (an eighth of the integer work per thread)
+          uint32_t my_vyx = 0;                                 // rows past M: no tap is valid
+          int my_off = 0;                                      // element offset of &x[n, y0, x0, 0] (fits 32 bits)
+          {
+            const int gm = mt * 128 + prow + (GROUP_THREADS / 8) * chunk;
+            if (gm < p.M) {
+              const int n = cb_div(gm, p.hw_mul, p.hw_shr);
+              const int r = gm - n * p.HoWo;
+              const int oy = cb_div(r, p.wo_mul, p.wo_shr), ox = r - oy * p.Wo;
+              const int y0 = p.s * oy - p.ph, x0 = p.s * ox - p.pw;
+              my_vyx = cb_tap_mask(y0, p.kh, p.H) | (cb_tap_mask(x0, p.kw, p.W) << 8);
+              my_off = ((n * p.H + y0) * p.W + x0) * p.xs;
             }
           }
-          if (p.dbg & 32) { if (lane == 0) tc::mbar_wait(&empty[stage], phase ^ 1); __syncwarp(); }
-          else tc::mbar_wait(&empty[stage], phase ^ 1);
+#pragma unroll
+          for (int q = 0; q < PPT; ++q) {
+            const int src_lane = (lane & ~7) | q;
+            vyx[q] = __shfl_sync(0xffffffffu, my_vyx, src_lane);
+            base[q] = p.x + __shfl_sync(0xffffffffu, my_off, src_lane);
+          }
         }
-        if (threadIdx.x == 0 && (p.dbg & 8)) tc::mbar_arrive(&full[stage]);
-        if (threadIdx.x == 0 && !(p.dbg & 8)) {
+        // Slot not free yet = the tensor core is behind: hand over everything issued so far before blocking.
+        // (Warp-uniform decision: lane 0 arrives for the warp.)
+        if (!__all_sync(0xffffffffu, cb_mbar_test(&empty[stage], phase ^ 1))) {
+          if (pending) {
+            cb_cp_async_wait<0>();
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[astage]);
+            pending = 0;
+          }
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+        }
+        if (gtid == 0 && (p.dbg & 8)) tc::mbar_arrive(&full[stage]);
+        if (gtid == 0 && !(p.dbg & 8)) {
           tc::mbar_expect_tx(&full[stage], (uint32_t)p.b_stage);
           cb_bulk_load(tc::smem_u32(sB + stage * p.b_stage), wsrc + (int64_t)ks * p.b_stage, (uint32_t)p.b_stage,
                        tc::smem_u32(&full[stage]));
         }
+        // (ky, kx, c) of this thread's chunk: k = ks * 64 + chunk * 8 = (ky * kw + kx) * Cin + c
+        const int k0 = ks * KC + chunk * 8;
+        const int tap = cb_div(k0, p.ci_mul, p.ci_shr), c = k0 - tap * p.Cin;
+        const int ky = cb_div(tap, p.kw_mul, p.kw_shr), kx = tap - ky * p.kw;     // ky >= kh in the K tail: no mask bit
+        const int tapoff = (ky * p.W + kx) * p.xs + c;
         const uint32_t a_dst = tc::smem_u32(sA + stage * A_STAGE + chunk * PLANE + prow * 16);
-        const int tapoff = (ky * p.W + kx) * p.xs + c;        // ky >= kh (K tail): vy has no such bit
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
-          const bool ok = ((vy[q] >> ky) & (vx[q] >> kx) & 1u) != 0;
+          const bool ok = ((vyx[q] >> ky) & (vyx[q] >> (8 + kx)) & 1u) != 0;
           const bf16* src = ok ? base[q] + tapoff : p.x;
-          if (!(p.dbg & 1)) cb_cp_async16(a_dst + q * (BUILDERS / 8) * 16, src, ok ? 16u : 0u);
+          if (!(p.dbg & 1)) cb_cp_async16(a_dst + q * (GROUP_THREADS / 8) * 16, src, ok ? 16u : 0u);
         }
         cb_cp_async_commit();
-        c += KC;
-        while (c >= p.Cin) { c -= p.Cin; if (++kx == p.kw) { kx = 0; ++ky; } }
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        if (++pending > lag) {
-          cb_cp_async_wait_dyn(lag);
-          if (!(p.dbg & 16)) tc::fence_proxy_async();          // generic-proxy writes -> async (tensor core) proxy
+        if (pending) {                                         // one item of run-ahead per warp: hand over the previous
+          cb_cp_async_wait<1>();
+          tc::fence_proxy_async();                             // generic-proxy writes -> async (tensor core) proxy
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&full[astage]);       // one arrival per warp: 9 per stage instead of 257
-          if (++astage == p.stages) astage = 0;
-          --pending;
+          if (lane == 0) tc::mbar_arrive(&full[astage]);
         }
+        astage = stage; pending = 1;
       }
     }
-    cb_cp_async_wait<0>();
-    tc::fence_proxy_async();
-    __syncwarp();
-    for (; pending > 0; --pending) {
+    if (pending) {
+      cb_cp_async_wait<0>();
+      tc::fence_proxy_async();
+      __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full[astage]);
-      if (++astage == p.stages) astage = 0;
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
@@ -233,10 +238,10 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
             const uint64_t db = db0 + (uint64_t)((kk * 256) >> 4);
             if (!(p.dbg & 2)) tc::mma_bf16(tmem_base + acc * p.Ncols, da, db, idesc, (ks | kk) != 0);
           }
-          tc::mma_commit(&empty[stage]);
+          if (p.dbg & 64) tc::mbar_arrive(&empty[stage]); else tc::mma_commit(&empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&tfull[acc]);
+        if (p.dbg & 64) tc::mbar_arrive(&tfull[acc]); else tc::mma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; aphase ^= 1; }
       }
     }
@@ -362,11 +367,16 @@ int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const flo
   fast_div((uint32_t)(p.Ho * p.Wo), &p.hw_mul, &p.hw_shr);
   fast_div((uint32_t)p.Wo, &p.wo_mul, &p.wo_shr);
   fast_div((uint32_t)p.n_tiles, &p.nt_mul, &p.nt_shr);
+  fast_div((uint32_t)p.KS, &p.ks_mul, &p.ks_shr);
+  fast_div((uint32_t)Cin, &p.ci_mul, &p.ci_shr);
+  fast_div((uint32_t)kw, &p.kw_mul, &p.kw_shr);
+  // run = 1: with GROUPS dividing the ring size every slot is always filled by the same group, in order, so the
+  // parity wait on its empty barrier can never be a whole ring generation off (longer runs would need a counter)
+  p.run = 1;
   p.HoWo = p.Ho * p.Wo;
   static const int dbg_env = getenv("LG_CONVBN_DBG") ? atoi(getenv("LG_CONVBN_DBG")) : 0;
   p.dbg = dbg_env;
-  int stages = (196 * 1024) / (A_STAGE + p.b_stage);
-  p.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+  p.stages = 8 * (A_STAGE + p.b_stage) <= 196 * 1024 ? 8 : 4;        // power of two: slot = item & (stages - 1)
   const size_t shm = (size_t)p.stages * (A_STAGE + p.b_stage) + 1024 + 256 + 2 * (size_t)Cout * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
