@@ -78,6 +78,27 @@ def test_pool2d_modes(cfg, dtype):
     assert float(y[..., :8].abs().max()) == 0 and float(y[..., 32:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("cfg", [(64, 35, 35, 288, 1, 1, 1), (64, 35, 35, 288, 1, 1, 2), (32, 71, 71, 192, 2, 0, 0),
+                                 (100, 8, 8, 2048, 1, 1, 0), (16, 17, 17, 768, 2, 0, 0)])
+def test_pool3_sliding_window_full_size(cfg):
+    """The Inception pools at their real sizes (bf16): the kernel walks multi-row segments with a 3-row window."""
+    from littlegan_b200 import kernels as K
+    N, H, W_, C, s, p, mode = cfg
+    x = _rand((N, H, W_, C), 9, torch.bfloat16).cuda()
+    xc = x.float().permute(0, 3, 1, 2)
+    if mode == 0:
+        ref = F.max_pool2d(xc, 3, stride=s, padding=p)
+    else:
+        ref = F.avg_pool2d(xc, 3, stride=s, padding=p, count_include_pad=(mode == 2))
+    ref = ref.permute(0, 2, 3, 1)
+    y = torch.zeros(N, ref.shape[1], ref.shape[2], C + 16, dtype=torch.bfloat16, device="cuda")
+    K.pool2d(x, y, 8, 3, s, p, mode)
+    assert rel_err(y[..., 8:8 + C], ref) < 1e-2
+    if mode == 0:
+        assert torch.equal(y[..., 8:8 + C].float(), ref)        # a max of bf16 values is exact
+    assert float(y[..., :8].abs().max()) == 0 and float(y[..., 8 + C:].abs().max()) == 0
+
+
 @pytest.mark.parametrize("src", ["u8", "f32"])
 def test_resize_bilinear_tf1_and_normalise(src):
     from littlegan_b200 import kernels as K
