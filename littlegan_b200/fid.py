@@ -6,10 +6,11 @@ materialising the [N, 2048] fp64 activation matrix and calling np.mean / np.cov
 (`fid.py:95,186-187`).  With torch.distributed initialised every rank accumulates its shard and
 the (n, S1, S2) triple is all-reduced once (SURVEY 8 e).
 
-The Inception-2015 pool_3 forward itself (`fid.py:36-106`) needs an external weight download and
-is a later-round row: `sess` here is any callable mapping an image batch
-[b,H,W,3] (0..255) to a CUDA fp32 feature matrix [b,d]; pass `sess=None` with a 2-D input to
-feed precomputed activations.
+The Inception-2015 pool_3 forward itself (`fid.py:36-106`) is `littlegan_b200.inception.InceptionPool3`: an instance
+is the `sess` argument here (any callable mapping an image batch [b,H,W,3] in 0..255 to a CUDA fp32 feature matrix
+[b,d] works); pass `sess=None` with a 2-D input to feed precomputed activations.  The file-based variants
+(`fid.py:197-318`: `*_from_files`, `_handle_path`, `calculate_fid_given_paths`) decode on host threads one batch ahead
+of the GPU and hand the forward image BYTES.
 """
 import warnings
 
@@ -151,3 +152,100 @@ def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
         offset = torch.eye(sigma1.shape[0], dtype=torch.float64, device=dev) * eps
         tr = _trace_sqrt_product(sigma1 + offset, sigma2 + offset)
     return float(diff.dot(diff) + torch.trace(sigma1) + torch.trace(sigma2) - 2 * tr)
+
+
+# ------------------------------------------------------------------ file-based variants (fid.py:197-318)
+def load_image_batch(files):
+    """fid.py:197-204: the images of `files` as one array [n,H,W,3].  uint8 (the forward's input stage reads bytes;
+    the reference widens the same values to float32)."""
+    from PIL import Image
+    out = []
+    for fn in files:
+        with Image.open(str(fn)) as im:
+            out.append(np.array(im.convert("RGB"), dtype=np.uint8))
+    return np.stack(out)
+
+
+def create_inception_graph(pth=None, dtype="bf16"):
+    """fid.py:36-42 stand-in: the pool_3 feature extractor.  `pth`: a converted weight file (`inception.load_npz`
+    layout); None = random weights (there is no network to fetch the 2015 GraphDef, fid.py:276-287)."""
+    from .inception import InceptionPool3, load_npz
+    return InceptionPool3(weights=None if pth is None else load_npz(str(pth)), dtype=dtype)
+
+
+def check_or_download_inception(inception_path):
+    """fid.py:273-288 without the download: returns the converted weight file under `inception_path` or raises."""
+    import pathlib
+    if inception_path is None:
+        return None
+    p = pathlib.Path(inception_path)
+    f = p if p.suffix == ".npz" else p / "inception_2015_pool3.npz"
+    if not f.exists():
+        raise RuntimeError("no converted Inception weights at %s (no network: convert classify_image_graph_def.pb "
+                           "offline into the inception.load_npz layout)" % f)
+    return str(f)
+
+
+def get_activations_from_files(files, sess, batch_size=50, verbose=False):
+    """fid.py:207-240 as a generator of CUDA feature batches; the next batch is decoded on a host thread while the
+    GPU runs the current one; the N % batch tail is dropped as in the reference."""
+    from concurrent.futures import ThreadPoolExecutor
+    d0 = len(files)
+    if batch_size > d0:
+        print("warning: batch size is bigger than the data size. setting batch size to data size")
+        batch_size = d0
+    n_batches = d0 // batch_size
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        nxt = pool.submit(load_image_batch, files[:batch_size]) if n_batches else None
+        for i in range(n_batches):
+            if verbose:
+                print("\rPropagating batch %d/%d" % (i + 1, n_batches), end="", flush=True)
+            batch = nxt.result()
+            if i + 1 < n_batches:
+                nxt = pool.submit(load_image_batch, files[(i + 1) * batch_size:(i + 2) * batch_size])
+            feats = sess(batch)
+            if isinstance(feats, np.ndarray):
+                feats = torch.from_numpy(feats)
+            yield feats.reshape(batch_size, -1).to("cuda", torch.float32, non_blocking=True)
+    if verbose:
+        print(" done")
+
+
+def calculate_activation_statistics_from_files(files, sess, batch_size=50, verbose=False, as_numpy=True):
+    """fid.py:243-260 -> (mu, sigma) in fp64, streaming."""
+    acc = None
+    for feats in get_activations_from_files(files, sess, batch_size, verbose):
+        if acc is None:
+            acc = FeatureStatistics(feats.shape[1], feats.device)
+        acc.update(feats)
+    if acc is None:
+        raise InvalidFIDException("no images")
+    mu, sigma = acc.finalize()
+    return (mu.cpu().numpy(), sigma.cpu().numpy()) if as_numpy else (mu, sigma)
+
+
+def _handle_path(path, sess, low_profile=False):
+    """fid.py:291-304: statistics of an .npz file (`mu`, `sigma`) or of the *.jpg / *.png files of a directory."""
+    import pathlib
+    path = str(path)
+    if path.endswith(".npz"):
+        with np.load(path) as f:
+            return f["mu"][:], f["sigma"][:]
+    p = pathlib.Path(path)
+    files = sorted(p.glob("*.jpg")) + sorted(p.glob("*.png"))
+    if low_profile:
+        return calculate_activation_statistics_from_files(files, sess)
+    return calculate_activation_statistics(load_image_batch(files), sess)
+
+
+def calculate_fid_given_paths(paths, inception_path, low_profile=False, sess=None):
+    """fid.py:307-318.  `sess`: a ready feature extractor (skips loading weights from `inception_path`)."""
+    import os
+    for p in paths:
+        if not os.path.exists(p):
+            raise RuntimeError("Invalid path: %s" % p)
+    if sess is None:
+        sess = create_inception_graph(check_or_download_inception(inception_path))
+    m1, s1 = _handle_path(paths[0], sess, low_profile=low_profile)
+    m2, s2 = _handle_path(paths[1], sess, low_profile=low_profile)
+    return calculate_frechet_distance(m1, s1, m2, s2)

@@ -178,3 +178,51 @@ def test_celeba_rejects_wrong_size_and_short_attr_list(tmp_path):
     (tmp_path / "list.txt").write_text("000001.png" + " 1" * 40 + "\n")
     with pytest.raises(ValueError):
         CelebA(a, pin=False)
+
+
+def test_fid_file_helpers_host_side(tmp_path):
+    """fid.py:197-204, 273-318 host glue: batch loading, path validation, the weight-file check (no download here)."""
+    import numpy as np
+    from littlegan_b200 import fid
+    imgs, _ = _write_celeba(tmp_path, 5, 16)
+    files = sorted((tmp_path / "img").glob("*.png"))
+    batch = fid.load_image_batch(files)
+    assert batch.dtype == np.uint8 and np.array_equal(batch, imgs)
+    with pytest.raises(RuntimeError, match="Invalid path"):
+        fid.calculate_fid_given_paths([str(tmp_path / "img"), str(tmp_path / "nope")], None, sess=lambda x: x)
+    with pytest.raises(RuntimeError, match="no converted Inception weights"):
+        fid.check_or_download_inception(str(tmp_path))
+    assert fid.check_or_download_inception(None) is None
+    np.savez(tmp_path / "stats.npz", mu=np.arange(4.0), sigma=np.eye(4))
+    mu, sigma = fid._handle_path(str(tmp_path / "stats.npz"), None)
+    assert np.array_equal(mu, np.arange(4.0)) and np.array_equal(sigma, np.eye(4))
+
+
+def test_inception_program_matches_the_oracle_table():
+    """The product's graph program and the oracle's unit table are written independently; they must list the same 94
+    conv units (name, channels, kernel, stride, padding) in the same order, and the blocks must concatenate to the
+    widths of the published graph."""
+    from littlegan_b200 import inception as I
+    from oracle import inception_oracle as IO
+    got = [(u["name"], u["cin"], u["cout"], tuple(u["k"]), u["s"], tuple(u["p"])) for u in I.unit_specs()]
+    assert got == [tuple(u) for u in IO.UNITS]
+    assert len(got) == 94 and sum(1 for _ in I._units(I.program(False))) == 94
+    width, widths = 3, []
+    for st in I.program():
+        if isinstance(st, dict):
+            assert st["cin"] == width
+            width = st["cout"]
+        elif isinstance(st, list):
+            total = 0
+            for br in st:
+                c = width
+                for piece in br:
+                    if isinstance(piece, dict):
+                        assert piece["cin"] == c, piece["name"]
+                    elif isinstance(piece, list):
+                        assert all(u["cin"] == c for u in piece)
+                    c = I.InceptionPool3._width(piece, c)
+                total += c
+            width = total
+            widths.append(width)
+    assert widths == [256, 288, 288, 768, 768, 768, 768, 768, 1280, 2048, 2048]

@@ -182,3 +182,38 @@ def test_fid_statistics_through_the_inception_session():
     mu_ref, sigma_ref = fid_oracle.activation_statistics(feats)
     assert np.abs(mu - mu_ref).max() < 1e-4 * np.abs(mu_ref).max()
     assert np.abs(sigma - sigma_ref).max() < 1e-3 * np.abs(sigma_ref).max()
+
+
+def test_fid_given_paths_and_file_statistics(tmp_path):
+    """fid.py:207-318: statistics from image files (batched, decoded ahead on a host thread) equal the in-memory
+    path and the oracle; calculate_fid_given_paths over directory / .npz inputs."""
+    from PIL import Image
+    from littlegan_b200 import fid
+    from littlegan_b200.inception import InceptionPool3
+    from oracle import fid_oracle
+    W = IO.random_weights(seed=6)
+    rng = np.random.default_rng(5)
+    dirs = []
+    for d, shift in (("a", 0), ("b", 40)):
+        (tmp_path / d).mkdir()
+        arr = np.clip(rng.integers(0, 216, (9, 32, 32, 3)) + shift, 0, 255).astype(np.uint8)
+        for i, im in enumerate(arr):
+            Image.fromarray(im, "RGB").save(str(tmp_path / d / ("%03d.png" % i)))
+        dirs.append((str(tmp_path / d), arr))
+    net = InceptionPool3(weights=W)
+    files = sorted((tmp_path / "a").glob("*.png"))
+    mu, sigma = fid.calculate_activation_statistics_from_files(files, net, batch_size=4)       # 8 of 9 used
+    feats = IO.InceptionOracle(W, dtype=torch.float64)(torch.from_numpy(dirs[0][1][:8]).double()).numpy()
+    mu_ref, sigma_ref = fid_oracle.activation_statistics(feats)
+    assert np.abs(mu - mu_ref).max() < 1e-4 * np.abs(mu_ref).max()
+    assert np.abs(sigma - sigma_ref).max() < 1e-3 * np.abs(sigma_ref).max()
+    mu_mem, sigma_mem = fid.calculate_activation_statistics(dirs[0][1][:8], net, batch_size=4)
+    assert np.abs(mu - mu_mem).max() < 1e-6 * np.abs(mu_mem).max()
+    d_ab = fid.calculate_fid_given_paths([dirs[0][0], dirs[1][0]], None, sess=net)
+    d_ba = fid.calculate_fid_given_paths([dirs[1][0], dirs[0][0]], None, sess=net, low_profile=True)
+    assert d_ab > 0 and abs(d_ab - d_ba) < 1e-3 * d_ab            # low_profile batches of 9 < 50 -> all 9 used in both
+    mu_b, sigma_b = fid._handle_path(dirs[1][0], net)
+    np.savez(tmp_path / "b.npz", mu=mu_b, sigma=sigma_b)
+    d_npz = fid.calculate_fid_given_paths([dirs[0][0], str(tmp_path / "b.npz")], None, sess=net)
+    assert abs(d_npz - d_ab) < 1e-6 * d_ab
+    assert abs(fid.calculate_fid_given_paths([dirs[0][0], dirs[0][0]], None, sess=net)) < 1e-6 * d_ab
