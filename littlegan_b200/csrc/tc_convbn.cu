@@ -2,14 +2,12 @@
 // an implicit GEMM  y[pos][co] = sum_k patch[pos][k] * W[k][co]  with  k = (ky, kx, c), any kh x kw / stride / padding /
 // odd map sizes (299, 149, 147, 73, 71, 35, 17, 8 do not tile into TMA boxes, so the patch matrix is gathered).
 //
-//   * 8 builder warps gather the A operand: thread (m, half) owns output position m of the 128-position tile and
-//     copies 16-byte runs (8 channels of one tap - channel counts are multiples of 8) straight from the NHWC map into
-//     the no-swizzle K-major core-matrix layout [k-chunk of 8][position][16 B] with cp.async; out-of-image taps and the
-//     K / M tails use its zero-fill form.  The (ky, kx, c) walk is incremental (no divisions in the stage loop) and a
-//     thread arrives for a stage only after issuing up to six more (ring size - 1), so the gathers of a whole ring are
-//     in flight per thread; when the next slot is not free yet it hands over everything issued before blocking.
-//     The stage's weight block, prepacked in exactly its shared-memory image, arrives by ONE bulk copy (TMA unit)
-//     that completes on the same full barrier.
+//   * 16 builder warps in 4 independent groups gather the A operand, each group filling a different ring item: thread
+//     (position row, chunk) copies 16-byte runs (8 channels of one tap - channel counts are multiples of 8) straight
+//     from the NHWC map into the no-swizzle K-major core-matrix layout [k-chunk of 8][position][16 B] with cp.async;
+//     out-of-image taps and the K / M tails use its zero-fill form.  Tile setup (positions -> image coordinates, tap
+//     validity bit masks) is division-free and shared across the 8 chunk lanes by shuffles.  The item's weight block,
+//     prepacked in exactly its shared-memory image, arrives by ONE bulk copy (TMA unit) on the same full barrier.
 //   * one elected thread issues 128 x Ncols x 16 tcgen05.mma over a 4-8 stage mbarrier ring into one of two TMEM
 //     accumulators (Ncols <= 256, Cout > 256 is split into equal column tiles);
 //   * 4 epilogue warps read the accumulator (tcgen05.ld), apply scale / shift / ReLU and write bf16 rows into the
@@ -41,18 +39,6 @@ __device__ __forceinline__ void cb_cp_async16(uint32_t dst, const void* src, uin
 __device__ __forceinline__ void cb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cb_cp_async_wait_dyn(int n) {   // at most n of this thread's groups still pending
-  switch (n) {
-    case 0: cb_cp_async_wait<0>(); break;
-    case 1: cb_cp_async_wait<1>(); break;
-    case 2: cb_cp_async_wait<2>(); break;
-    case 3: cb_cp_async_wait<3>(); break;
-    case 4: cb_cp_async_wait<4>(); break;
-    case 5: cb_cp_async_wait<5>(); break;
-    case 6: cb_cp_async_wait<6>(); break;
-    default: cb_cp_async_wait<7>(); break;
-  }
-}
 __device__ __forceinline__ int cb_div(int n, uint32_t mul, uint32_t shr) {   // n / d, (mul, shr) from fast_div
   return mul ? (int)(__umulhi((uint32_t)n, mul) >> shr) : n;
 }
@@ -78,8 +64,8 @@ struct CBParams {
   int H, W, Cin, xs, Ho, Wo, kh, kw, s, ph, pw, ys, relu;
   int M, K, Cout, Ncols, n_tiles, m_tiles, KS, stages, b_stage;   // b_stage = Ncols * KC * 2 bytes
   int HoWo;
-  int dbg;                                                         // LG_CONVBN_DBG knock-outs (profiling only): 1 no A copies, 2 no MMAs, 4 no epilogue, 8 no B copies
-  int run;                                                         // consecutive ring items per builder group
+  int dbg;       // LG_CONVBN_DBG knock-outs (profiling only; scripts/convbn_knockout.sh): 1 no A copies, 2 no MMAs,
+                 // 4 no epilogue, 8 no B copies, 64 plain arrive instead of tcgen05.commit
   uint32_t hw_mul, hw_shr, wo_mul, wo_shr, nt_mul, nt_shr;         // / (Ho*Wo), / Wo, / n_tiles as multiply-high + shift
   uint32_t ks_mul, ks_shr, ci_mul, ci_shr, kw_mul, kw_shr;         // / KS, / Cin, / kw
 };
@@ -137,9 +123,10 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
     int cur_tile = -1;
     const uint8_t* wsrc = nullptr;
     int astage = 0, pending = 0;                               // oldest item this warp has not arrived for yet
-    for (int blk = group; blk * p.run < total_items; blk += GROUPS) {
-      const int item_end = min(total_items, (blk + 1) * p.run);
-      for (int item = blk * p.run; item < item_end; ++item) {
+    // item i -> group i % GROUPS: with GROUPS dividing the ring size every slot is always filled by the same group, in
+    // order, so the parity wait on its empty barrier can never be a whole ring generation off
+    {
+      for (int item = group; item < total_items; item += GROUPS) {
         const int tl = cb_div(item, p.ks_mul, p.ks_shr), ks = item - tl * p.KS;
         const int stage = item & smask;
         const uint32_t phase = (uint32_t)(item >> sshift_) & 1u;
@@ -370,10 +357,6 @@ int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const flo
   fast_div((uint32_t)p.KS, &p.ks_mul, &p.ks_shr);
   fast_div((uint32_t)Cin, &p.ci_mul, &p.ci_shr);
   fast_div((uint32_t)kw, &p.kw_mul, &p.kw_shr);
-  // run = 1: with GROUPS dividing the ring size every slot is always filled by the same group, in order, so the
-  // parity wait on its empty barrier can never be a whole ring generation off (longer runs would need a counter)
-  p.run = 1;
-  p.HoWo = p.Ho * p.Wo;
   static const int dbg_env = getenv("LG_CONVBN_DBG") ? atoi(getenv("LG_CONVBN_DBG")) : 0;
   p.dbg = dbg_env;
   p.stages = 8 * (A_STAGE + p.b_stage) <= 196 * 1024 ? 8 : 4;        // power of two: slot = item & (stages - 1)
