@@ -357,6 +357,7 @@ int lg_tc_convbn(const void* x, const void* wpack, const float* scale, const flo
   fast_div((uint32_t)p.KS, &p.ks_mul, &p.ks_shr);
   fast_div((uint32_t)Cin, &p.ci_mul, &p.ci_shr);
   fast_div((uint32_t)kw, &p.kw_mul, &p.kw_shr);
+  p.HoWo = p.Ho * p.Wo;
   static const int dbg_env = getenv("LG_CONVBN_DBG") ? atoi(getenv("LG_CONVBN_DBG")) : 0;
   p.dbg = dbg_env;
   p.stages = 8 * (A_STAGE + p.b_stage) <= 196 * 1024 ? 8 : 4;        // power of two: slot = item & (stages - 1)
