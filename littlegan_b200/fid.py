@@ -167,23 +167,33 @@ def load_image_batch(files):
 
 
 def create_inception_graph(pth=None, dtype="bf16"):
-    """fid.py:36-42 stand-in: the pool_3 feature extractor.  `pth`: a converted weight file (`inception.load_npz`
-    layout); None = random weights (there is no network to fetch the 2015 GraphDef, fid.py:276-287)."""
-    from .inception import InceptionPool3, load_npz
-    return InceptionPool3(weights=None if pth is None else load_npz(str(pth)), dtype=dtype)
+    """fid.py:36-42 stand-in: the pool_3 feature extractor.  `pth`: the reference's own model file
+    (`classify_image_graph_def.pb` or the .tgz around it - read without TensorFlow, `inception.load_graphdef`), or a
+    converted `.npz` (`inception.load_npz`); None = random weights."""
+    from .inception import InceptionPool3, load_graphdef, load_npz
+    if pth is None:
+        weights = None
+    elif str(pth).endswith(".npz"):
+        weights = load_npz(str(pth))
+    else:
+        weights = load_graphdef(str(pth))
+    return InceptionPool3(weights=weights, dtype=dtype)
 
 
 def check_or_download_inception(inception_path):
-    """fid.py:273-288 without the download: returns the converted weight file under `inception_path` or raises."""
+    """fid.py:273-288 without the download (no network here): the model file under `inception_path` - the
+    reference's `classify_image_graph_def.pb`, the .tgz, or a converted `.npz` - or an error saying what to put there."""
     import pathlib
     if inception_path is None:
         return None
     p = pathlib.Path(inception_path)
-    f = p if p.suffix == ".npz" else p / "inception_2015_pool3.npz"
-    if not f.exists():
-        raise RuntimeError("no converted Inception weights at %s (no network: convert classify_image_graph_def.pb "
-                           "offline into the inception.load_npz layout)" % f)
-    return str(f)
+    if p.is_file():
+        return str(p)
+    for name in ("classify_image_graph_def.pb", "inception-2015-12-05.tgz", "inception_2015_pool3.npz"):
+        if (p / name).exists():
+            return str(p / name)
+    raise RuntimeError("no Inception model file under %s (no network: place classify_image_graph_def.pb from "
+                       "inception-2015-12-05.tgz there)" % p)
 
 
 def get_activations_from_files(files, sess, batch_size=50, verbose=False):

@@ -245,3 +245,183 @@ class InceptionPool3:
     def __call__(self, images):
         """images [b,H,W,3] in 0..255 (numpy / torch, uint8 or float) -> CUDA fp32 [b,2048]."""
         return self.features_from_normalised(self.preprocess(images))
+
+
+# ------------------------------------------------------------------ weights from the reference's own model file
+# The reference feeds `classify_image_graph_def.pb` (inception-2015-12-05.tgz, fid.py:276-287) to TensorFlow.  Without
+# TensorFlow the file is still just a protobuf: the functions below read its Const nodes with a minimal wire-format
+# parser and map the graph's scopes onto the unit names used here, so a user who has the file gets the real network.
+def _pb_fields(buf):
+    """(field number, wire type, value) of one protobuf message; length-delimited values are memoryviews."""
+    buf = memoryview(buf)
+    i, n = 0, len(buf)
+    while i < n:
+        key = shift = 0
+        while True:
+            b = buf[i]; i += 1
+            key |= (b & 0x7F) << shift
+            shift += 7
+            if not b & 0x80:
+                break
+        field, wt = key >> 3, key & 7
+        if wt == 0:
+            v = shift = 0
+            while True:
+                b = buf[i]; i += 1
+                v |= (b & 0x7F) << shift
+                shift += 7
+                if not b & 0x80:
+                    break
+        elif wt == 1:
+            v = buf[i:i + 8]; i += 8
+        elif wt == 5:
+            v = buf[i:i + 4]; i += 4
+        elif wt == 2:
+            ln = shift = 0
+            while True:
+                b = buf[i]; i += 1
+                ln |= (b & 0x7F) << shift
+                shift += 7
+                if not b & 0x80:
+                    break
+            v = buf[i:i + ln]; i += ln
+        else:
+            raise ValueError("unsupported protobuf wire type %d" % wt)
+        yield field, wt, v
+
+
+def _pb_tensor(buf):
+    """TensorProto -> float32 ndarray (DT_FLOAT only; tensor_content or float_val), or None for other dtypes."""
+    dtype, shape, content, floats = 0, [], None, []
+    for f, wt, v in _pb_fields(buf):
+        if f == 1 and wt == 0:
+            dtype = v
+        elif f == 2 and wt == 2:                               # TensorShapeProto { repeated Dim dim = 2 }
+            for f2, wt2, v2 in _pb_fields(v):
+                if f2 == 2 and wt2 == 2:
+                    size = 0
+                    for f3, wt3, v3 in _pb_fields(v2):
+                        if f3 == 1 and wt3 == 0:
+                            size = v3
+                    shape.append(size)
+        elif f == 4 and wt == 2:
+            content = bytes(v)
+        elif f == 5 and wt == 2:                               # packed repeated float
+            floats.append(np.frombuffer(bytes(v), dtype="<f4"))
+        elif f == 5 and wt == 5:
+            floats.append(np.frombuffer(bytes(v), dtype="<f4"))
+    if dtype != 1:
+        return None
+    count = int(np.prod(shape)) if shape else 1
+    if content is not None:
+        arr = np.frombuffer(content, dtype="<f4")
+    else:
+        arr = np.concatenate(floats) if floats else np.zeros(0, np.float32)
+        if arr.size == 1 and count > 1:                        # TF stores a constant-filled tensor as one value
+            arr = np.full(count, arr[0], np.float32)
+    if arr.size != count:
+        raise ValueError("tensor has %d values for shape %s" % (arr.size, shape))
+    return arr.astype(np.float32).reshape(shape)
+
+
+def parse_graphdef_consts(buf, wanted=None):
+    """name -> float32 array of the Const nodes of a serialized GraphDef (optionally only the names in `wanted`)."""
+    out = {}
+    for f, wt, node in _pb_fields(buf):
+        if f != 1 or wt != 2:                                  # GraphDef { repeated NodeDef node = 1 }
+            continue
+        name, op, tensor = None, None, None
+        for f2, wt2, v2 in _pb_fields(node):
+            if f2 == 1 and wt2 == 2:
+                name = bytes(v2).decode()
+            elif f2 == 2 and wt2 == 2:
+                op = bytes(v2).decode()
+            elif f2 == 5 and wt2 == 2:                         # map<string, AttrValue> attr: entry {key = 1, value = 2}
+                key, val = None, None
+                for f3, wt3, v3 in _pb_fields(v2):
+                    if f3 == 1 and wt3 == 2:
+                        key = bytes(v3).decode()
+                    elif f3 == 2 and wt3 == 2:
+                        val = v3
+                if key == "value" and val is not None:
+                    for f4, wt4, v4 in _pb_fields(val):        # AttrValue { TensorProto tensor = 8 }
+                        if f4 == 8 and wt4 == 2:
+                            tensor = v4
+        if op == "Const" and tensor is not None and (wanted is None or name in wanted):
+            arr = _pb_tensor(tensor)
+            if arr is not None:
+                out[name] = arr
+    return out
+
+
+def graphdef_scope(unit_name):
+    """Scope of a unit in the 2015 graph: the stem units are conv, conv_1 .. conv_4; Mixed_5b .. Mixed_7c are mixed,
+    mixed_1 .. mixed_10 with the branches as towers (tower, tower_1, tower_2) and the 1x3 / 3x1 forks as tower*/mixed."""
+    stem = {"Conv2d_1a_3x3": "conv", "Conv2d_2a_3x3": "conv_1", "Conv2d_2b_3x3": "conv_2", "Conv2d_3b_1x1": "conv_3",
+            "Conv2d_4a_3x3": "conv_4"}
+    if unit_name in stem:
+        return stem[unit_name]
+    block, branch = unit_name.split(".")
+    order = ["Mixed_5b", "Mixed_5c", "Mixed_5d", "Mixed_6a", "Mixed_6b", "Mixed_6c", "Mixed_6d", "Mixed_6e", "Mixed_7a",
+             "Mixed_7b", "Mixed_7c"]
+    idx = order.index(block)
+    scope = "mixed" if idx == 0 else "mixed_%d" % idx
+    nth = lambda i: "conv" if i == 0 else "conv_%d" % i
+    kind = "A" if idx < 3 else "B" if idx == 3 else "C" if idx < 8 else "D" if idx == 8 else "E"
+    table = {
+        "A": {"branch1x1": "conv", "branch5x5_1": "tower/conv", "branch5x5_2": "tower/conv_1",
+              "branch3x3dbl_1": "tower_1/conv", "branch3x3dbl_2": "tower_1/conv_1", "branch3x3dbl_3": "tower_1/conv_2",
+              "branch_pool": "tower_2/conv"},
+        "B": {"branch3x3": "conv", "branch3x3dbl_1": "tower/conv", "branch3x3dbl_2": "tower/conv_1",
+              "branch3x3dbl_3": "tower/conv_2"},
+        "C": dict([("branch1x1", "conv"), ("branch_pool", "tower_2/conv")]
+                  + [("branch7x7_%d" % (i + 1), "tower/" + nth(i)) for i in range(3)]
+                  + [("branch7x7dbl_%d" % (i + 1), "tower_1/" + nth(i)) for i in range(5)]),
+        "D": dict([("branch3x3_%d" % (i + 1), "tower/" + nth(i)) for i in range(2)]
+                  + [("branch7x7x3_%d" % (i + 1), "tower_1/" + nth(i)) for i in range(4)]),
+        "E": {"branch1x1": "conv", "branch3x3_1": "tower/conv", "branch3x3_2a": "tower/mixed/conv",
+              "branch3x3_2b": "tower/mixed/conv_1", "branch3x3dbl_1": "tower_1/conv", "branch3x3dbl_2": "tower_1/conv_1",
+              "branch3x3dbl_3a": "tower_1/mixed/conv", "branch3x3dbl_3b": "tower_1/mixed/conv_1",
+              "branch_pool": "tower_2/conv"},
+    }
+    return scope + "/" + table[kind][branch]
+
+
+def weights_from_graphdef(buf):
+    """The weight dict of `InceptionPool3` from the bytes of `classify_image_graph_def.pb`.  Every kernel's shape is
+    checked against the unit it is mapped to.  The graph normalises with scale_after_normalization = false, so its
+    gamma constants are not applied."""
+    specs = unit_specs()
+    wanted = set()
+    for u in specs:
+        sc = graphdef_scope(u["name"])
+        wanted.update([sc + "/conv2d_params", sc + "/batchnorm/beta", sc + "/batchnorm/moving_mean",
+                       sc + "/batchnorm/moving_variance"])
+    consts = parse_graphdef_consts(buf, wanted)
+    out = {}
+    for u in specs:
+        sc = graphdef_scope(u["name"])
+        try:
+            W = consts[sc + "/conv2d_params"]
+            beta, mean, var = (consts[sc + "/batchnorm/" + k] for k in ("beta", "moving_mean", "moving_variance"))
+        except KeyError as e:
+            raise ValueError("%s: constant %s not found in the graph" % (u["name"], e)) from None
+        want = (u["k"][0], u["k"][1], u["cin"], u["cout"])
+        if tuple(W.shape) != want or any(t.reshape(-1).shape != (u["cout"],) for t in (beta, mean, var)):
+            raise ValueError("%s (%s): kernel %s, expected %s" % (u["name"], sc, tuple(W.shape), want))
+        out[u["name"]] = dict(W=torch.from_numpy(W.copy()), beta=torch.from_numpy(beta.reshape(-1).copy()),
+                              mean=torch.from_numpy(mean.reshape(-1).copy()), var=torch.from_numpy(var.reshape(-1).copy()))
+    return out
+
+
+def load_graphdef(path):
+    """`classify_image_graph_def.pb`, or the inception-2015-12-05.tgz that contains it (fid.py:276-287)."""
+    path = str(path)
+    if path.endswith((".tgz", ".tar.gz")):
+        import tarfile
+        with tarfile.open(path, mode="r") as tf_:
+            buf = tf_.extractfile("classify_image_graph_def.pb").read()
+    else:
+        with open(path, "rb") as f:
+            buf = f.read()
+    return weights_from_graphdef(buf)

@@ -190,7 +190,7 @@ def test_fid_file_helpers_host_side(tmp_path):
     assert batch.dtype == np.uint8 and np.array_equal(batch, imgs)
     with pytest.raises(RuntimeError, match="Invalid path"):
         fid.calculate_fid_given_paths([str(tmp_path / "img"), str(tmp_path / "nope")], None, sess=lambda x: x)
-    with pytest.raises(RuntimeError, match="no converted Inception weights"):
+    with pytest.raises(RuntimeError, match="no Inception model file"):
         fid.check_or_download_inception(str(tmp_path))
     assert fid.check_or_download_inception(None) is None
     np.savez(tmp_path / "stats.npz", mu=np.arange(4.0), sigma=np.eye(4))
@@ -226,3 +226,75 @@ def test_inception_program_matches_the_oracle_table():
             width = total
             widths.append(width)
     assert widths == [256, 288, 288, 768, 768, 768, 768, 768, 1280, 2048, 2048]
+
+
+def _pb_varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def _pb_len(field, payload):
+    return _pb_varint((field << 3) | 2) + _pb_varint(len(payload)) + payload
+
+
+def _pb_const_node(name, arr, how="content", dtype=1):
+    """A serialized NodeDef{name, op='Const', attr{'value': AttrValue{tensor}}} as TensorFlow writes it."""
+    import numpy as np
+    shape = b"".join(_pb_len(2, _pb_varint((1 << 3) | 0) + _pb_varint(d)) for d in arr.shape)
+    tensor = _pb_varint((1 << 3) | 0) + _pb_varint(dtype) + _pb_len(2, shape)
+    flat = np.ascontiguousarray(arr, dtype="<f4").reshape(-1)
+    if how == "content":
+        tensor += _pb_len(4, flat.tobytes())
+    elif how == "packed":
+        tensor += _pb_len(5, flat.tobytes())
+    elif how == "fill":                                        # one float_val standing for a constant-filled tensor
+        tensor += _pb_varint((5 << 3) | 5) + flat[:1].tobytes()
+    attr = _pb_len(5, _pb_len(1, b"value") + _pb_len(2, _pb_len(8, tensor)))
+    dt_attr = _pb_len(5, _pb_len(1, b"dtype") + _pb_len(2, _pb_varint((6 << 3) | 0) + _pb_varint(dtype)))
+    return _pb_len(1, _pb_len(1, name.encode()) + _pb_len(2, b"Const") + dt_attr + attr)
+
+
+def test_inception_weights_from_the_reference_graphdef_format():
+    """fid.py:36-42 loads classify_image_graph_def.pb through TensorFlow; here the same file is read by a minimal
+    protobuf wire parser.  A synthetic GraphDef with the 2015 graph's scopes and real kernel shapes round-trips."""
+    import numpy as np
+    from littlegan_b200 import inception as I
+    nodes, want = [], {}
+    for i, u in enumerate(I.unit_specs()):
+        sc = I.graphdef_scope(u["name"])
+        kh, kw = u["k"]
+        W = np.full((kh, kw, u["cin"], u["cout"]), 0.001 * (i + 1), np.float32)
+        W[0, 0, 0, :] = np.arange(u["cout"], dtype=np.float32)
+        beta = np.linspace(-1, 1, u["cout"]).astype(np.float32)
+        mean = np.full(u["cout"], 0.25 * (i % 5), np.float32)
+        var = np.linspace(0.5, 1.5, u["cout"]).astype(np.float32)
+        want[u["name"]] = (W, beta, mean, var)
+        nodes.append(_pb_const_node(sc + "/conv2d_params", W))
+        nodes.append(_pb_const_node(sc + "/batchnorm/beta", beta, how="packed"))
+        nodes.append(_pb_const_node(sc + "/batchnorm/moving_mean", mean, how="fill"))
+        nodes.append(_pb_const_node(sc + "/batchnorm/moving_variance", var))
+        nodes.append(_pb_const_node(sc + "/batchnorm/gamma", np.ones(u["cout"], np.float32)))     # present, unused
+        nodes.append(_pb_len(1, _pb_len(1, (sc + "/Conv2D").encode()) + _pb_len(2, b"Conv2D")
+                             + _pb_len(3, (sc + "/conv2d_params").encode())))                     # a non-Const node
+    nodes.append(_pb_const_node("pool_3/_reshape/shape", np.array([1, 2048], np.float32), dtype=3))   # int32: skipped
+    graph = b"".join(nodes) + _pb_len(4, _pb_varint((1 << 3) | 0) + _pb_varint(21))                # versions field
+    weights = I.weights_from_graphdef(graph)
+    assert len(weights) == 94
+    for name, (W, beta, mean, var) in want.items():
+        w = weights[name]
+        assert np.array_equal(w["W"].numpy(), W) and np.array_equal(w["beta"].numpy(), beta)
+        assert np.array_equal(w["mean"].numpy(), mean) and np.array_equal(w["var"].numpy(), var)
+        assert "gamma" not in w
+    consts = I.parse_graphdef_consts(graph)
+    assert "pool_3/_reshape/shape" not in consts and "conv/Conv2D" not in consts
+    # a kernel of the wrong shape under a unit's scope is an error, as is a missing constant
+    bad = _pb_const_node("conv/conv2d_params", np.zeros((3, 3, 3, 16), np.float32)) + b"".join(nodes[1:])
+    with pytest.raises(ValueError, match="Conv2d_1a_3x3"):
+        I.weights_from_graphdef(bad)
+    with pytest.raises(ValueError, match="not found"):
+        I.weights_from_graphdef(b"".join(nodes[6:]))
