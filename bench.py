@@ -35,6 +35,9 @@ E_MAC, DC_MAC = 596.4e6, 825.8e6
 # The reference step is 7 Dc + 13 E conv passes per image (27.07 GFLOP); this implementation EXECUTES 12 E: the
 # encoder pass over `fake` that the reference computes twice (D(fake) and adjuster([real ; fake])) runs once.
 STEP_FLOP_PER_IMG = 2 * (7 * DC_MAC + 12 * E_MAC)      # 25.88 GFLOP executed, adjuster on
+# DRAM bytes of one captured step at batch 64 (ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the
+# launches of one replay); None until profiles/ holds the capture it comes from
+STEP_DRAM_BYTES = None
 
 
 def _peaks():
@@ -114,22 +117,34 @@ def cpu_oracle_rate(sample_batch, steps, warmup):
     return sample_batch * steps / dt, dt / steps * 1e3, cores
 
 
+def _config(world):
+    """The workload both arms are quoted on (BASELINE.json configs[1]; at 8 GPUs configs[2]'s global batch 512)."""
+    return {"workload": "littlegan-128 full train step (G+D+Adjuster), cond 40, batch 64/GPU",
+            "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"}
+
+
 def run_reference(a):
+    """The reference's CPU path (its restatement: TF 1.15 is not installable) on rank 0's host cores, on the
+    product arm's config.  Every step is one REAL 64-image per-GPU batch - the whole global batch at N = 1, a
+    1/N sample of it at N > 1 (one host, one process: the CPU arm has no data parallelism to offer)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 16
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
+    sample = PER_GPU_BATCH
     rate, ms, cores = cpu_oracle_rate(sample, a.steps, a.warmup)
     unit = "images/sec"
     line = {
         "impl": "reference", "metric": "LittleGAN G+D+A train step throughput @128x128", "value": rate,
         "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "littlegan-128 full train step (G+D+Adjuster), cond 40",
-                   "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * a.gpus},
+        "config": _config(world),
         "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port",
-                         "sample": "full train step on a %d-image slice of the batch, oracle restatement in "
-                                   "PyTorch-CPU fp32 (TF 1.15 not installable)" % sample},
+                         "sample": "every step = one full train step on a %d-image batch (the per-GPU batch of the "
+                                   "config%s) on ONE host process using all %d cores; oracle restatement in "
+                                   "PyTorch-CPU fp32 (TF 1.15 not installable)" % (
+                                       sample, "" if world == 1 else ": 1/%d of the global batch" % world, cores)},
         "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -173,7 +188,187 @@ def dominant_kernel_roofline(peaks):
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
             # (profiles/r1_ncu_tc_dgrad_dec2.txt): 18.69 MB + 0.12 MB; algorithmic input bytes 18.4 MB, the
             # 33.6 MB output stays in the 126 MB L2 for the kernel's lifetime
-            "traffic": 18.8e6, "traffic_unit": "bytes/launch"}
+            "traffic": 18.8e6, "traffic_unit": "bytes/launch",
+            "traffic_source": "profiles/r1_ncu_tc_dgrad_dec2.txt (ncu --set full of this launch; not re-measured "
+                              "by this run)"}
+
+
+def _time_launch(fn, flush, reps=10, warm=3):
+    """Average CUDA-event time (ms) of fn() on the current stream, L2 evicted before every launch."""
+    import torch
+    tot = 0.0
+    for i in range(warm + reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        if i >= warm:
+            tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def hbm_rooflines(peaks, trainer):
+    """The bandwidth-bound kernels of the step, each timed ALONE at its largest step geometry (decoder layer 4 of
+    the adjuster's 2B batch: [128,128,128,32] bf16 = 134 MB per map; the generator's Adam range), algorithmic
+    bytes (SURVEY 8 d) / launch time against the measured HBM copy bandwidth."""
+    import torch
+    from littlegan_b200 import kernels as K
+    N, H, C = 2 * PER_GPU_BATCH, 128, 32
+    M = H * H * C
+    bf = torch.bfloat16
+    z = torch.randn(N, H, H, C, device="cuda").to(bf)
+    g = torch.randn(N, H, H, C, device="cuda").to(bf)
+    out = torch.empty_like(z)
+    gamma, beta = torch.ones(1, device="cuda"), torch.zeros(1, device="cuda")
+    dgamma, dbeta = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    dbias = torch.zeros(C, device="cuda")
+    zf = z.float().reshape(N, -1)
+    stats = torch.stack([zf.sum(1), (zf * zf).sum(1)], 1).double().contiguous()
+    del zf
+    red = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    map_bytes = N * M * 2
+    res = []
+
+    def add(name, ms, nbytes, what):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm"], "ms_per_launch": ms, "algorithmic_bytes": nbytes, "what": what})
+
+    ms = _time_launch(lambda: K.instnorm_act_fwd(z, stats, gamma, beta, None, out, 1e-3, 1.0, 0.3), flush)
+    add("instnorm_fwd (IN apply + LeakyReLU)", ms, 2 * map_bytes, "1 read + 1 write of a [128,128,128,32] bf16 map")
+    fuse = K.bias_grad_fusable(z)
+
+    def bwd_two_pass():
+        red.zero_()
+        K.instnorm_act_bwd(g, z, stats, gamma, beta, red, out, dgamma, dbeta, 1e-3, 1.0, 0.3, dy_ready=False,
+                           dbias=dbias if fuse else None)
+    ms = _time_launch(bwd_two_pass, flush)
+    add("instnorm_bwd_reduce + instnorm_bwd_apply", ms, 5 * map_bytes,
+        "reduce: read g, z; apply: read g, z, write dz (+ fused d bias / d gamma / d beta)")
+    red.normal_()
+    ms = _time_launch(lambda: K.instnorm_act_bwd(g, z, stats, gamma, beta, red, out, dgamma, dbeta, 1e-3, 1.0, 0.3,
+                                                 dy_ready=True, dbias=dbias if fuse else None), flush)
+    add("instnorm_bwd_apply<dy_ready> (pass 1 fused into the producing conv)", ms, 3 * map_bytes,
+        "read dy, z, write dz (+ fused d bias / d gamma / d beta)")
+    lo, hi = trainer._range("Generator", 11)
+    n = hi - lo
+    P, G, Mm, V = (torch.randn(n, device="cuda") for _ in range(4))
+    V.abs_()
+    st = torch.zeros(4, dtype=torch.float64, device="cuda")
+    K.adam_advance(st, 5e-5, 0.5, 0.9)
+    ms = _time_launch(lambda: K.adam_apply(P, G, Mm, V, st, 0.5, 0.9, 1e-8, 0.0), flush)
+    add("adam_apply (generator range, %d params)" % n, ms, 28 * n, "read g, p, m, v; write p, m, v (fp32)")
+    return res
+
+
+def sustained_run(graph, seconds, B, world, local, rank):
+    """Replays the captured step back to back for >= `seconds` with the clock sampler on: the throughput a long
+    training run sees (power / clock steady state), next to the short timed region of `value`."""
+    import torch
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+        sampler.rows.clear()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    n = 0
+    e0.record()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(50):
+            graph.replay()
+        n += 50
+        torch.cuda.current_stream().synchronize() if n % 500 == 0 else None
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    clocks = sampler.stop() if rank == 0 else None
+    power = None
+    if rank == 0:
+        pw = []
+        for r in sampler.rows:
+            try:
+                pw.append(float(r[2]))
+            except Exception:
+                pass
+        pw.sort()
+        power = pw[len(pw) // 2] if pw else None
+    return {"seconds": ms * n / 1e3, "steps": n, "ms_per_step": ms, "images_per_sec_per_gpu": B / (ms * 1e-3),
+            "clocks": clocks, "power_w_median": power}
+
+
+def predict_bench(trainer, world, reps=5):
+    """configs[3]: EagerTrainer.predict (eager_trainer.py:265-298), batch 256 per GPU, HOST numpy inputs, wall
+    clock per call (every call ends in a device->host read of the MSE scalars and the x100 integer lists)."""
+    import numpy as np
+    import torch
+    B = 256
+    a = trainer.args
+    rng = np.random.default_rng(0)
+    noise = rng.standard_normal((B, a.noise_dim)).astype(np.float32)
+    cond = (0.96 * rng.choice([-1.0, 1.0], size=(B, a.cond_dim)) + 0.02).astype(np.float32)
+    image = rng.uniform(-1, 1, size=(B, 128, 128, 3)).astype(np.float32)
+    for _ in range(2):
+        trainer.predict(noise, cond, image)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        trainer.predict(noise, cond, image)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    return ms, B
+
+
+def fid50k_bench(world, rank):
+    """configs[4]: FID statistics of 50 000 synthetic 128x128 images sharded over the ranks: host image bytes ->
+    Inception pool_3 (random weights: the 2015 model file is an external download) -> streaming (n, S1, S2) -> one
+    SUM all-reduce -> mu / sigma -> Frechet distance against a second statistics pair on rank 0.  Each rank cycles a
+    pool of <= 5000 host images (bounded host memory and generation time); every image crosses PCIe every time."""
+    import numpy as np
+    import torch
+    from littlegan_b200 import fid
+    from littlegan_b200.inception import InceptionPool3
+    total = 50000
+    per = total // world
+    pool_n = min(per, 5000)
+    pool = np.random.default_rng(100 + rank).integers(0, 256, (pool_n, 128, 128, 3), dtype=np.uint8)
+    net = InceptionPool3(seed=0, dtype="bf16")
+    acc = fid.FeatureStatistics(2048)
+    for feats in fid.get_activations(pool[:300], net, 100):          # warm-up (kernels, pinned staging, NCCL)
+        acc.update(feats)
+    acc.finalize()
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    t0 = time.perf_counter()
+    acc = fid.FeatureStatistics(2048)
+    done = 0
+    while done < per:
+        n = min(pool_n, per - done)
+        for feats in fid.get_activations(pool[:n], net, 100):
+            acc.update(feats)
+        done += n
+    mu, sigma = acc.finalize()
+    torch.cuda.synchronize()
+    t_stats = time.perf_counter() - t0
+    d = None
+    t_dist = 0.0
+    if rank == 0:
+        mu2 = mu * 1.01 + 0.01
+        sigma2 = sigma * 1.1 + torch.eye(2048, dtype=torch.float64, device=sigma.device) * 1e-3
+        fid.calculate_frechet_distance(mu, sigma, mu2, sigma2)       # warm-up
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        d = fid.calculate_frechet_distance(mu, sigma, mu2, sigma2)
+        t_dist = time.perf_counter() - t1
+    return {"images": per * world, "per_rank": per, "features_statistics_s": t_stats, "frechet_distance_s": t_dist,
+            "images_per_sec": per * world / t_stats, "distance": d,
+            "note": "wall clock incl. host->device image bytes; Inception on random weights"}
 
 
 def run_product(a):
@@ -248,6 +443,33 @@ def run_product(a):
     clocks = sampler.stop() if rank == 0 else None
     assert all(x == x for x in losses), "non-finite loss"
 
+    # ---- extras (none of them inside the timed regions above): sustained replay, configs[3] predict, configs[4] FID
+    extra = {}
+    if not a.no_extras:
+        sus = sustained_run(graph, a.sustain_seconds, B, world, local, rank)
+        ms_pred, b_pred = predict_bench(trainer, world)
+        fidr = fid50k_bench(world, rank)
+        tt = torch.tensor([sus["ms_per_step"], ms_pred, fidr["features_statistics_s"]], dtype=torch.float64,
+                          device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sus["ms_per_step"] = float(tt[0])
+        sus["images_per_sec"] = B * world / (float(tt[0]) * 1e-3)
+        fidr["features_statistics_s"] = float(tt[2])
+        fidr["images_per_sec"] = fidr["images"] / float(tt[2])
+        extra = {"sustained": sus,
+                 "predict": {"workload": "configs[3]: predict, batch 256/GPU, host numpy inputs", "ms_per_call": float(tt[1]),
+                             "images_per_sec": b_pred * world / (float(tt[1]) * 1e-3), "per_gpu_batch": b_pred},
+                 "fid50k": fidr}
+    # data-parallel invariant: the replicas must hold bit-identical parameters after any number of steps
+    if world > 1:
+        ref = trainer.P.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([1.0 if torch.equal(ref, trainer.P) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        assert float(same) == 1.0, "parameter replicas diverged across ranks"
+        extra["replicas_bit_identical"] = True
+
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -263,9 +485,7 @@ def run_product(a):
             "metric": "LittleGAN G+D+A train step throughput @128x128", "value": value, "unit": "images/sec",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "littlegan-128 full train step (G+D+Adjuster), cond 40, batch 64/GPU",
-                       "per_gpu_batch": B, "global_batch": gb, "parallelism": "dp%d" % world,
-                       "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"},
+            "config": _config(world),
             "clocks": clocks,
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/sec", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
@@ -275,12 +495,18 @@ def run_product(a):
         }
         if world == 1:
             line["roofline"] = dominant_kernel_roofline(peaks)
+            if not a.no_extras:
+                extra["roofline_hbm"] = hbm_rooflines(peaks, trainer)
+                # sum of dram__bytes_read + dram__bytes_write over one replay of the captured step (ncu, batch 64);
+                # an offline number: profiles/ holds the launch list it was summed from
+                extra["step_dram_bytes"] = STEP_DRAM_BYTES
             if not a.no_cpu_baseline:
                 rate, ms, cores = cpu_oracle_rate(16, 4, 1)
                 line["cpu_baseline"] = {
                     "value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                     "sample": "4 full train steps on a 16-image batch (configs[0]), oracle restatement in "
                               "PyTorch-CPU fp32 (TF 1.15 not installable)"}
+        line["extra_keys"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         # Captured graphs hold NCCL work; tearing the communicator down underneath them can block.
@@ -299,6 +525,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained / predict / fid50k / HBM-roofline extras")
+    ap.add_argument("--sustain-seconds", type=float, default=5.0)
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

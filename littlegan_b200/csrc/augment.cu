@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(AT) augment_apply_kernel(const float* __restri
     // the step counter advances here: every thread takes the step from params[3], which pass 1 wrote
     if (gid == 0) state[1] += 1ull;
     curandStatePhilox4_32_10_t st;
-    // subsequences below 2^32 belong to the per-image draws of pass 1
-    curand_init(state[0], (1ull << 32) + (unsigned long long)gid, 3ull * step, &st);
+    // subsequences below 2^32 belong to the per-image draws of pass 1.  The offset counts 32-bit Philox outputs:
+    // a thread consumes 3 x curand_normal4 = 12 of them per step, so step k owns outputs [12k, 12k + 12)
+    curand_init(state[0], (1ull << 32) + (unsigned long long)gid, 12ull * step, &st);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const float4 g4 = curand_normal4(&st);

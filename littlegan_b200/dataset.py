@@ -175,7 +175,13 @@ class DevicePrefetcher:
     """Wraps an iterator of pinned host batches: the host->device copy of the next batches is
     issued on a side stream while the current step computes (the role of tf.data's prefetch,
     dataset.py:23).  get_next() returns CUDA tensors and makes the consumer stream wait for their
-    copy; a buffer is recycled only after the consumer has read it."""
+    copy.
+
+    Buffer recycling contract: the consumer must have QUEUED its reads of a batch on the stream that was
+    current at get_next() before the second-next get_next() call (`_train_step` draws two batches and then
+    reads both, eager_trainer.py:120-121).  The `consumed` event of a batch is therefore recorded one call
+    late - at the start of the second get_next() after the one that handed it out - and the copy that reuses
+    its slot (depth + 2 slots: issued at the earliest in that same call, after the record) waits for it."""
 
     def __init__(self, iterator, depth=4):
         self.it = iterator
@@ -185,7 +191,7 @@ class DevicePrefetcher:
         self.bufs = None
         self.slot = 0
         self.done = False
-        self._prev = None         # consumed-event of the buffer handed out by the previous get_next
+        self._handed = []         # consumed-events of the batches handed out by the last two get_next calls
         for _ in range(depth):
             self._issue()
 
@@ -215,13 +221,13 @@ class DevicePrefetcher:
 
     def get_next(self):
         cur = torch.cuda.current_stream()
-        if self._prev is not None:
-            self._prev.record(cur)              # the consumer's reads of the previous buffer are queued by now
-            self._prev = None
+        # the batch handed out two calls ago: its reads are queued by now (see the class docstring)
+        while len(self._handed) >= 2:
+            self._handed.pop(0).record(cur)
         if not self.ring:
             raise OutOfRangeError()
         ev, dimg, dcond, consumed = self.ring.pop(0)
         cur.wait_event(ev)
-        self._prev = consumed
+        self._handed.append(consumed)
         self._issue()
         return dimg, dcond

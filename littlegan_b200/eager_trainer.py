@@ -116,6 +116,9 @@ class EagerTrainer:
         self._chain_streams = {}
         self._rb, self._rb_count = None, 0
         self._aug_state = None
+        # config key `debug_taps` (tests): keep every per-layer activation of the last step in self.taps (the
+        # references keep the buffers out of the allocator's reuse; the arithmetic and the launches are unchanged)
+        self.taps = {} if getattr(args, "debug_taps", False) else None
         self.test_noise = self.test_cond = self.test_image = None
         if getattr(args, "result_dir", None) and getattr(args, "init_dirs", False):
             self._init_dir()
@@ -200,6 +203,10 @@ class EagerTrainer:
     def adjuster_loss(self, cond_ori, cond_disc, pr_disc, image_ori, image_adj):
         """eager_trainer.py:98-102."""
         return self.generator_loss(cond_ori, cond_disc, pr_disc, image_ori, image_adj)
+
+    def _tap(self, **named):
+        if self.taps is not None:
+            self.taps.update(named)
 
     # ------------------------------------------------------------------ the step
     def _alloc_static(self):
@@ -298,6 +305,7 @@ class EagerTrainer:
             outs3, ectx3 = E.encoder_forward(rt, D.encoder, enc_in)
         outs = [o[off:] for o in outs3]
         ectx = [(x[off:], z[off:], st[off:], None if xp is None else xp[off:]) for (x, z, st, xp) in ectx3]
+        self._tap(enc_off=off, enc=outs3, g_head=g_dctx[0][0], g_dec=[c[0] for c in g_dctx[1:]] + [g_x4], fake=fake)
 
         # The step is three chains that depend only on the forward pass and on the (read-only until Adam)
         # weights: the D-loss backward, the G-loss backward and the whole adjuster sub-step.  They run on
@@ -314,6 +322,7 @@ class EagerTrainer:
                 self._adjuster_chain(S, batch_no, [(o[:B], o[2 * B:]) for o in outs3])
 
         pr, c = E.disc_heads_forward(rt, D, outs[3])              # rows [:B] new_image, [B:] fake
+        self._tap(pr=pr, c=c)
 
         # ---- losses + gradients w.r.t. the logits (eager_trainer.py:139-140)
         dl_pr_d = rt.empty(2 * B, 1, dtype=f32)
@@ -337,6 +346,7 @@ class EagerTrainer:
         ectx_f = [(x[B:], z[B:], st[B:], None) for (x, z, st, _) in ectx]
         g4 = E.disc_heads_backward(rt, D, outs[3][B:], dl_pr_g, dl_c_g, wgrad=False)
         g_img = E.encoder_backward(rt, D.encoder, ectx_f, g4, wgrad=False, input_grad=True)
+        self._tap(g_fake_via_D=g_img)
         dpre = torch.empty_like(fake)
         K.l1_tanh_bwd(fake, S["img2"], g_img, dpre, a.l1_lambda, l_gen)
         g = E.generator_tail_backward(rt, G.decoder, G.conv, g_dctx, g_x4, dpre, wgrad=True)
@@ -388,6 +398,8 @@ class EagerTrainer:
         K.bce_sigmoid_multi([(apr, soft(1.0), 1.0, l_adj, dl_pr_a), (ac, S["acond_t"], 1.0, l_adj, dl_c_a)])
         g4 = E.disc_heads_backward(rt, D, outs2[3], dl_pr_a, dl_c_a, wgrad=False)
         g_img = E.encoder_backward(rt, D.encoder, ectx2, g4, wgrad=False, input_grad=True)
+        self._tap(a_head=a_dctx[0][0], a_dec=[c[0] for c in a_dctx[1:]] + [a_x4], adj=adj, da_enc=outs2, da_pr=apr,
+                  da_c=ac, g_adj_via_D=g_img)
         dpre = torch.empty_like(adj)
         K.l1_tanh_bwd(adj, S["aimg_t"], g_img, dpre, a.l1_lambda, l_adj)
         g = E.generator_tail_backward(rt, A.decoder, A.conv, a_dctx, a_x4, dpre, wgrad=False)
@@ -395,26 +407,46 @@ class EagerTrainer:
         S["adj"] = adj
         self._reduce_async("Adjuster", batch_no)
 
+    def _bucket(self, name, batch_no, part=None):
+        """Flat [lo, hi) of one gradient bucket: the optimiser's active range (`_range`), optionally cut down to
+        the tensors [part[0], part[1]) of that optimiser; None when the cut is empty."""
+        lo, hi = self._range(name, batch_no)
+        if part is not None:
+            offs = self._offsets[name]
+            lo, hi = max(lo, offs[part[0]]), min(hi, offs[part[1]])
+        return (lo, hi) if lo < hi else None
+
+    @staticmethod
+    def _all_reduce_mean(dist, buf):
+        """Average `buf` over the ranks in place (NCCL: one AVG all-reduce; gloo has no AVG: SUM, then scale)."""
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            buf.div_(dist.get_world_size())
+
     def _reduce_async(self, name, batch_no, part=None):
         """Data parallel: average this optimiser's (active range of the) flat gradient arena over the
         ranks on a side stream, so that NCCL runs under the remaining backward work; the ranges of
         the three optimisers are disjoint and the main stream joins before the first Adam.
         part = (first, last+1) tensor indices of the optimiser: reduce only that bucket of the range (the
-        generator's decoder gradients are complete while its dense-layer gradients are still being computed)."""
+        generator's decoder gradients are complete while its dense-layer gradients are still being computed).
+        Host arenas (the gloo protocol tests): the same bucket arithmetic, reduced synchronously."""
         dist = _dist()
         if dist is None:
             return
+        rng = self._bucket(name, batch_no, part)
+        if rng is None:
+            return
+        buf = self.Gd[rng[0]:rng[1]]
+        if not buf.is_cuda:
+            self._all_reduce_mean(dist, buf)
+            return
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream()
-        lo, hi = self._range(name, batch_no)
-        if part is not None:
-            offs = self._offsets[name]
-            lo, hi = max(lo, offs[part[0]]), min(hi, offs[part[1]])
-            if lo >= hi:
-                return
         self._comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._comm_stream):
-            dist.all_reduce(self.Gd[lo:hi], op=dist.ReduceOp.AVG)
+            self._all_reduce_mean(dist, buf)
 
     def _variant(self, batch_no):
         a = self.args
@@ -443,9 +475,11 @@ class EagerTrainer:
             with torch.cuda.graph(g, pool=self._pool):
                 self._step_body(S, adj_on, batch_no, aug)
             K.note_capture(K.launch_count() - n0)
-            self._graphs[key] = (g, S["adj"])
-        g, adj = self._graphs[key]
+            self._graphs[key] = (g, S["adj"], None if self.taps is None else dict(self.taps))
+        g, adj, taps = self._graphs[key]
         S["adj"] = adj
+        if taps is not None:
+            self.taps = dict(taps)              # the buffers THIS variant's graph writes
         g.replay()
 
     def _to_static(self, dst, src):

@@ -166,12 +166,19 @@ def load_image_batch(files):
     return np.stack(out)
 
 
-def create_inception_graph(pth=None, dtype="bf16"):
+def create_inception_graph(pth=None, dtype="bf16", allow_random=False):
     """fid.py:36-42 stand-in: the pool_3 feature extractor.  `pth`: the reference's own model file
     (`classify_image_graph_def.pb` or the .tgz around it - read without TensorFlow, `inception.load_graphdef`), or a
-    converted `.npz` (`inception.load_npz`); None = random weights."""
+    converted `.npz` (`inception.load_npz`).  Without a model file this raises: an 'FID' from a randomly
+    initialised network is a plausible-looking but meaningless number.  `allow_random=True` (throughput runs and
+    tests only) builds the network on random weights."""
     from .inception import InceptionPool3, load_graphdef, load_npz
     if pth is None:
+        if not allow_random:
+            raise RuntimeError("no Inception model file given (the reference downloads inception-2015-12-05.tgz, "
+                               "fid.py:273-288; there is no network here): pass the path of "
+                               "classify_image_graph_def.pb / the .tgz / a converted .npz, or allow_random=True "
+                               "for a throughput run on random weights")
         weights = None
     elif str(pth).endswith(".npz"):
         weights = load_npz(str(pth))

@@ -31,6 +31,31 @@ def launch_count_of_last_capture():
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
+# which kernel family each conv launch took: ("fprop"|"dgrad"|"wgrad", "tc"|"rows"|"simt") -> launches
+_PATHS = {}
+_WARNED = set()
+
+
+def path_counts(reset=False):
+    """Conv launches so far by (operation, kernel family); tests assert that a bf16 run never took "simt"."""
+    out = dict(_PATHS)
+    if reset:
+        _PATHS.clear()
+    return out
+
+
+def _note_path(op, family, t, geom):
+    key = (op, family)
+    _PATHS[key] = _PATHS.get(key, 0) + 1
+    if family == "simt" and t.dtype == torch.bfloat16 and (op, geom) not in _WARNED:
+        # bf16 maps are the tensor-core mode: a geometry the tcgen05 planner rejects still computes correctly on
+        # the fp32-FMA kernel, but ~10x slower - say so once per geometry instead of silently
+        _WARNED.add((op, geom))
+        import warnings
+        warnings.warn("littlegan_b200: %s with geometry (N,Hb,Wb,A,B,stride)=%s has no tcgen05 form (channel counts "
+                      "must be multiples of 16 and the maps large enough for TMA tiles); running it on the much "
+                      "slower SIMT fp32-FMA kernel" % (op, geom), RuntimeWarning, stacklevel=3)
+
 
 def _p(t):
     return None if t is None else t.data_ptr()
@@ -91,6 +116,7 @@ def conv2d_fprop(big, W, bias, out, stats, stride, wpack=None, use_tc=False, nor
     _cuda(big, W, bias, out, stats, wpack)
     N, Hb, Wb, A = big.shape
     B = out.shape[3]
+    _note_path("fprop", "tc" if use_tc else "simt", big, (N, Hb, Wb, A, B, stride))
     check(_lib.load().lg_conv2d_fprop(_p(big), _p(W), _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
                                       stride, dt(big), int(use_tc), _nb(norm_bwd), _st()), "lg_conv2d_fprop")
     return out
@@ -118,6 +144,7 @@ def conv2d_fprop_rows(big, wpack, bias, out, stats, stride, A, norm_bwd=None):
     _cuda(big, wpack, bias, out, stats)
     N, Hb, Wb, A_big = big.shape
     B = out.shape[3]
+    _note_path("fprop", "rows", big, (N, Hb, Wb, A, B, stride))
     check(_lib.load().lg_conv2d_fprop_rows(_p(big), A_big, _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
                                            stride, _nb(norm_bwd), _st()), "lg_conv2d_fprop_rows")
     return out
@@ -128,6 +155,7 @@ def conv2d_dgrad(small, W, bias, out, stats, stride, act=ACT_NONE, wpack=None, u
     _cuda(small, W, bias, out, stats, wpack)
     N, Hb, Wb, A = out.shape
     B = small.shape[3]
+    _note_path("dgrad", "tc" if use_tc else "simt", small, (N, Hb, Wb, A, B, stride))
     check(_lib.load().lg_conv2d_dgrad(_p(small), _p(W), _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
                                       stride, act, dt(small), int(use_tc), _nb(norm_bwd), _st()), "lg_conv2d_dgrad")
     return out
@@ -154,6 +182,7 @@ def conv2d_dgrad_rows(small, wpack, bias, out, stats, stride):
     _cuda(small, wpack, bias, out, stats)
     N, Hb, Wb, A = out.shape
     B = small.shape[3]
+    _note_path("dgrad", "rows", small, (N, Hb, Wb, A, B, stride))
     check(_lib.load().lg_conv2d_dgrad_rows(_p(small), _p(wpack), _p(bias), _p(out), _p(stats), N, Hb, Wb, A, B,
                                            stride, _st()), "lg_conv2d_dgrad_rows")
     return out
@@ -168,6 +197,7 @@ def conv2d_dgrad_rgb(small, W, bias, out, out_pad8, stats, stride, act=ACT_NONE)
     _cuda(small, W, bias, out, out_pad8, stats)
     N, Hb, Wb, A = out.shape
     B = small.shape[3]
+    _note_path("dgrad", "rows", small, (N, Hb, Wb, A, B, stride))
     check(_lib.load().lg_conv2d_dgrad_rgb(_p(small), _p(W), _p(bias), _p(out), _p(out_pad8), _p(stats), N, Hb, Wb,
                                           A, B, stride, act, _st()), "lg_conv2d_dgrad_rgb")
     return out
@@ -178,6 +208,7 @@ def conv2d_wgrad(big, small, dW, stride, use_tc=False):
     _cuda(big, small, dW)
     N, Hb, Wb, A = big.shape
     B = small.shape[3]
+    _note_path("wgrad", "tc" if use_tc else "simt", big, (N, Hb, Wb, A, B, stride))
     check(_lib.load().lg_conv2d_wgrad(_p(big), _p(small), _p(dW), N, Hb, Wb, A, B, stride, dt(big), int(use_tc),
                                       _st()), "lg_conv2d_wgrad")
 
@@ -187,6 +218,7 @@ def conv2d_wgrad_padded(big_padded, small, dW, stride):
     _cuda(big_padded, small, dW)
     N, Hb, Wb, A_big = big_padded.shape
     A, B = dW.shape[2], dW.shape[3]
+    _note_path("wgrad", "tc", big_padded, (N, Hb, Wb, A, B, stride))
     check(_lib.load().lg_conv2d_wgrad_padded(_p(big_padded), _p(small), _p(dW), N, Hb, Wb, A_big, A, B, stride,
                                              _st()), "lg_conv2d_wgrad_padded")
 

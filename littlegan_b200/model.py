@@ -38,10 +38,22 @@ def _glorot(shape, fan_in, fan_out):
     return w.to(torch.float32).to(_device())
 
 
+def _check_geometry(kernel_size, strides):
+    """Every CUDA path of the conv family is written for the reference's 5x5 kernels (sample.config.json:14;
+    the C-ABI carries no kernel-size argument) at stride 1 or 2: refuse anything else up front instead of
+    letting a kernel read 25 taps out of a smaller buffer."""
+    if int(kernel_size) != 5:
+        raise ValueError("littlegan_b200 implements kernel_size 5 only (got %r): the CUDA kernels and the C-ABI "
+                         "are specialised for the reference's 5x5 convolutions" % (kernel_size,))
+    if int(strides) not in (1, 2):
+        raise ValueError("littlegan_b200 implements strides 1 and 2 only (got %r)" % (strides,))
+
+
 class Conv2D:
     """tf.layers.Conv2D(filters, k, strides, 'same'): kernel [k,k,in,out], bias [out]."""
 
     def __init__(self, in_channels, filters, kernel_size, strides):
+        _check_geometry(kernel_size, strides)
         k = kernel_size
         self.filters, self.kernel_size, self.strides = filters, k, strides
         self.kernel = _glorot((k, k, in_channels, filters), k * k * in_channels, k * k * filters)
@@ -59,6 +71,7 @@ class Conv2DTranspose:
     """tf.layers.Conv2DTranspose(filters, k, strides, 'same'): kernel [k,k,out,in], bias [out]."""
 
     def __init__(self, in_channels, filters, kernel_size, strides, activation=None):
+        _check_geometry(kernel_size, strides)
         k = kernel_size
         self.filters, self.kernel_size, self.strides, self.activation = filters, k, strides, activation
         self.kernel = _glorot((k, k, filters, in_channels), k * k * filters, k * k * in_channels)

@@ -158,7 +158,13 @@ def init_weights(args, seed=0, dtype=torch.float32):
 # --------------------------------------------------------------------------- #
 # models (model.py)
 # --------------------------------------------------------------------------- #
-def encoder(args, x, W):
+def _tap(taps, name, x):
+    """Record a per-layer activation for the parity tests (`taps`: dict or None)."""
+    if taps is not None:
+        taps[name] = x.detach()
+
+
+def encoder(args, x, W, taps=None, tag="enc"):
     """Encoder.call (model.py:18-27). W = 16 tensors. Dropout is identity
     (tf.layers.dropout default training=False)."""
     outs = []
@@ -167,11 +173,12 @@ def encoder(args, x, W):
         x = conv2d_same(x, k, b, 2)
         x = instance_norm(x, g, be)
         x = leaky(x, args.leaky_alpha)
+        _tap(taps, "%s%d" % (tag, i + 1), x)
         outs.append(x)
     return outs
 
 
-def decoder(args, x, add, W):
+def decoder(args, x, add, W, taps=None, tag="dec"):
     """Decoder.call (model.py:43-51). W = 16 tensors."""
     for i in range(4):
         if add[i] is not None:
@@ -180,37 +187,42 @@ def decoder(args, x, add, W):
         x = conv2d_transpose_same(x, k, b, 2)
         x = instance_norm(x, g, be)
         x = leaky(x, args.leaky_alpha)
+        _tap(taps, "%s%d" % (tag, i + 1), x)
     return x
 
 
-def discriminator(args, x, WD):
+def discriminator(args, x, WD, taps=None, tag="d_"):
     """Discriminator.call (model.py:66-73) -> (pr [B,1], c [B,cond])."""
-    feats = encoder(args, x, WD[:16])
+    feats = encoder(args, x, WD[:16], taps, tag + "enc")
     f = feats[-1].reshape(feats[-1].shape[0], -1)
     pr = torch.sigmoid(f @ WD[16] + WD[17])
     c = torch.sigmoid(f @ WD[18] + WD[19])
+    _tap(taps, tag + "pr", pr)
+    _tap(taps, tag + "c", c)
     return pr, c
 
 
-def generator(args, noise, cond, WG):
+def generator(args, noise, cond, WG, taps=None, tag="g_"):
     """Generator.call (model.py:90-105)."""
     x = torch.cat([noise, cond], dim=-1) @ WG[0] + WG[1]
     x = leaky(x, args.leaky_alpha)
     x = x.reshape(-1, args.init_dim, args.init_dim, args.conv_filter[0])
     x = instance_norm(x, WG[2], WG[3])
-    x = decoder(args, x, [None] * 4, WG[4:20])
+    _tap(taps, tag + "head", x)
+    x = decoder(args, x, [None] * 4, WG[4:20], taps, tag + "dec")
     return torch.tanh(conv2d_transpose_same(x, WG[20], WG[21], 1))
 
 
-def adjuster(args, image, cond, WD, WG, WA):
+def adjuster(args, image, cond, WD, WG, WA, taps=None, tag="a_"):
     """Adjuster.call (model.py:126-136): shared encoder (D's), own dense+norm,
     shared decoder and final conv (G's), reversed encoder maps as skips."""
-    enc = encoder(args, image, WD[:16])
+    enc = encoder(args, image, WD[:16], taps, tag + "enc")
     c = cond @ WA[0] + WA[1]
     c = leaky(c, args.leaky_alpha)
     c = instance_norm(c, WA[2], WA[3])
     c = c.reshape(-1, args.init_dim, args.init_dim, args.conv_filter[0])
-    x = decoder(args, c, enc[::-1], WG[4:20])
+    _tap(taps, tag + "head", c)
+    x = decoder(args, c, enc[::-1], WG[4:20], taps, tag + "dec")
     return torch.tanh(conv2d_transpose_same(x, WG[20], WG[21], 1))
 
 
@@ -292,9 +304,13 @@ class OracleTrainer:
         return list(range(n))
 
     def train_step(self, batch_no, real_image_1, real_cond_1, real_image_2, real_cond_2,
-                   noise, new_image=None, return_grads=False):
+                   noise, new_image=None, return_grads=False, taps=None):
         """_train_step (eager_trainer.py:115-169) with the random draws
-        (noise, augmented new_image) injected so runs are reproducible."""
+        (noise, augmented new_image) injected so runs are reproducible.
+        `taps`: a dict that receives every per-layer activation of the step (g_*: generator; dr_* / df_*:
+        discriminator on new_image / fake_image; a_*: adjuster; da_*: discriminator on the adjusted images)
+        plus `g_fake_via_D` / `g_adj_via_D`, the gradients of the adversarial + attribute terms of gen_loss /
+        adj_loss with respect to the generated / adjusted images."""
         a, W = self.args, self.W
         cast = lambda t: t.to(self.dtype)
         real_image_1, real_cond_1, real_image_2, real_cond_2, noise = map(
@@ -303,9 +319,12 @@ class OracleTrainer:
         if a.use_gp:
             raise NotImplementedError("GP didn't implemented on eager mode")
 
-        fake_image = generator(a, noise, real_cond_2, W["G"])
-        real_pr, real_c = discriminator(a, new_image, W["D"])
-        fake_pr, fake_c = discriminator(a, fake_image, W["D"])
+        fake_image = generator(a, noise, real_cond_2, W["G"], taps)
+        real_pr, real_c = discriminator(a, new_image, W["D"], taps, "dr_")
+        fake_pr, fake_c = discriminator(a, fake_image, W["D"], taps, "df_")
+        if taps is not None:
+            adv = bce(soft(torch.ones_like(fake_pr)), fake_pr) + bce(real_cond_2, fake_c)
+            taps["g_fake_via_D"] = torch.autograd.grad(adv, fake_image, retain_graph=True)[0].detach()
         disc_loss = discriminator_loss(real_cond_1, real_c, real_pr, fake_pr)
         gen_loss = generator_loss(a, real_cond_2, fake_c, fake_pr, real_image_2, fake_image)
 
@@ -327,8 +346,11 @@ class OracleTrainer:
             adj_target_cond = torch.cat([real_cond_2, real_cond_1], 0)
             adj_input_image = torch.cat([real_image_1, fake_const], 0)
             adj_target_image = torch.cat([real_image_2, real_image_1], 0)
-            adj_image = adjuster(a, adj_input_image, adj_input_cond, W["D"], W["G"], W["A"])
-            adj_pr, adj_c = discriminator(a, adj_image, W["D"])
+            adj_image = adjuster(a, adj_input_image, adj_input_cond, W["D"], W["G"], W["A"], taps)
+            adj_pr, adj_c = discriminator(a, adj_image, W["D"], taps, "da_")
+            if taps is not None:
+                adv = bce(soft(torch.ones_like(adj_pr)), adj_pr) + bce(adj_target_cond, adj_c)
+                taps["g_adj_via_D"] = torch.autograd.grad(adv, adj_image, retain_graph=True)[0].detach()
             adj_loss = adjuster_loss(a, adj_target_cond, adj_c, adj_pr, adj_target_image, adj_image)
             gA = torch.autograd.grad(adj_loss, a_vars)
             self.opt["A"].apply(zip(gA, a_vars))

@@ -298,3 +298,27 @@ def test_inception_weights_from_the_reference_graphdef_format():
         I.weights_from_graphdef(bad)
     with pytest.raises(ValueError, match="not found"):
         I.weights_from_graphdef(b"".join(nodes[6:]))
+
+
+def test_unsupported_kernel_size_fails_fast():
+    """the CUDA kernels and the C-ABI are 5x5-only; any other `kernel_size` must raise at
+    construction instead of reading 25 taps out of a smaller buffer."""
+    from littlegan_b200 import model as M
+    pargs = product_args(small_args())
+    pargs.kernel_size = 3
+    with pytest.raises(ValueError, match="kernel_size 5 only"):
+        M.Encoder(pargs)
+    with pytest.raises(ValueError, match="kernel_size 5 only"):
+        M.Decoder(pargs)
+    with pytest.raises(ValueError):
+        M.Conv2D(8, 8, 5, 3)
+
+
+def test_fid_without_inception_weights_raises():
+    """`calculate_fid_given_paths(paths, None)` is the reference's default call (it downloads the
+    model); here there is no download, and a silently random network would give a meaningless 'FID'."""
+    from littlegan_b200 import fid
+    with pytest.raises(RuntimeError, match="no Inception model file"):
+        fid.create_inception_graph(None)
+    with pytest.raises(RuntimeError, match="no Inception model file"):
+        fid.create_inception_graph(fid.check_or_download_inception(None))

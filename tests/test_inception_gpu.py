@@ -161,10 +161,10 @@ def test_pool3_features_bf16_storage():
     net = InceptionPool3(weights=W, dtype="bf16")
     assert sum(p[3] is not None for p in net.params.values()) == 94          # every unit on tcgen05 (RGB stem padded to 8)
     got = net(img)
-    # 20 units deep with every activation rounded to bf16: errors accumulate beyond the per-layer 2e-2
-    assert rel_err(got, want) < 6e-2
+    # north_star's bf16 tolerance, max-norm relative (measured 4e-3: pool_3 averages 64 positions)
+    assert rel_err(got, want) < 2e-2
     d = (got.double().cpu() - want).norm() / want.norm()
-    assert float(d) < 2e-2
+    assert float(d) < 1e-2
 
 
 def test_fid_statistics_through_the_inception_session():

@@ -691,7 +691,7 @@ def test_augment_draws_and_noise_statistics():
     state = K.augment_state(1234, "cuda")
     params = torch.zeros(4 + 4 * N, device="cuda")
     out = torch.empty(N, H, H, 3, device="cuda")
-    seen, flips_all = [], []
+    seen, flips_all, groups = [], [], []
     for step in range(6):
         K.augment(x, out, params, state=state)
         p = params.cpu()
@@ -709,6 +709,16 @@ def test_augment_draws_and_noise_statistics():
         assert abs(float((nz ** 4).mean() / nz.var() ** 2) - 3.0) < 0.05          # Gaussian kurtosis
         per_img = nz.reshape(N, -1)
         assert float(torch.corrcoef(per_img[:8, :4096])[0, 1:].abs().max()) < 0.08   # independent across images
+        groups.append(nz.reshape(-1, 12)[:65536])               # the 12 values one thread draws for its 4 pixels
+    # independent across steps, at every shift inside a thread's 12 draws (a Philox offset that advances by
+    # fewer than 12 outputs per step would replay values of step k at shifted positions in step k+1 / k+2)
+    for d in (1, 2, 3):
+        for k in range(6 - d):
+            a, b = groups[k], groups[k + d]
+            a = (a - a.mean(0)) / a.std(0)
+            b = (b - b.mean(0)) / b.std(0)
+            cross = (a.T @ b) / a.shape[0]
+            assert float(cross.abs().max()) < 0.03, (k, d, float(cross.abs().max()))
     assert len(set(seen)) == 6
     frac = float(torch.cat(flips_all).mean())
     assert 0.38 < frac < 0.62

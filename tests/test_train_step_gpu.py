@@ -384,3 +384,38 @@ def test_train_step_from_decoded_bytes(tmp_path):
     for a, b in zip(runs[0][:3], runs[1][:3]):
         assert abs(a - b) < 1e-5 * abs(b)
     assert float((runs[0][3] - runs[1][3]).abs().max()) < 1e-5
+
+
+def test_device_prefetcher_keeps_unread_buffers():
+    """`_train_step` draws two batches and only then reads them.  With the consumer stream stalled
+    (the host runs far ahead of the GPU) no host->device copy may land in a buffer whose reads are not queued yet:
+    every batch must arrive intact although the ring has only depth + 2 slots."""
+    from littlegan_b200.dataset import DevicePrefetcher
+    from littlegan_b200.eager_trainer import OutOfRangeError
+
+    class _Numbered:
+        def __init__(self, n):
+            self.n, self.i = n, 0
+            self.pool = [(torch.full((256, 1024), float(k)).pin_memory(), torch.full((4, 5), float(k)).pin_memory())
+                         for k in range(n)]
+
+        def get_next(self):
+            if self.i >= self.n:
+                raise OutOfRangeError()
+            self.i += 1
+            return self.pool[self.i - 1]
+
+    n = 24
+    pf = DevicePrefetcher(_Numbered(n), depth=2)
+    torch.cuda._sleep(int(4e8))                       # ~0.2 s: every read below is queued behind this
+    kept = []
+    for step in range(n // 2):
+        a = pf.get_next()
+        b = pf.get_next()                             # second draw BEFORE the first batch is read
+        kept.append((a[0].clone(), a[1].clone(), b[0].clone(), b[1].clone()))
+    with pytest.raises(OutOfRangeError):
+        pf.get_next()
+    torch.cuda.synchronize()
+    for step, (ai, ac, bi, bc) in enumerate(kept):
+        for t, k in ((ai, 2 * step), (ac, 2 * step), (bi, 2 * step + 1), (bc, 2 * step + 1)):
+            assert float(t.min()) == float(t.max()) == float(k), (step, k, float(t.min()), float(t.max()))
