@@ -158,6 +158,42 @@ def init_weights(args, seed=0, dtype=torch.float32):
 # --------------------------------------------------------------------------- #
 # models (model.py)
 # --------------------------------------------------------------------------- #
+class _RoundBF16(torch.autograd.Function):
+    """Storage emulation for the bf16-mode parity tests: the value AND the gradient that flows back through this
+    point are rounded to bf16 (round-to-nearest-even), as a tensor that the product keeps in HBM as bf16 is - the
+    forward map it stores, and the gradient with respect to it that the backward pass stores."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundGradBF16(torch.autograd.Function):
+    """Identity forward; the gradient is rounded to bf16 (a gradient the product stores without ever storing the
+    forward value at that point, e.g. the pre-tanh gradient of the final layer)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _q(args):
+    """args.store == "bf16": emulate the product's bf16 map storage (see _RoundBF16); default: exact arithmetic."""
+    return _RoundBF16.apply if getattr(args, "store", None) == "bf16" else (lambda x: x)
+
+
+def _qg(args):
+    return _RoundGradBF16.apply if getattr(args, "store", None) == "bf16" else (lambda x: x)
+
+
 def _tap(taps, name, x):
     """Record a per-layer activation for the parity tests (`taps`: dict or None)."""
     if taps is not None:
@@ -168,11 +204,12 @@ def encoder(args, x, W, taps=None, tag="enc"):
     """Encoder.call (model.py:18-27). W = 16 tensors. Dropout is identity
     (tf.layers.dropout default training=False)."""
     outs = []
+    q = _q(args)
     for i in range(4):
         k, b, g, be = W[4 * i:4 * i + 4]
-        x = conv2d_same(x, k, b, 2)
+        x = q(conv2d_same(x, k, b, 2))
         x = instance_norm(x, g, be)
-        x = leaky(x, args.leaky_alpha)
+        x = q(leaky(x, args.leaky_alpha))
         _tap(taps, "%s%d" % (tag, i + 1), x)
         outs.append(x)
     return outs
@@ -180,13 +217,16 @@ def encoder(args, x, W, taps=None, tag="enc"):
 
 def decoder(args, x, add, W, taps=None, tag="dec"):
     """Decoder.call (model.py:43-51). W = 16 tensors."""
+    q = _q(args)
     for i in range(4):
         if add[i] is not None:
-            x = x + add[i]
+            x = q(x + add[i])          # storage emulation: the product stores the SUM (one rounding)
         k, b, g, be = W[4 * i:4 * i + 4]
-        x = conv2d_transpose_same(x, k, b, 2)
+        x = q(conv2d_transpose_same(x, k, b, 2))
         x = instance_norm(x, g, be)
         x = leaky(x, args.leaky_alpha)
+        if i == 3 or add[i + 1] is None:
+            x = q(x)
         _tap(taps, "%s%d" % (tag, i + 1), x)
     return x
 
@@ -207,10 +247,10 @@ def generator(args, noise, cond, WG, taps=None, tag="g_"):
     x = torch.cat([noise, cond], dim=-1) @ WG[0] + WG[1]
     x = leaky(x, args.leaky_alpha)
     x = x.reshape(-1, args.init_dim, args.init_dim, args.conv_filter[0])
-    x = instance_norm(x, WG[2], WG[3])
+    x = _q(args)(instance_norm(x, WG[2], WG[3]))
     _tap(taps, tag + "head", x)
     x = decoder(args, x, [None] * 4, WG[4:20], taps, tag + "dec")
-    return torch.tanh(conv2d_transpose_same(x, WG[20], WG[21], 1))
+    return _q(args)(torch.tanh(_qg(args)(conv2d_transpose_same(x, WG[20], WG[21], 1))))
 
 
 def adjuster(args, image, cond, WD, WG, WA, taps=None, tag="a_"):
@@ -223,7 +263,7 @@ def adjuster(args, image, cond, WD, WG, WA, taps=None, tag="a_"):
     c = c.reshape(-1, args.init_dim, args.init_dim, args.conv_filter[0])
     _tap(taps, tag + "head", c)
     x = decoder(args, c, enc[::-1], WG[4:20], taps, tag + "dec")
-    return torch.tanh(conv2d_transpose_same(x, WG[20], WG[21], 1))
+    return _q(args)(torch.tanh(_qg(args)(conv2d_transpose_same(x, WG[20], WG[21], 1))))
 
 
 # --------------------------------------------------------------------------- #
@@ -363,6 +403,39 @@ class OracleTrainer:
         if return_grads:
             out["grads"] = dict(D=dict(zip(d_idx, gD)), G=dict(zip(g_idx, gG)),
                                 A=None if gA is None else dict(zip(a_idx, gA)))
+        return out
+
+    @torch.no_grad()
+    def forward_losses(self, batch_no, real_image_1, real_cond_1, real_image_2, real_cond_2, noise,
+                       new_image=None, weights=None, args=None):
+        """The three losses of `_train_step` (eager_trainer.py:134-140, 152-161) WITHOUT the update, plus for each
+        the sum of the absolute values of its terms (`*_scale`: soft labels lie outside [0,1], so a loss is a
+        difference of O(1) terms that may pass through zero - its own value is no scale for a relative error).
+        `weights` / `args` override self.W / self.args (the parity tests evaluate a bf16-storage-emulating copy
+        on bf16-representable weights)."""
+        a = args or self.args
+        W = weights or self.W
+        cast = lambda t: t.to(self.dtype)
+        i1, c1, i2, c2, noise = map(cast, (real_image_1, real_cond_1, real_image_2, real_cond_2, noise))
+        new_image = i1 if new_image is None else cast(new_image)
+        one = lambda p: soft(torch.ones_like(p))
+        zero = lambda p: soft(torch.zeros_like(p))
+        fake = generator(a, noise, c2, W["G"])
+        real_pr, real_c = discriminator(a, new_image, W["D"])
+        fake_pr, fake_c = discriminator(a, fake, W["D"])
+        out = {}
+        t = [2 * bce(c1, real_c), bce(one(real_pr), real_pr), bce(zero(fake_pr), fake_pr)]
+        out["disc_loss"], out["disc_scale"] = float(sum(t)), float(sum(x.abs() for x in t))
+        t = [bce(one(fake_pr), fake_pr), bce(c2, fake_c), a.l1_lambda * (i2 - fake).abs().mean()]
+        out["gen_loss"], out["gen_scale"] = float(sum(t)), float(sum(x.abs() for x in t))
+        out["adj_loss"] = out["adj_scale"] = None
+        if a.train_adj and batch_no > 10:
+            cin = (torch.cat([c2, c1], 0) + 1) * 0.5
+            ct = torch.cat([c2, c1], 0)
+            adj = adjuster(a, torch.cat([i1, fake], 0), cin, W["D"], W["G"], W["A"])
+            apr, ac = discriminator(a, adj, W["D"])
+            t = [bce(one(apr), apr), bce(ct, ac), a.l1_lambda * (torch.cat([i2, i1], 0) - adj).abs().mean()]
+            out["adj_loss"], out["adj_scale"] = float(sum(t)), float(sum(x.abs() for x in t))
         return out
 
     @torch.no_grad()

@@ -57,15 +57,20 @@ def test_model_forwards(dtype):
         assert rel_err(a, b) < t * 3
 
 
-def _one_step_parity(oargs, batch_no, B, t_loss, t_grad, t_w, t_grad_hard=None):
-    """t_grad: bound every gradient tensor must meet ... unless t_grad_hard is given: then at least
-    60% of the tensors meet t_grad and all meet t_grad_hard.  (LeakyReLU's derivative is
-    discontinuous at 0: in a 10^6-element map a few pre-activations lie within fp32 rounding of 0,
-    and each such sign flip moves the affected gradient entries by one of their ~10^3 summands.)"""
+def _one_step_parity(oargs, batch_no, B, t_loss, t_grad, t_w, fp32_floor=False):
+    """t_grad: bound every gradient tensor must meet.  fp32_floor (full-size maps): LeakyReLU's derivative is
+    discontinuous at 0 - in a 10^6-element map a few pre-activations lie within fp32 rounding of 0, and each such
+    sign flip moves the affected gradient entries by one of their ~10^3 summands - so no two fp32 implementations
+    agree to 1e-4 on every tensor; the bound of a tensor is then 3x the CPU fp32 oracle's OWN distance from the
+    fp64 oracle on that tensor (never below t_grad)."""
     pargs, gen, disc, adj, trainer, W = _setup(oargs, "fp32")
     ot = O.OracleTrainer(oargs, W, dtype=torch.float64)
     i1, c1, i2, c2, noise = O.synthetic_batch(oargs, B, seed=5)
     ref = ot.train_step(batch_no, i1, c1, i2, c2, noise, return_grads=True)
+    ref32 = None
+    if fp32_floor:
+        ref32 = O.OracleTrainer(oargs, W, dtype=torch.float32).train_step(batch_no, i1, c1, i2, c2, noise,
+                                                                          return_grads=True)
     res = trainer._train_step(batch_no, _ListIterator([(i1, c1), (i2, c2)]), noise=noise)
     assert res[0] is True
     assert rel_err(res[1], ref["fake_image"]) < 1e-4
@@ -94,8 +99,10 @@ def _one_step_parity(oargs, batch_no, B, t_loss, t_grad, t_w, t_grad_hard=None):
                 e = rel_err(got, gref)
             worst = max(worst, e)
             errs.append(e)
-            assert e < (t_grad_hard or t_grad), (key, idx, e)
-    assert sum(e < t_grad for e in errs) >= 0.6 * len(errs), sorted(errs)[-10:]
+            bound = t_grad
+            if ref32 is not None and gref.numel() > 1:
+                bound = max(t_grad, 3.0 * rel_err(ref32["grads"][key][idx], gref))
+            assert e < bound, (key, idx, e, bound)
     # updated weights.  One TF-Adam step moves every weight by ~1.58*lr regardless of |g|, so a
     # gradient that is pure rounding noise (the ~0 d(gamma) above) can legitimately flip the step:
     # the bound is a few lr relative to max|w|, not fp32 epsilon.
@@ -120,7 +127,7 @@ def test_train_step_small_fp32(batch_no):
 def test_train_step_full_size_fp32():
     """The real 128x128 architecture (cond 40), batch 2, full step with adjuster."""
     oargs = O.make_args(cond_dim=40, batch_size=2, use_partition=False)
-    _one_step_parity(oargs, 11, 2, 1e-4, 1e-4, 1e-4, t_grad_hard=1e-2)
+    _one_step_parity(oargs, 11, 2, 1e-4, 1e-4, 1e-4, fp32_floor=True)
 
 
 def test_use_gp_raises():
