@@ -5,6 +5,8 @@ import json
 import math
 import os
 
+import pytest
+
 import numpy as np
 import torch
 
@@ -249,3 +251,78 @@ def test_inception_resize_is_tf1_bilinear():
     y = IO.resize_bilinear_tf1(x, 6, 8)
     assert torch.allclose(y[0, 0, :, 0], torch.tensor([0, 0.5, 1, 1.5, 2, 2.5, 3, 3], dtype=torch.float64))
     assert torch.allclose(y[0, :, 0, 0], torch.tensor([0, 2, 4, 6, 8, 8], dtype=torch.float64))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-held goldens (written by scripts/make_tf_goldens.py where TensorFlow 1.15 exists)
+# ------------------------------------------------------------------------------------------------
+_TF_STEP = os.path.join(os.path.dirname(__file__), "golden", "tf_step.npz")
+_TF_TRAJ = os.path.join(os.path.dirname(__file__), "golden", "tf_trajectory.json")
+
+
+@pytest.mark.skipif(not os.path.isfile(_TF_STEP), reason="tests/golden/tf_step.npz absent: TensorFlow 1.15 is not "
+                    "installable here; a maintainer runs scripts/make_tf_goldens.py once (oracle stays unpinned)")
+def test_oracle_matches_tf_goldens():
+    """Pins the train-step oracle to the UNMODIFIED reference on TF 1.15: per-layer activations, losses, every
+    gradient and the updated weights of one step at batch_no 11 (adjuster on) and 15 (partition step)."""
+    from tests.util import small_args
+    z = np.load(_TF_STEP, allow_pickle=False)
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    oargs = small_args(use_partition=True)
+    W = {k: [t(z["w_%s_%d" % (k, j)]) for j in range(n)] for k, n in (("D", 20), ("G", 22), ("A", 4))}
+    i1, c1, i2, c2, noise = (t(z[k]) for k in ("i1", "c1", "i2", "c2", "noise"))
+    rel = lambda got, want: float((got.double() - want.double()).abs().max() / want.double().abs().max().clamp_min(1e-30))
+    for batch_no in (11, 15):
+        p = "b%d_" % batch_no
+        Wd = {k: [w.double() for w in v] for k, v in W.items()}
+        with torch.no_grad():
+            for i, m in enumerate(O.encoder(oargs, i1.double(), Wd["D"][:16])):
+                assert rel(m, t(z[p + "enc%d_real1" % (i + 1)])) < 1e-4
+            assert rel(O.generator(oargs, noise.double(), c2.double(), Wd["G"]), t(z[p + "fake0"])) < 1e-4
+            pr, c = O.discriminator(oargs, i1.double(), Wd["D"])
+            assert rel(pr, t(z[p + "pr_real1"])) < 1e-4 and rel(c, t(z[p + "c_real1"])) < 1e-4
+            adj0 = O.adjuster(oargs, i1.double(), ((c2 + 1) * 0.5).double(), Wd["D"], Wd["G"], Wd["A"])
+            assert rel(adj0, t(z[p + "adj0"])) < 1e-4
+        ot = O.OracleTrainer(oargs, W, dtype=torch.float64)
+        ref = ot.train_step(batch_no, i1, c1, i2, c2, noise, return_grads=True)
+        assert rel(ref["fake_image"], t(z[p + "fake_image"])) < 1e-4
+        assert rel(ref["adj_image"], t(z[p + "adj_image"])) < 1e-4
+        for got, want in zip((ref["gen_loss"], ref["disc_loss"], ref["adj_loss"]), z[p + "losses"]):
+            assert abs(float(got) - float(want)) < 1e-4 * abs(float(want))
+        for key in "DGA":
+            idx = sorted(ref["grads"][key])              # the partition group of this step, in weight order
+            for j, i in enumerate(idx):
+                want = t(z[p + "grad_%s_%d" % (key, j)])
+                got = ref["grads"][key][i]
+                if want.numel() == 1:
+                    assert abs(float(got) - float(want)) < 1e-4 * max(abs(float(want)), 1e-1), (key, i)
+                else:
+                    assert rel(got, want) < 1e-4, (batch_no, key, i)
+        step = 1.6 * oargs.lr * (1 - 0.9) ** 0.5 / (1 - 0.5)         # size of the first TF-Adam step
+        for key, n in (("D", 20), ("G", 22), ("A", 4)):
+            for j in range(n):
+                diff = (ot.W[key][j].detach().double() - t(z[p + "new_%s_%d" % (key, j)]).double()).abs()
+                assert float(diff.max()) < 2.5 * step, (key, j)      # at most a sign flip of a noise-level gradient
+                if diff.numel() > 1:
+                    assert float((diff > 0.05 * step).double().mean()) < 5e-3, (key, j)
+
+
+@pytest.mark.skipif(not os.path.isfile(_TF_TRAJ), reason="tests/golden/tf_trajectory.json absent (see above)")
+def test_oracle_trajectory_matches_tf():
+    """100 free-running steps: within 1% of TensorFlow's losses until the TF-Adam chaos sets in (first 10 steps),
+    and a median deviation over all steps no larger than two fp32 implementations show against each other."""
+    import json
+    from tests.util import small_args
+    tr = json.load(open(_TF_TRAJ))
+    oargs = small_args(use_partition=True)
+    ot = O.OracleTrainer(oargs, O.init_weights(oargs, tr["weight_seed"]), dtype=torch.float32)
+    devs = []
+    for b in range(1, len(tr["gen"]) + 1):
+        i1, c1, i2, c2, noise = O.synthetic_batch(oargs, tr["B"], seed=tr["data_seed"] + b)
+        ref = ot.train_step(b, i1, c1, i2, c2, noise)
+        for got, want in ((ref["gen_loss"], tr["gen"][b - 1]), (ref["disc_loss"], tr["disc"][b - 1])):
+            d = abs(float(got) - want) / abs(want)
+            devs.append(d)
+            if b <= 10:
+                assert d < 0.01, (b, float(got), want)
+    assert float(np.median(devs)) < 0.02
