@@ -113,6 +113,7 @@ class EagerTrainer:
         self._pool = None
         self._noise_gen = None
         self._comm_stream = None
+        self._reduced = {}                       # optimiser name -> event behind its last all-reduce of this step
         self._chain_streams = {}
         self._rb, self._rb_count = None, 0
         self._aug_state = None
@@ -353,15 +354,26 @@ class EagerTrainer:
         self._reduce_async("Generator", batch_no, part=(4, 22))     # decoder + final conv: under the dense backward
         E.head_backward(rt, G.dense, G.norm, g_hctx, g)
         self._reduce_async("Generator", batch_no, part=(0, 4))
+        if adj_on:
+            # The collectives of one communicator execute in issue order, so the adjuster's bucket - produced by the
+            # LONGEST chain - is issued last: issued from inside its chain (which is launched first) it made the
+            # discriminator's and the generator's all-reduces wait for the whole adjuster sub-step and all four
+            # ran, exposed, behind the last backward kernel (profiles/r2_dp2_timeline_before.txt).
+            with torch.cuda.stream(sA):
+                self._reduce_async("Adjuster", batch_no)
 
         main.wait_stream(sD)
         if adj_on:
             main.wait_stream(sA)
 
-        # ---- apply: A (if trained), D, G (eager_trainer.py:164-168); D grads value-clipped (:146-148)
-        if _dist() is not None:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)   # join the gradient all-reduces
-        for name in (["Adjuster"] if adj_on else []) + ["Discriminator", "Generator"]:
+        # ---- apply (eager_trainer.py:164-168); D grads value-clipped (:146-148).  The reference applies A, D, G; the
+        # three optimisers own disjoint tensors and every gradient was taken at the pre-update weights, so the order
+        # is immaterial: the adjuster - whose all-reduce is the last collective - goes last, and each Adam waits only
+        # for its own optimiser's all-reduce (the adjuster's runs under the Adams of D and G).
+        for name in ["Discriminator", "Generator"] + (["Adjuster"] if adj_on else []):
+            ev = self._reduced.pop(name, None)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
             lo, hi = self._range(name, batch_no)
             grad = self.Gd[lo:hi]
             lr, b1, b2 = self._hyper[name]
@@ -405,7 +417,6 @@ class EagerTrainer:
         g = E.generator_tail_backward(rt, A.decoder, A.conv, a_dctx, a_x4, dpre, wgrad=False)
         E.head_backward(rt, A.dense, A.norm, a_hctx, g)
         S["adj"] = adj
-        self._reduce_async("Adjuster", batch_no)
 
     def _bucket(self, name, batch_no, part=None):
         """Flat [lo, hi) of one gradient bucket: the optimiser's active range (`_range`), optionally cut down to
@@ -447,6 +458,9 @@ class EagerTrainer:
         self._comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._comm_stream):
             self._all_reduce_mean(dist, buf)
+            ev = torch.cuda.Event()
+            ev.record(self._comm_stream)
+        self._reduced[name] = ev                 # the optimiser's LAST bucket: what its Adam waits for
 
     def _variant(self, batch_no):
         a = self.args

@@ -1,0 +1,119 @@
+"""Data-parallel equivalence ON HARDWARE (SURVEY 4 layer 5): the 2-GPU NCCL step - each rank on its half of the
+batch, the flat gradient arenas all-reduced (average) inside the step - equals the 1-GPU step on the whole batch.
+-m gpu; skipped on a box with fewer than 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests/test_dp_nccl_gpu.py)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import littlegan_oracle as O
+from tests.util import build_product, product_args, rel_err
+
+pytestmark = pytest.mark.gpu
+B_GLOBAL = 16
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _It:
+    def __init__(self, items):
+        self.items = list(items)
+
+    def get_next(self):
+        return self.items.pop(0)
+
+
+def _steps(dtype, world, rank, n_steps):
+    """n_steps train steps (batch_no 11.., adjuster on; CUDA graph from the second) on this rank's slice of the
+    global batches.  Returns (gradient arena after the first step, parameter arena after the last, losses)."""
+    from littlegan_b200.eager_trainer import EagerTrainer
+    per = B_GLOBAL // world
+    oargs = O.make_args(cond_dim=40, batch_size=per, use_partition=False)
+    pargs = product_args(oargs, dtype=dtype, cuda_graph=True)
+    gen, disc, adj = build_product(pargs, seed=0)
+    trainer = EagerTrainer(pargs, gen, disc, adj, None)
+    sl = slice(rank * per, (rank + 1) * per)
+    grads, losses = None, []
+    for k in range(n_steps):
+        i1, c1, i2, c2, noise = O.synthetic_batch(O.make_args(cond_dim=40), B_GLOBAL, seed=50 + k)
+        res = trainer._train_step(11 + k, _It([(i1[sl], c1[sl]), (i2[sl], c2[sl])]), noise=noise[sl])
+        torch.cuda.synchronize()
+        if k == 0:
+            grads = trainer.Gd.clone()
+        losses.append([float(res[3]), float(res[4]), float(res[5])])
+    return grads.cpu(), trainer.P.clone().cpu(), torch.tensor(losses, dtype=torch.float64), trainer._offsets
+
+
+def _worker(rank, world, port, dtype, n_steps, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g, P, losses, _ = _steps(dtype, world, rank, n_steps)
+        # the replicas must stay bit-identical: same averaged gradients -> same Adam update on every rank
+        ref = P.cuda()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([float(torch.equal(ref.cpu(), P))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        lsum = losses.cuda()
+        dist.all_reduce(lsum)                          # local losses are local-batch means: their mean is global
+        if rank == 0:
+            q.put((g.numpy(), P.numpy(), (lsum / world).cpu().numpy(), float(same)))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        os._exit(0)                                    # captured graphs hold NCCL work: skip the destructor chain
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_two_gpu_step_equals_one_gpu_step(dtype):
+    n_steps = 3
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, dtype, n_steps, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g2, P2, l2, same = q.get()
+    for p in procs:
+        p.join(120)
+    assert same == 1.0, "parameter replicas diverged across ranks"
+    g1, P1, l1, offsets = _steps(dtype, 1, 0, n_steps)
+    g2, P2 = torch.from_numpy(g2), torch.from_numpy(P2)
+    # losses: mean over ranks of the local-batch means == the global-batch mean.  Exact (up to summation order) on
+    # the first step; afterwards the replicas of the two runs are no longer the same network - one TF-Adam step
+    # moves every weight by ~1.6 lr in the direction of sign(g), and gradients at rounding-noise level (the
+    # analytically-zero d gamma) take either sign - so later steps only have to stay close
+    dl = (torch.from_numpy(l2) - l1).abs()
+    assert float(dl[0].max()) < (1e-5 if dtype == "fp32" else 3e-4), dl
+    assert float(dl.max()) < 1e-2, dl
+    # gradients of the first step, tensor by tensor.  fp32 mode: only the split-K / atomics order differs with the
+    # batch split.  bf16 mode: the planner also picks different tile / pair / split configurations - and so
+    # different bf16 rounding points of a few stored gradients - for 8 and 16 images: within the bf16 tolerance
+    tol = 2e-5 if dtype == "fp32" else 2e-2
+    worst = 0.0
+    for name, offs in offsets.items():
+        for lo, hi in zip(offs[:-1], offs[1:]):
+            a, b = g2[lo:hi], g1[lo:hi]
+            if float(b.abs().max()) < 1e-6:
+                continue                               # alignment padding / analytically-zero scalars
+            e = rel_err(a, b)
+            worst = max(worst, e)
+            if hi - lo > 64:
+                assert e < tol, (name, lo, e)
+    print("2-GPU vs 1-GPU first-step gradients: worst per-tensor max-norm error %.2e (%s)" % (worst, dtype))
+    # parameters after 3 steps: one TF-Adam step moves a weight by ~lr whatever |g|, so only the sign of
+    # noise-level gradients can differ - bounded by a few lr per step
+    lr = 5e-5
+    assert float((P2 - P1).abs().max()) < 2.5 * 1.6 * lr * n_steps
+    assert float(((P2 - P1).abs() > 0.1 * lr).double().mean()) < (1e-3 if dtype == "fp32" else 5e-2)
