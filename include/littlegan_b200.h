@@ -315,6 +315,21 @@ int lg_fid_accumulate(const float* X, const double* shift, double* S1, double* S
 int lg_fid_finalize(const double* S1, const double* S2, const double* shift, double* mu,
                     double* sigma, int64_t n, int d, void* stream);
 
+/* ---- Frechet distance (fid.py:112-163: scipy.linalg.sqrtm of sigma1 sigma2 in fp64) ------------------------
+ * Tr sqrtm(sigma1 sigma2) = Tr (R sigma2 R)^(1/2) with R = sigma1^(1/2) (same spectrum, symmetric PSD), both
+ * square roots by the coupled Newton-Schulz iteration - fp64 matrix products only.  The host side
+ * (littlegan_b200/fid.py) drives the iteration through these three entry points; all matrices are row-major
+ * double[n,n] in device memory. */
+
+/* C = alpha * A @ B + diag * I.  C must not alias A or B. */
+int lg_dgemm(const double* A, const double* B, double* C, int n, double alpha, double diag, void* stream);
+/* out3[0] = trace(A), out3[1] = ||A||_F^2, out3[2] = max_ij |A_ij - A_ji|  (device doubles, written by the launch). */
+int lg_dmat_stats(const double* A, int n, double* out3, void* stream);
+/* dst = alpha * S + diag * I with S = src, or (src + src^T) / 2 when `symmetrise` (then dst != src), or 0 when
+ * src is NULL. */
+int lg_dmat_scale_shift(const double* src, double* dst, int n, double alpha, double diag, int symmetrise,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

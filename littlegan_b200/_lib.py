@@ -69,6 +69,9 @@ SIGNATURES = {
     "lg_resize_bilinear_norm": (_i, [_vp, _vp] + [_i] * 7 + [_f, _f, _i, _i, _vp]),
     "lg_fid_accumulate": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "lg_fid_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "lg_dgemm": (_i, [_vp, _vp, _vp, _i, _d, _d, _vp]),
+    "lg_dmat_stats": (_i, [_vp, _i, _vp, _vp]),
+    "lg_dmat_scale_shift": (_i, [_vp, _vp, _i, _d, _d, _i, _vp]),
 }
 
 

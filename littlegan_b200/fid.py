@@ -12,6 +12,7 @@ is the `sess` argument here (any callable mapping an image batch [b,H,W,3] in 0.
 (`fid.py:197-318`: `*_from_files`, `_handle_path`, `calculate_fid_given_paths`) decode on host threads one batch ahead
 of the GPU and hand the forward image BYTES.
 """
+import math
 import warnings
 
 import numpy as np
@@ -125,20 +126,77 @@ def calculate_activation_statistics(images, sess=None, batch_size=50, verbose=Fa
     return mu, sigma
 
 
+_NS_MAX_ITERS = 60
+
+
+def _sqrtm_psd(A, want_matrix=True, tol=1e-14):
+    """Square root of a symmetric PSD fp64 matrix A [n,n] (CUDA) by the coupled Newton-Schulz iteration
+        Y0 = A / c, Z0 = I;  T = (3 I - Z Y) / 2;  Y <- Y T, Z <- T Z;   Y -> (A / c)^(1/2),  c = ||A||_F >= lambda_max
+    on this library's fp64 GEMM (csrc/fid.cu `lg_dgemm`): no eigen-solver, no library call.
+    Returns (sqrt(A) or None, Tr sqrt(A), iterations).
+
+    Each eigen-component converges monotonically from below - quadratically once lambda_k/c has grown to O(1),
+    after ~log(c / lambda) / log(2.25) iterations - so Tr Y increases until every component above the rounding
+    level has arrived.  Numerically-zero eigenvalues of a singular A are rounding noise of either sign; a negative
+    one grows like -|noise| * 1.5^k, so the iteration stops as soon as the trace stops increasing by more than
+    `tol` (relative) - long before such a component matters - and never runs past _NS_MAX_ITERS."""
+    n = A.shape[0]
+    dev = A.device
+    stats = torch.empty(3, dtype=torch.float64, device=dev)
+    K.dmat_stats(A, stats)
+    tr_a, fro2, _ = stats.tolist()
+    if not (math.isfinite(tr_a) and math.isfinite(fro2)):
+        return None, float("nan"), 0
+    c = math.sqrt(fro2)
+    if c == 0.0:
+        return (torch.zeros_like(A) if want_matrix else None), 0.0, 0
+    Y, Z, T, Yn, Zn = (torch.empty_like(A) for _ in range(5))
+    K.dmat_scale_shift(A, Y, 1.0 / c, 0.0)
+    K.dmat_scale_shift(None, Z, 0.0, 1.0)
+    prev, best, iters = None, None, 0
+    for k in range(_NS_MAX_ITERS):
+        K.dgemm(Z, Y, T, -0.5, 1.5)
+        K.dgemm(Y, T, Yn)
+        K.dgemm(T, Z, Zn)
+        Y, Yn, Z, Zn = Yn, Y, Zn, Z
+        K.dmat_stats(Y, stats)
+        t = float(stats[0])
+        iters = k + 1
+        if not math.isfinite(t):
+            return None, float("nan"), iters
+        if prev is not None and t - prev <= tol * abs(t):
+            if t < prev:                       # a rounding-noise component has started to grow: keep the peak
+                Y, t = Yn, prev                # (Yn holds the previous iterate)
+            best = t
+            break
+        prev = best = t
+    root = math.sqrt(c)
+    if want_matrix:
+        K.dmat_scale_shift(Y, T, root, 0.0, symmetrise=True)
+        return T, best * root, iters
+    return None, best * root, iters
+
+
 def _trace_sqrt_product(s1, s2):
-    """Tr sqrtm(s1 s2) for symmetric PSD s1, s2 via two symmetric eigendecompositions (fp64, GPU):
-    the spectrum of s1 s2 equals that of s1^(1/2) s2 s1^(1/2)."""
-    w, v = torch.linalg.eigh(s1)
-    root = (v * w.clamp_min(0).sqrt()) @ v.T
-    m = root @ s2 @ root
-    lam = torch.linalg.eigvalsh((m + m.T) * 0.5)
-    return lam.clamp_min(0).sqrt().sum()
+    """Tr sqrtm(s1 s2) for symmetric PSD s1, s2 (fp64, CUDA): the spectrum of s1 s2 is that of the symmetric PSD
+    matrix R s2 R with R = s1^(1/2); both square roots by Newton-Schulz on the library's own fp64 GEMM."""
+    R, _, _ = _sqrtm_psd(s1.contiguous(), want_matrix=True)
+    if R is None:
+        return torch.tensor(float("nan"), dtype=torch.float64, device=s1.device)
+    tmp, M = torch.empty_like(R), torch.empty_like(R)
+    K.dgemm(R, s2.contiguous(), tmp)
+    K.dgemm(tmp, R, M)
+    Ms = torch.empty_like(M)
+    K.dmat_scale_shift(M, Ms, 1.0, 0.0, symmetrise=True)
+    _, tr, _ = _sqrtm_psd(Ms, want_matrix=False)
+    return torch.tensor(tr, dtype=torch.float64, device=s1.device)
 
 
 def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
     """fid.py:112-163: ||mu1-mu2||^2 + Tr s1 + Tr s2 - 2 Tr sqrtm(s1 s2), fp64 on the GPU.
-    The reference's scipy.linalg.sqrtm (Schur) is replaced by the symmetric form above; the
-    non-finite fallback (add eps*I to both covariances, `fid.py:148-152`) is kept."""
+    The reference's scipy.linalg.sqrtm (Schur) is replaced by the symmetric Newton-Schulz form above (hand-written
+    fp64 GEMM kernels, no cuSOLVER); the non-finite fallback (add eps*I to both covariances, `fid.py:148-152`) is
+    kept."""
     dev = torch.device("cuda")
     t = lambda x: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(dev, torch.float64)
     mu1, mu2 = torch.atleast_1d(t(mu1)), torch.atleast_1d(t(mu2))
@@ -151,7 +209,11 @@ def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
         warnings.warn("fid calculation produces singular product; adding %s to diagonal of cov estimates" % eps)
         offset = torch.eye(sigma1.shape[0], dtype=torch.float64, device=dev) * eps
         tr = _trace_sqrt_product(sigma1 + offset, sigma2 + offset)
-    return float(diff.dot(diff) + torch.trace(sigma1) + torch.trace(sigma2) - 2 * tr)
+    st = torch.empty(2, 3, dtype=torch.float64, device=dev)
+    K.dmat_stats(sigma1.contiguous(), st[0])
+    K.dmat_stats(sigma2.contiguous(), st[1])
+    d2 = diff.cpu().numpy()                       # the reference's diff.dot(diff), fp64 on the host
+    return float(d2.dot(d2) + float(st[0, 0]) + float(st[1, 0]) - 2 * float(tr))
 
 
 # ------------------------------------------------------------------ file-based variants (fid.py:197-318)

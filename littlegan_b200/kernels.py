@@ -417,6 +417,31 @@ def fid_finalize(S1, S2, shift, mu, sigma, n):
           "lg_fid_finalize")
 
 
+def dgemm(A, B, C, alpha=1.0, diag=0.0):
+    """C = alpha * A @ B + diag * I on fp64 [n,n] matrices (csrc/fid.cu)."""
+    _cuda(A, B, C)
+    n = A.shape[0]
+    if not (A.dtype == B.dtype == C.dtype == torch.float64 and A.shape == B.shape == C.shape == (n, n)):
+        raise _lib.LittleGANError("dgemm: needs three fp64 [n,n] matrices")
+    check(_lib.load().lg_dgemm(_p(A), _p(B), _p(C), n, float(alpha), float(diag), _st()), "lg_dgemm")
+    return C
+
+
+def dmat_stats(A, out3):
+    """out3 (3 device doubles) = [trace(A), ||A||_F^2, max |A - A^T|]."""
+    _cuda(A, out3)
+    check(_lib.load().lg_dmat_stats(_p(A), A.shape[0], _p(out3), _st()), "lg_dmat_stats")
+    return out3
+
+
+def dmat_scale_shift(src, dst, alpha=1.0, diag=0.0, symmetrise=False):
+    """dst = alpha * (src | (src + src^T)/2 | 0) + diag * I."""
+    _cuda(src, dst)
+    check(_lib.load().lg_dmat_scale_shift(_p(src), _p(dst), dst.shape[0], float(alpha), float(diag), int(symmetrise),
+                                          _st()), "lg_dmat_scale_shift")
+    return dst
+
+
 # ------------------------------------------------------------------------------------ augmentation
 AUG_MAX_BRIGHTNESS, AUG_CONTRAST, AUG_MAX_HUE, AUG_NOISE_STD = 0.02, (0.75, 1.003), 0.03, 0.1 * 0.2
 

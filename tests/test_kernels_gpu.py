@@ -750,3 +750,48 @@ def test_u8_rescale_is_bit_exact(n):
     assert torch.equal(outb.cpu(), torch.from_numpy(want).to(torch.bfloat16))
     with pytest.raises(Exception):
         K.u8_rescale(x.cuda().float(), out)
+
+
+# ------------------------------------------------------------------------------------------------
+# Frechet distance without a library eigen-solver (fid.py:112-163): fp64 GEMM + Newton-Schulz
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 37, 128, 200, 512])
+def test_dgemm_matches_fp64_matmul(n):
+    """lg_dgemm: C = alpha A B + diag I on row-major fp64 matrices, any n (tile tails)."""
+    from littlegan_b200 import kernels as K
+    g = torch.Generator().manual_seed(n)
+    A = torch.randn(n, n, generator=g, dtype=torch.float64)
+    B = torch.randn(n, n, generator=g, dtype=torch.float64)
+    C = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    K.dgemm(A.cuda(), B.cuda(), C, -0.5, 1.5)
+    ref = -0.5 * (A @ B) + 1.5 * torch.eye(n, dtype=torch.float64)
+    assert float((C.cpu() - ref).abs().max()) < 1e-12 * max(1.0, float(ref.abs().max()))
+    st = torch.empty(3, dtype=torch.float64, device="cuda")
+    K.dmat_stats(C, st)
+    assert abs(float(st[0]) - float(ref.trace())) < 1e-10 * max(1.0, abs(float(ref.trace())))
+    assert abs(float(st[1]) - float((ref * ref).sum())) < 1e-10 * float((ref * ref).sum())
+    assert abs(float(st[2]) - float((ref - ref.T).abs().max())) < 1e-12 * max(1.0, float(ref.abs().max()))
+    with pytest.raises(Exception):
+        K.dgemm(C, C, C)                                  # the output must not alias an operand
+
+
+@pytest.mark.parametrize("d,n1,n2", [(256, 3000, 2000), (24, 400, 300), (200, 1000, 150), (384, 60, 90)])
+def test_frechet_distance_matches_scipy(d, n1, n2):
+    """Full-rank, odd-sized and SINGULAR (fewer samples than dimensions) covariances against the reference's own
+    arithmetic (scipy.linalg.sqrtm of sigma1 sigma2).  scipy's Schur square root of a singular product is itself
+    only good to ~1e-7 relative, hence the looser bound there."""
+    from littlegan_b200 import fid
+    rng = np.random.RandomState(d)
+    x1 = (rng.randn(n1, d) @ (rng.randn(d, d) / np.sqrt(d))) * 0.5 + 0.3
+    x2 = (rng.randn(n2, d) @ (rng.randn(d, d) / np.sqrt(d))) * 0.7 + 0.1
+    m1, s1 = fid_oracle.activation_statistics(x1)
+    m2, s2 = fid_oracle.activation_statistics(x2)
+    ref = fid_oracle.frechet_distance(m1, s1, m2, s2)
+    got = fid.calculate_frechet_distance(m1, s1, m2, s2)
+    singular = min(n1, n2) <= d
+    assert abs(got - ref) < (1e-6 if singular else 1e-9) * abs(ref), (got, ref)
+    assert abs(fid.calculate_frechet_distance(m1, s1, m1, s1)) < 1e-7 * np.trace(s1)
+    # the square root itself
+    R, tr, iters = fid._sqrtm_psd(torch.from_numpy(s1).cuda())
+    assert iters < fid._NS_MAX_ITERS
+    assert float((R @ R - torch.from_numpy(s1).cuda()).abs().max()) < 1e-9 * np.abs(s1).max()
