@@ -132,7 +132,7 @@ def test_instnorm_fwd_bwd(shape, alphas, zdt, odt):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("rows,C", [(512, 64), (100, 384), (333, 3), (64, 32), (7, 1), (6, 24576)])
+@pytest.mark.parametrize("rows,C", [(512, 64), (100, 384), (8192, 384), (1001, 192), (333, 3), (64, 32), (7, 1), (6, 24576)])
 def test_bias_grad(rows, C, dtype):
     from littlegan_b200 import kernels as K
     g = _rand((rows, C), 30, dtype)
@@ -233,19 +233,23 @@ def test_bce_and_l1():
         assert rel_err(dpre.cpu()[ok], dref[ok]) < tol(dtype)
 
 
-def test_adam_matches_tf_form():
+@pytest.mark.parametrize("n,off", [(1000, 0), (1003, 0), (1000, 1), (3, 0), (700001, 0)])
+def test_adam_matches_tf_form(n, off):
+    """16-byte vector path (aligned ranges, n % 4 tail), the scalar path (off = 1: misaligned views) and a range
+    that spans several grid passes."""
     from littlegan_b200 import kernels as K
-    n = 1000
     p0 = _rand((n,), 60, torch.float32);
     opt = O.TFAdam(5e-5, 0.5, 0.9)
     p_ref = p0.clone().double()
-    p = p0.clone().cuda(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    buf = lambda src=None: (torch.zeros(n + off, device="cuda")[off:] if src is None else
+                            torch.cat([torch.zeros(off), src]).cuda()[off:])
+    p = buf(p0); m = buf(); v = buf()
     state = torch.zeros(4, dtype=torch.float64, device="cuda")
     for step in range(3):
         g = _rand((n,), 61 + step, torch.float32)
         opt.apply([(g.double().clamp(-0.5, 0.5), p_ref)])
         K.adam_advance(state, 5e-5, 0.5, 0.9)
-        K.adam_apply(p, g.cuda(), m, v, state, 0.5, 0.9, 1e-8, 0.5)
+        K.adam_apply(p, buf(g), m, v, state, 0.5, 0.9, 1e-8, 0.5)
     assert float(state[0]) == 3.0
     assert float((p.cpu().double() - p_ref).abs().max()) < 5e-7   # fp32 rounding of p ~ 1
 
