@@ -267,28 +267,30 @@ def hbm_rooflines(peaks, trainer):
     return res
 
 
-def sustained_run(graph, seconds, B, world, local, rank):
-    """Replays the captured step back to back for >= `seconds` with the clock sampler on: the throughput a long
-    training run sees (power / clock steady state), next to the short timed region of `value`."""
+def sustained_run(graph, n_steps, B, world, local, rank):
+    """Replays the captured step back to back `n_steps` times (>= 5 s of work; the count is fixed up front and identical
+    on every rank - the graph contains the NCCL all-reduces, so all ranks must replay it equally often) with the clock
+    sampler on: the throughput a long training run sees (power / clock steady state), next to the short timed region
+    of `value`."""
     import torch
+    import torch.distributed as dist
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
         sampler.rows.clear()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    n = 0
     e0.record()
-    while time.perf_counter() - t0 < seconds:
-        for _ in range(50):
-            graph.replay()
-        n += 50
-        torch.cuda.current_stream().synchronize() if n % 500 == 0 else None
+    for i in range(n_steps):
+        graph.replay()
+        if i % 500 == 499:
+            torch.cuda.current_stream().synchronize()       # bound the launch queue
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+    ms = e0.elapsed_time(e1) / n_steps
     clocks = sampler.stop() if rank == 0 else None
     power = None
     if rank == 0:
@@ -300,8 +302,8 @@ def sustained_run(graph, seconds, B, world, local, rank):
                 pass
         pw.sort()
         power = pw[len(pw) // 2] if pw else None
-    return {"seconds": ms * n / 1e3, "steps": n, "ms_per_step": ms, "images_per_sec_per_gpu": B / (ms * 1e-3),
-            "clocks": clocks, "power_w_median": power}
+    return {"seconds": ms * n_steps / 1e3, "steps": n_steps, "ms_per_step": ms,
+            "images_per_sec_per_gpu": B / (ms * 1e-3), "clocks": clocks, "power_w_median": power}
 
 
 def predict_bench(trainer, world, reps=5):
@@ -446,38 +448,13 @@ def run_product(a):
     clocks = sampler.stop() if rank == 0 else None
     assert all(x == x for x in losses), "non-finite loss"
 
-    # ---- extras (none of them inside the timed regions above): sustained replay, configs[3] predict, configs[4] FID
-    extra = {}
-    if not a.no_extras:
-        sus = sustained_run(graph, a.sustain_seconds, B, world, local, rank)
-        ms_pred, b_pred = predict_bench(trainer, world)
-        fidr = fid50k_bench(world, rank)
-        tt = torch.tensor([sus["ms_per_step"], ms_pred, fidr["features_statistics_s"]], dtype=torch.float64,
-                          device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        sus["ms_per_step"] = float(tt[0])
-        sus["images_per_sec"] = B * world / (float(tt[0]) * 1e-3)
-        fidr["features_statistics_s"] = float(tt[2])
-        fidr["images_per_sec"] = fidr["images"] / float(tt[2])
-        extra = {"sustained": sus,
-                 "predict": {"workload": "configs[3]: predict, batch 256/GPU, host numpy inputs", "ms_per_call": float(tt[1]),
-                             "images_per_sec": b_pred * world / (float(tt[1]) * 1e-3), "per_gpu_batch": b_pred},
-                 "fid50k": fidr}
-    # data-parallel invariant: the replicas must hold bit-identical parameters after any number of steps
-    if world > 1:
-        ref = trainer.P.clone()
-        dist.broadcast(ref, src=0)
-        same = torch.tensor([1.0 if torch.equal(ref, trainer.P) else 0.0], device="cuda")
-        dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        assert float(same) == 1.0, "parameter replicas diverged across ranks"
-        extra["replicas_bit_identical"] = True
-
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
 
+    # ---- the contract line, complete before any extra runs
+    line = None
     if rank == 0:
         peaks = _peaks()
         gb = B * world
@@ -498,17 +475,63 @@ def run_product(a):
         }
         if world == 1:
             line["roofline"] = dominant_kernel_roofline(peaks)
-            if not a.no_extras:
-                extra["roofline_hbm"] = hbm_rooflines(peaks, trainer)
-                # sum of dram__bytes_read + dram__bytes_write over one replay of the captured step (ncu, batch 64);
-                # an offline number: profiles/ holds the launch list it was summed from
-                extra["step_dram_bytes"] = STEP_DRAM_BYTES
             if not a.no_cpu_baseline:
                 rate, ms, cores = cpu_oracle_rate(16, 4, 1)
                 line["cpu_baseline"] = {
                     "value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                     "sample": "4 full train steps on a 16-image batch (configs[0]), oracle restatement in "
                               "PyTorch-CPU fp32 (TF 1.15 not installable)"}
+
+    # ---- extras (none of them inside the timed regions above): sustained replay, configs[3] predict, configs[4] FID.
+    # Every count below is derived from values that are identical on all ranks (the all-reduced ms_dev): the captured
+    # step and the FID statistics contain collectives.  A watchdog guards them: should an extra stall (a lost rank,
+    # a wedged collective), every rank leaves after `--extras-timeout` seconds and rank 0 still prints the contract
+    # line, with the reason under extra_keys.
+    extra = {}
+    done = threading.Event()
+
+    def _watchdog():
+        if done.wait(a.extras_timeout):
+            return
+        if rank == 0 and line is not None:
+            line["extra_keys"] = {"aborted": "extras exceeded %.0f s and were abandoned" % a.extras_timeout}
+            print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os._exit(0)
+
+    if not a.no_extras:
+        threading.Thread(target=_watchdog, daemon=True).start()
+        n_sus = max(100, int(a.sustain_seconds * 1e3 / ms_dev / 100.0 + 0.5) * 100)
+        sus = sustained_run(graph, n_sus, B, world, local, rank)
+        ms_pred, b_pred = predict_bench(trainer, world)
+        fidr = fid50k_bench(world, rank)
+        tt = torch.tensor([sus["ms_per_step"], ms_pred, fidr["features_statistics_s"]], dtype=torch.float64,
+                          device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sus["ms_per_step"] = float(tt[0])
+        sus["images_per_sec"] = B * world / (float(tt[0]) * 1e-3)
+        fidr["features_statistics_s"] = float(tt[2])
+        fidr["images_per_sec"] = fidr["images"] / float(tt[2])
+        extra = {"sustained": sus,
+                 "predict": {"workload": "configs[3]: predict, batch 256/GPU, host numpy inputs", "ms_per_call": float(tt[1]),
+                             "images_per_sec": b_pred * world / (float(tt[1]) * 1e-3), "per_gpu_batch": b_pred},
+                 "fid50k": fidr}
+        if world == 1 and rank == 0:
+            extra["roofline_hbm"] = hbm_rooflines(_peaks(), trainer)
+            # sum of dram__bytes_read + dram__bytes_write over one replay of the captured step (ncu, batch 64);
+            # an offline number: profiles/ holds the launch list it was summed from
+            extra["step_dram_bytes"] = STEP_DRAM_BYTES
+    # data-parallel invariant: the replicas must hold bit-identical parameters after any number of steps
+    if world > 1:
+        ref = trainer.P.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([1.0 if torch.equal(ref, trainer.P) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        assert float(same) == 1.0, "parameter replicas diverged across ranks"
+        extra["replicas_bit_identical"] = True
+    done.set()
+    if rank == 0:
         line["extra_keys"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -530,6 +553,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained / predict / fid50k / HBM-roofline extras")
     ap.add_argument("--sustain-seconds", type=float, default=5.0)
+    ap.add_argument("--extras-timeout", type=float, default=150.0)
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
