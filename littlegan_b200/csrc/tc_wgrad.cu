@@ -11,8 +11,11 @@
 // reduces its 128 x NT fp32 tile into dW with 16-byte vector reductions (red.global.add.v4.f32),
 // where a thread owns a (tap,a) row and therefore contiguous b.
 //
-// One tile x one k-slice per CTA: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue.
+// One tile x one k-slice per CTA: warps 0-3 = epilogue, warp 5 = MMA issuer + TMEM owner, and TWO TMA producer
+// warps (4: the big-map boxes, 6: the small-map boxes).  A stage is 4-6 boxes of 8 KB against four MMAs, and one
+// thread gets a wait / expect / TMA instruction out only every ~60-100 ns (scripts/ubench/tma_rows.cu: the per-SM
+// TMA rate doubles with a second issuing thread): with a single producer the N = 128 layers ran at the producer's
+// issue rate (6 instructions = ~350 ns per stage against ~190 ns of MMAs).
 #include <cuda.h>
 #include <stdio.h>
 
@@ -23,8 +26,8 @@
 
 namespace {
 
-constexpr int NUM_THREADS = 192;
-constexpr int PRODUCER_WARP = 4, MMA_WARP = 5;   // epilogue = warps 0-3; single-thread roles get the high warp ids
+constexpr int NUM_THREADS = 224;
+constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, PRODUCER_B_WARP = 6;   // epilogue = warps 0-3
 constexpr int MAX_STAGES = 8;
 constexpr int KP = 64;                   // positions per k-block
 constexpr int SMEM_BUDGET = 200 * 1024;
@@ -76,7 +79,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
   if (warp == PRODUCER_WARP && lane == 0) {
     tc::tma_prefetch_desc(&tmBig);
     tc::tma_prefetch_desc(&tmSmall);
-    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 2); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(tfull, 1);
     tc::fence_barrier_init();
   }
@@ -106,6 +109,28 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
       }
       const uint32_t smem_u = tc::smem_u32(smem), full_u = tc::smem_u32(full), empty_u = tc::smem_u32(empty);
       const uint32_t stage_bytes_u = (uint32_t)p.stage_bytes, a_bytes_u = (uint32_t)p.a_bytes;
+      const int nstages = p.stages;
+      int pw = kb0 % p.pbW, ph = (kb0 / p.pbW) % p.pbH, pn = kb0 / (p.pbW * p.pbH);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int j0 = pw * p.BW, i0 = ph * p.BH, n0 = pn * p.BN;
+        const uint32_t fb = full_u + (uint32_t)stage * 8u;
+        const uint32_t sa = smem_u + (uint32_t)stage * stage_bytes_u;
+        tc::mbar_wait_addr(empty_u + (uint32_t)stage * 8u, phase ^ 1);
+        tc::mbar_expect_tx_addr(fb, a_bytes_u);
+        const int bx = p.s * j0, by = p.s * i0;
+#pragma unroll
+        for (int bi = 0; bi < 8; ++bi)
+          if (bi < nbox_a)
+            tc::tma_load_4d_addr(sa + bi * a_box_bytes, &tmBig, fb, box_ch[bi], bx + box_dx[bi], by + box_dy[bi], n0);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        if (++pw == p.pbW) { pw = 0; if (++ph == p.pbH) { ph = 0; ++pn; } }
+      }
+    }
+  } else if (warp == PRODUCER_B_WARP) {
+    if (num_kb > 0 && tc::elect_one()) {
+      const uint32_t smem_u = tc::smem_u32(smem), full_u = tc::smem_u32(full), empty_u = tc::smem_u32(empty);
+      const uint32_t stage_bytes_u = (uint32_t)p.stage_bytes, a_bytes_u = (uint32_t)p.a_bytes;
       const int nstages = p.stages, b_ch0 = nt * p.NT;
       int pw = kb0 % p.pbW, ph = (kb0 / p.pbW) % p.pbH, pn = kb0 / (p.pbW * p.pbH);
       int stage = 0; uint32_t phase = 0;
@@ -114,12 +139,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
         const uint32_t fb = full_u + (uint32_t)stage * 8u;
         const uint32_t sa = smem_u + (uint32_t)stage * stage_bytes_u;
         tc::mbar_wait_addr(empty_u + (uint32_t)stage * 8u, phase ^ 1);
-        tc::mbar_expect_tx_addr(fb, stage_bytes_u);
-        const int bx = p.s * j0, by = p.s * i0;
-#pragma unroll
-        for (int bi = 0; bi < 8; ++bi)
-          if (bi < nbox_a)
-            tc::tma_load_4d_addr(sa + bi * a_box_bytes, &tmBig, fb, box_ch[bi], bx + box_dx[bi], by + box_dy[bi], n0);
+        tc::mbar_expect_tx_addr(fb, stage_bytes_u - a_bytes_u);
 #pragma unroll
         for (int bi = 0; bi < 4; ++bi)
           if (bi < nbox_b)
