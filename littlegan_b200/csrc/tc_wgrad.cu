@@ -11,8 +11,9 @@
 // reduces its 128 x NT fp32 tile into dW with 16-byte vector reductions (red.global.add.v4.f32),
 // where a thread owns a (tap,a) row and therefore contiguous b.
 //
-// One tile x one k-slice per CTA: warps 0-3 = epilogue, warp 5 = MMA issuer + TMEM owner, and TWO TMA producer
-// warps (4: the big-map boxes, 6: the small-map boxes).  A stage is 4-6 boxes of 8 KB against four MMAs, and one
+// One tile x one k-slice per CTA: warps 0-3 = epilogue, warp 5 = MMA issuer + TMEM owner, and THREE TMA producer
+// warps (4: the big-map boxes, 6 / 7: the even / odd small-map boxes; a fourth producer - big-map boxes split too,
+// MMA warp below the producers - was slower: 689 vs 950 TFLOP/s on enc2).  A stage is 4-6 boxes of 8 KB against four MMAs, and one
 // thread gets a wait / expect / TMA instruction out only every ~60-100 ns (scripts/ubench/tma_rows.cu: the per-SM
 // TMA rate doubles with a second issuing thread): with a single producer the N = 128 layers ran at the producer's
 // issue rate (6 instructions = ~350 ns per stage against ~190 ns of MMAs).
@@ -26,8 +27,9 @@
 
 namespace {
 
-constexpr int NUM_THREADS = 224;
-constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, PRODUCER_B_WARP = 6;   // epilogue = warps 0-3
+constexpr int NUM_THREADS = 256;
+constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, PRODUCER_B_WARP = 6;   // epilogue = warps 0-3; warps 6, 7: small-map boxes
+constexpr int NUM_PRODUCERS = 3;
 constexpr int MAX_STAGES = 8;
 constexpr int KP = 64;                   // positions per k-block
 constexpr int SMEM_BUDGET = 200 * 1024;
@@ -79,7 +81,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
   if (warp == PRODUCER_WARP && lane == 0) {
     tc::tma_prefetch_desc(&tmBig);
     tc::tma_prefetch_desc(&tmSmall);
-    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 2); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], NUM_PRODUCERS); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(tfull, 1);
     tc::fence_barrier_init();
   }
@@ -127,7 +129,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
         if (++pw == p.pbW) { pw = 0; if (++ph == p.pbH) { ph = 0; ++pn; } }
       }
     }
-  } else if (warp == PRODUCER_B_WARP) {
+  } else if (warp >= PRODUCER_B_WARP) {
+    // two threads share the small-map boxes of a stage (even / odd box index)
+    const int half = warp - PRODUCER_B_WARP;
+    const int mine = (nbox_b - half + 1) >> 1;
     if (num_kb > 0 && tc::elect_one()) {
       const uint32_t smem_u = tc::smem_u32(smem), full_u = tc::smem_u32(full), empty_u = tc::smem_u32(empty);
       const uint32_t stage_bytes_u = (uint32_t)p.stage_bytes, a_bytes_u = (uint32_t)p.a_bytes;
@@ -139,10 +144,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
         const uint32_t fb = full_u + (uint32_t)stage * 8u;
         const uint32_t sa = smem_u + (uint32_t)stage * stage_bytes_u;
         tc::mbar_wait_addr(empty_u + (uint32_t)stage * 8u, phase ^ 1);
-        tc::mbar_expect_tx_addr(fb, stage_bytes_u - a_bytes_u);
+        tc::mbar_expect_tx_addr(fb, (uint32_t)(mine * b_box_bytes));
 #pragma unroll
         for (int bi = 0; bi < 4; ++bi)
-          if (bi < nbox_b)
+          if (bi < nbox_b && (bi & 1) == half)
             tc::tma_load_4d_addr(sa + a_bytes_u + bi * b_box_bytes, &tmSmall, fb, b_ch0 + bi * p.b_blk, j0, i0, n0);
         if (++stage == nstages) { stage = 0; phase ^= 1; }
         if (++pw == p.pbW) { pw = 0; if (++ph == p.pbH) { ph = 0; ++pn; } }
