@@ -520,7 +520,11 @@ class EagerTrainer:
         dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
     def _train_step(self, batch_no, iterator, noise=None, new_image=None):
-        """eager_trainer.py:115-169.  `noise` / `new_image` may be injected for reproducible runs; by default
+        """eager_trainer.py:115-169.  Returns (True, fake_image, adj_image | None, gen_loss, disc_loss, adj_loss | None).
+        `fake_image` / `adj_image` are VIEWS of buffers the next step overwrites (the reference returns fresh tensors):
+        `.clone()` them to keep them across steps (`train()` writes its image dumps before the next step); the losses
+        are `LossValue` objects that stay valid.
+        `noise` / `new_image` may be injected for reproducible runs; by default
         noise ~ N(0,1) is drawn on the device and new_image is the reference's augmentation of real_image_1
         (eager_trainer.py:127-131: flip / brightness / contrast / hue / Gaussian noise, csrc/augment.cu) with
         device-side Philox draws; `augment: false` in the config makes new_image = real_image_1."""
