@@ -326,3 +326,57 @@ def test_oracle_trajectory_matches_tf():
             if b <= 10:
                 assert d < 0.01, (b, float(got), want)
     assert float(np.median(devs)) < 0.02
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers the bf16-mode parity tests rely on (tests/test_parity_bf16_gpu.py)
+# ------------------------------------------------------------------------------------------------
+def test_bf16_storage_emulation_rounds_value_and_gradient():
+    """`store="bf16"`: the stored map AND the gradient flowing back through it are rounded to bf16; the default
+    oracle is exact.  The emulation stays a small perturbation of the forward pass and leaves its structure alone."""
+    from tests.util import small_args
+    x = torch.tensor([1.0 + 2 ** -10, -3.3, 0.1], dtype=torch.float64, requires_grad=True)
+    y = O._RoundBF16.apply(x)
+    assert torch.equal(y.detach(), x.detach().to(torch.bfloat16).double())
+    g = torch.tensor([1.0 + 2 ** -10, 0.3, -7.77], dtype=torch.float64)
+    y.backward(g)
+    assert torch.equal(x.grad, g.to(torch.bfloat16).double())
+    x2 = torch.tensor([0.123456789], dtype=torch.float64, requires_grad=True)
+    z = O._RoundGradBF16.apply(x2)
+    assert torch.equal(z.detach(), x2.detach())                  # value untouched
+    z.backward(torch.tensor([0.123456789], dtype=torch.float64))
+    assert torch.equal(x2.grad, torch.tensor([0.123456789]).to(torch.bfloat16).double())
+
+    oargs, eargs = small_args(), small_args(store="bf16")
+    W = O.init_weights(oargs, 0)
+    i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=5)
+    t0, t1 = {}, {}
+    r0 = O.OracleTrainer(oargs, W, dtype=torch.float64).train_step(11, i1, c1, i2, c2, noise, taps=t0)
+    r1 = O.OracleTrainer(eargs, W, dtype=torch.float64).train_step(11, i1, c1, i2, c2, noise, taps=t1)
+    assert set(t0) == set(t1) and len(t0) >= 34
+    for k in ("gen_loss", "disc_loss", "adj_loss"):
+        assert 0 < abs(float(r0[k]) - float(r1[k])) < 1e-2 * abs(float(r0[k]))
+    for k in ("g_dec4", "dr_enc4", "a_dec4", "da_enc4"):
+        d = float((t0[k] - t1[k]).abs().max() / t0[k].abs().max())
+        assert 0 < d < 5e-2, (k, d)
+        # every stored map of the emulating oracle is bf16-representable
+        assert torch.equal(t1[k], t1[k].to(torch.bfloat16).to(t1[k].dtype))
+
+
+def test_forward_losses_equal_the_train_step_losses():
+    """OracleTrainer.forward_losses (forward only) reproduces the three losses of train_step and reports each
+    loss's scale = the sum of the absolute values of its terms."""
+    from tests.util import small_args
+    oargs = small_args(use_partition=True)
+    W = O.init_weights(oargs, 0)
+    ot = O.OracleTrainer(oargs, W, dtype=torch.float64)
+    for b in (3, 11):
+        i1, c1, i2, c2, noise = O.synthetic_batch(oargs, 4, seed=20 + b)
+        fl = ot.forward_losses(b, i1, c1, i2, c2, noise)
+        ref = ot.train_step(b, i1, c1, i2, c2, noise)
+        for k in ("gen", "disc", "adj"):
+            if ref[k + "_loss"] is None:
+                assert fl[k + "_loss"] is None and fl[k + "_scale"] is None
+                continue
+            assert abs(fl[k + "_loss"] - float(ref[k + "_loss"])) < 1e-12
+            assert fl[k + "_scale"] >= abs(fl[k + "_loss"]) - 1e-12
