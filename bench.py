@@ -415,7 +415,7 @@ def run_product(a):
         b += 1
         trainer._train_step(b, it)
     torch.cuda.synchronize()
-    graph = trainer._graphs[(True, None, True)][0]
+    graph = trainer._graphs[(True, None, True, True)][0]
     launches = K.launch_count_of_last_capture()
 
     # ---- device-resident timing: K replays of the captured step

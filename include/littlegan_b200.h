@@ -272,6 +272,14 @@ int lg_augment_apply(const float* x, const float* params, const float* noise, vo
 
 /* ---- casts ------------------------------------------------------------------------------- */
 int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+/* dst = src * scale + shift in fp32 arithmetic (dtypes LG_F32 / LG_BF16 each side): the in-step copies and the
+ * adjuster's input condition (cond + 1) * 0.5 (eager_trainer.py:155). */
+int lg_scale_shift(const void* src, void* dst, int64_t n, float scale, float shift, int src_dtype, int dst_dtype,
+                   void* stream);
+/* out[0..n) ~ N(0, 1) fp32 (the generator noise, eager_trainer.py:125 tf.random.normal) from Philox4x32-10.
+ * state: device uint64[3] = {seed, step, 0}; the launch advances `step` on the device (CUDA-graph replayable);
+ * out 16-byte aligned. */
+int lg_normal_fill(float* out, int64_t n, void* state, void* stream);
 /* data_rescale (utils.py:51-52, applied by dataset.py:29 to every decoded image): dst[i] = src[i] / 127.5 - 1 for
  * n decoded image bytes; dst fp32 or bf16 (dst_dtype).  Both pointers 16-byte aligned.  Replaces the host-side
  * tf.cast + tf.divide + tf.subtract of the input pipeline: the batch crosses PCIe as bytes. */

@@ -61,6 +61,8 @@ SIGNATURES = {
     "lg_augment_prepare": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
     "lg_augment_apply": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "lg_cast": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    "lg_scale_shift": (_i, [_vp, _vp, _i64, _f, _f, _i, _i, _vp]),
+    "lg_normal_fill": (_i, [_vp, _i64, _vp, _vp]),
     "lg_u8_rescale": (_i, [_vp, _vp, _i64, _i, _vp]),
     "lg_conv2d_bn_relu": (_i, [_vp] * 6 + [_i] * 16 + [_vp]),
     "lg_pack_conv_bn_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -166,7 +166,52 @@ __global__ void __launch_bounds__(AT) augment_apply_kernel(const float* __restri
   }
 }
 
+// out[i] ~ N(0, 1): Philox4x32-10(seed, subsequence = thread, offset = 4 * calls-per-thread * step), four values per
+// thread and pass; the step counter lives on the device and advances inside the launch (CUDA-graph replayable).
+__global__ void __launch_bounds__(256) normal_fill_kernel(float* __restrict__ out, int64_t n, unsigned long long* state) {
+  const unsigned long long seed = state[0], step = state[1];
+  const int64_t nthreads = (int64_t)gridDim.x * 256;
+  const int64_t gid = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t per = (n + 4 * nthreads - 1) / (4 * nthreads);          // float4 draws per thread and launch
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (2ull << 32) + (unsigned long long)gid, 4ull * (unsigned long long)per * step, &st);
+  for (int64_t q = 0; q < per; ++q) {
+    const int64_t e = (q * nthreads + gid) * 4;
+    const float4 g = curand_normal4(&st);
+    if (e + 3 < n) *reinterpret_cast<float4*>(out + e) = g;
+    else {
+      if (e < n) out[e] = g.x;
+      if (e + 1 < n) out[e + 1] = g.y;
+      if (e + 2 < n) out[e + 2] = g.z;
+    }
+  }
+  // every thread has read the step by the time the LAST CTA increments it: a separate tiny launch would be
+  // simpler, a grid-wide ticket keeps it one launch
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long done = atomicAdd(&state[2], 1ull);
+    last = done == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) { state[2] = 0ull; state[1] = step + 1ull; }
+}
+
 }  // namespace
+
+// Standard-normal fill of a fp32 buffer (the generator noise of eager_trainer.py:125: tf.random.normal).
+// state: device uint64[3] = {seed, step, 0}; the launch advances `step`.
+extern "C" int lg_normal_fill(float* out, int64_t n, void* state, void* stream) {
+  LG_REQUIRE(out && state && n > 0, "bad arguments");
+  LG_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+  int64_t need = (n / 4 + 255) / 256;
+  int64_t cap = (int64_t)lg_num_sms() * 4;
+  const unsigned grid = (unsigned)(need < 1 ? 1 : (need < cap ? need : cap));
+  normal_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, (unsigned long long*)state);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
 
 extern "C" int lg_augment_prepare(const float* x, int N, int H, int W, void* state, float* params, float max_brightness,
                                   float contrast_lo, float contrast_hi, float max_hue, int draw, void* stream) {

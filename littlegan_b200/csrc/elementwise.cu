@@ -479,6 +479,14 @@ __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = from_f<D>(to_f(s[i]));
 }
 
+// d = s * scale + shift (fp32 arithmetic): copies, casts and the adjuster's (cond + 1) / 2 (eager_trainer.py:155)
+template <typename S, typename D>
+__global__ void scale_shift_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n, float scale, float shift) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    d[i] = from_f<D>(fmaf(to_f(s[i]), scale, shift));
+}
+
 // data_rescale of utils.py:51-52 on decoded image bytes: y = x / 127.5 - 1 (fp32 division, then the subtraction,
 // each rounded once as TF's two ops are), 16 pixels-bytes per thread
 template <typename D>
@@ -889,6 +897,21 @@ extern "C" int lg_cast(const void* src, void* dst, int64_t n, int src_dtype, int
   else if (src_dtype == LG_BF16 && dst_dtype == LG_F32) cast_kernel<bf16, float><<<gsz, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
   else if (src_dtype == LG_F32 && dst_dtype == LG_F32) cast_kernel<float, float><<<gsz, 256, 0, st>>>((const float*)src, (float*)dst, n);
   else cast_kernel<bf16, bf16><<<gsz, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  LG_LAUNCH_CHECK();
+  return LG_OK;
+}
+
+extern "C" int lg_scale_shift(const void* src, void* dst, int64_t n, float scale, float shift, int src_dtype,
+                              int dst_dtype, void* stream) {
+  LG_REQUIRE(src && dst && n > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t need = (n + 255) / 256;
+  int64_t cap = (int64_t)lg_num_sms() * 16;
+  int gsz = (int)(need < cap ? need : cap);
+  if (src_dtype == LG_F32 && dst_dtype == LG_BF16) scale_shift_kernel<float, bf16><<<gsz, 256, 0, st>>>((const float*)src, (bf16*)dst, n, scale, shift);
+  else if (src_dtype == LG_BF16 && dst_dtype == LG_F32) scale_shift_kernel<bf16, float><<<gsz, 256, 0, st>>>((const bf16*)src, (float*)dst, n, scale, shift);
+  else if (src_dtype == LG_F32 && dst_dtype == LG_F32) scale_shift_kernel<float, float><<<gsz, 256, 0, st>>>((const float*)src, (float*)dst, n, scale, shift);
+  else scale_shift_kernel<bf16, bf16><<<gsz, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n, scale, shift);
   LG_LAUNCH_CHECK();
   return LG_OK;
 }

@@ -111,7 +111,7 @@ class EagerTrainer:
         self._graphs = {}
         self._seen = set()
         self._pool = None
-        self._noise_gen = None
+        self._noise_state = None                 # {seed, step, ticket} of the generator-noise Philox stream (device)
         self._comm_stream = None
         self._reduced = []                       # this step's buckets in issue order: (optimiser, lo, hi, event)
         self._chain_streams = {}
@@ -244,8 +244,9 @@ class EagerTrainer:
         return self.discriminator.encoder.convs + self.generator.decoder.convs + [self.generator.conv]
 
     def _prepare_inputs(self, S, aug):
-        """Casts / concatenations of the step inputs (part of the captured step).  aug: new_image is the
-        reference's augmentation of real_image_1 (eager_trainer.py:127-131) instead of the staged `in_new`."""
+        """Casts / concatenations of the step inputs (part of the captured step; this library's kernels only).
+        aug: new_image is the reference's augmentation of real_image_1 (eager_trainer.py:127-131) instead of the
+        staged `in_new`."""
         B = self.args.batch_size
         if aug:
             if self._aug_state is None:
@@ -256,14 +257,14 @@ class EagerTrainer:
             K.cast(S["in_new"], S["img3"][B:2 * B])
         K.cast(S["in_img2"], S["img2"])
         K.cast(S["in_img1"], S["real1"])
-        S["aimg_t"][:B].copy_(S["img2"])
-        S["aimg_t"][B:].copy_(S["real1"])
-        # eager_trainer.py:155-156
-        S["acond_t"][:B].copy_(S["cond2"])
-        S["acond_t"][B:].copy_(S["cond1"])
-        torch.add(S["acond_t"], 1.0, out=S["acond_in"]).mul_(0.5)
+        K.cast(S["in_img2"], S["aimg_t"][:B])                # adj_target_image = [real_image_2 ; real_image_1]
+        K.cast(S["in_img1"], S["aimg_t"][B:])
+        # eager_trainer.py:155-156: adj_target_cond = [cond_2 ; cond_1], adj_input_cond = (adj_target_cond + 1) * 0.5
+        K.scale_shift(S["cond2"], S["acond_t"][:B])
+        K.scale_shift(S["cond1"], S["acond_t"][B:])
+        K.scale_shift(S["acond_t"], S["acond_in"], 0.5, 0.5)
 
-    def _step_body(self, S, adj_on, batch_no, aug=False):
+    def _step_body(self, S, adj_on, batch_no, aug=False, draw_noise=False):
         a, rt = self.args, self.rt
         B = a.batch_size
         G, D, A = self.generator, self.discriminator, self.adjuster
@@ -281,6 +282,13 @@ class EagerTrainer:
             self._prepare_inputs(S, aug)
         rt.begin_step()
         E.refresh_packs(rt, self._conv_layers())
+        if draw_noise:
+            # the generator noise ~ N(0,1) (eager_trainer.py:125) is drawn inside the step, on the device, from a
+            # Philox stream whose step counter advances inside the launch: every replay of the graph draws anew
+            if self._noise_state is None:
+                rank = _dist().get_rank() if _dist() is not None else 0
+                self._noise_state = K.normal_state(int(getattr(a, "seed", 0)) * 1000003 + rank, rt.device)
+            K.normal_fill(S["noise"], self._noise_state)
 
         # ---- forward: G, and the encoder on [real_image_1 | new_image | fake] (eager_trainer.py:134-137, 157-160).
         # The real part of that batch does not depend on G: its encoder pass runs on a side stream while the
@@ -484,14 +492,14 @@ class EagerTrainer:
             grp = (batch_no // (a.partition_interval + 1)) % 3
         return adj_on, grp
 
-    def _run_step(self, S, batch_no, aug=False):
+    def _run_step(self, S, batch_no, aug=False, draw_noise=False):
         adj_on, grp = self._variant(batch_no)
-        key = (adj_on, grp, aug)
+        key = (adj_on, grp, aug) if not draw_noise else (adj_on, grp, aug, True)
         use_graph = bool(getattr(self.args, "cuda_graph", True))
         if not use_graph or key not in self._seen:
             # first occurrence of a variant runs eagerly (it also warms up lazy state before capture)
             self._seen.add(key)
-            self._step_body(S, adj_on, batch_no, aug)
+            self._step_body(S, adj_on, batch_no, aug, draw_noise)
             return
         g = self._graphs.get(key)
         if g is None:
@@ -501,7 +509,7 @@ class EagerTrainer:
                 self._pool = torch.cuda.graph_pool_handle()
             n0 = K.launch_count()
             with torch.cuda.graph(g, pool=self._pool):
-                self._step_body(S, adj_on, batch_no, aug)
+                self._step_body(S, adj_on, batch_no, aug, draw_noise)
             K.note_capture(K.launch_count() - n0)
             self._graphs[key] = (g, S["adj"], None if self.taps is None else dict(self.taps))
         g, adj, taps = self._graphs[key]
@@ -552,16 +560,10 @@ class EagerTrainer:
         aug = new_image is None and bool(getattr(a, "augment", True))
         if not aug:
             self._to_static(S["in_new"], real_image_1 if new_image is None else new_image)
-        if noise is None:
-            if self._noise_gen is None:
-                self._noise_gen = torch.Generator(device=self.rt.device)
-                rank = _dist().get_rank() if _dist() is not None else 0
-                self._noise_gen.manual_seed(int(getattr(a, "seed", 0)) * 1000003 + rank)
-            S["noise"].normal_(generator=self._noise_gen)
-        else:
+        if noise is not None:
             self._to_static(S["noise"], noise)
         adj_on, _ = self._variant(batch_no)
-        self._run_step(S, batch_no, aug)
+        self._run_step(S, batch_no, aug, draw_noise=noise is None)
         B = a.batch_size
         losses = self._read_back(S["loss"].clone())
         fake_image = S["fake"]

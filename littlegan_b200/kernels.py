@@ -395,6 +395,30 @@ def cast(src, dst):
     return dst
 
 
+def scale_shift(src, dst, scale=1.0, shift=0.0):
+    """dst = src * scale + shift (fp32 arithmetic; fp32 / bf16 either side).  scale 1, shift 0 = a device copy."""
+    _cuda(src, dst)
+    if src.numel() != dst.numel():
+        raise _lib.LittleGANError("scale_shift: size mismatch")
+    check(_lib.load().lg_scale_shift(_p(src), _p(dst), src.numel(), float(scale), float(shift), dt(src), dt(dst),
+                                     _st()), "lg_scale_shift")
+    return dst
+
+
+def normal_state(seed, device):
+    """{seed, step, ticket} of lg_normal_fill's Philox stream, on the device."""
+    return torch.tensor([int(seed), 0, 0], dtype=torch.int64, device=device)
+
+
+def normal_fill(out, state):
+    """out (fp32, CUDA) ~ N(0, 1); advances state[1] on the device."""
+    _cuda(out, state)
+    if out.dtype != torch.float32:
+        raise _lib.LittleGANError("normal_fill: needs an fp32 buffer")
+    check(_lib.load().lg_normal_fill(_p(out), out.numel(), _p(state), _st()), "lg_normal_fill")
+    return out
+
+
 def u8_rescale(src, dst):
     """data_rescale (utils.py:51-52) of decoded image bytes on the device: dst = src / 127.5 - 1."""
     _cuda(src, dst)

@@ -34,7 +34,7 @@ it = DevicePrefetcher(data.get_new_iterator(), depth=4)
 for b in range(12, 17):
     trainer._train_step(b, it)
 torch.cuda.synchronize()
-graph = trainer._graphs[(True, None, True)][0]
+graph = trainer._graphs[(True, None, True, True)][0]
 steps = 4
 if world > 1:
     dist.barrier()

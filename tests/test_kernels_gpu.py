@@ -799,3 +799,34 @@ def test_frechet_distance_matches_scipy(d, n1, n2):
     R, tr, iters = fid._sqrtm_psd(torch.from_numpy(s1).cuda())
     assert iters < fid._NS_MAX_ITERS
     assert float((R @ R - torch.from_numpy(s1).cuda()).abs().max()) < 1e-9 * np.abs(s1).max()
+
+
+def test_scale_shift_and_normal_fill():
+    """The in-step copies / (cond + 1) / 2 (eager_trainer.py:155) and the generator noise (eager_trainer.py:125) on
+    this library's own kernels."""
+    from littlegan_b200 import kernels as K
+    x = _rand((7, 41), 90, torch.float32)
+    for ddt in DTYPES:
+        out = torch.empty(7, 41, dtype=ddt, device="cuda")
+        K.scale_shift(x.cuda(), out, 0.5, 0.5)
+        ref = (x * 0.5 + 0.5).to(ddt)
+        assert torch.equal(out.cpu(), ref)
+    out = torch.empty(7, 41, device="cuda")
+    K.scale_shift(x.cuda(), out)
+    assert torch.equal(out.cpu(), x)
+    # N(0,1): moments, reproducible from (seed, step), different at every step, any length (vector tail)
+    for n in (64 * 93, 1000003, 5):
+        st = K.normal_state(1234, "cuda")
+        a = K.normal_fill(torch.empty(n, device="cuda"), st).clone()
+        assert int(st[1]) == 1 and int(st[2]) == 0
+        b = K.normal_fill(torch.empty(n, device="cuda"), st).clone()
+        assert int(st[1]) == 2
+        st2 = K.normal_state(1234, "cuda")
+        a2 = K.normal_fill(torch.empty(n, device="cuda"), st2)
+        assert torch.equal(a, a2) and not torch.equal(a, b)
+        if n > 1000:
+            for t in (a, b):
+                assert abs(float(t.mean())) < 4.0 / n ** 0.5 and abs(float(t.std()) - 1.0) < 4.0 / n ** 0.5
+                assert abs(float((t ** 4).mean()) - 3.0) < 0.2
+            assert abs(float((a * b).mean())) < 4.0 / n ** 0.5
+            assert abs(float((a[:-1] * a[1:]).mean())) < 4.0 / n ** 0.5
