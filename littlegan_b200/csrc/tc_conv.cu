@@ -336,11 +336,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         } else {
-          for (int e = 0; e < 16 && chb + e < p.Nch; ++e) {
-            float a = v[e] + sbias[chb + e];
-            s1 += a; s2 += a * a;
-            if (p.act == LG_ACT_TANH) a = tanhf(a);
-            if (valid) orow[chb + e] = __float2bfloat16_rn(a);
+          // channel tail (Nch not a multiple of 16 / 8): fully unrolled with constant indices - a run-time index
+          // into v[] forces the whole array into LOCAL memory (4 STL.128 per chunk and thread on every path)
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            if (chb + e < p.Nch) {
+              float a = v[e] + sbias[chb + e];
+              s1 += a; s2 += a * a;
+              if (p.act == LG_ACT_TANH) a = tanhf(a);
+              if (valid) orow[chb + e] = __float2bfloat16_rn(a);
+            }
           }
         }
       }

@@ -11,7 +11,15 @@
 // Shared-memory traffic per tile drops from 25 to 9 activation tiles and the tile count by 4x, which is
 // what bounds these layers (operand bytes through smem, not MMA issue).
 //
-// Warp roles as in tc_conv.cu: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer + TMEM owner.
+// Round 2: a pipeline stage is one SHIFT with up to two channel chunks (9 stages per tile for 128 input channels
+// instead of 18: the kernel was bound by the latency of its stage hand-shakes - knock-outs in profiles/r2_ubench.txt -
+// not by bandwidth or MMA issue), its boxes are issued by THREE producer threads (one thread gets a TMA instruction
+// out only every ~60-100 ns), and the taps of a shift - which feed DIFFERENT output phases - are ONE tcgen05.mma whose
+// N spans their accumulators (9 instead of 25 MMAs per k-step; an MMA re-reads its 128-row A operand from shared
+// memory whatever N is).
+//
+// Warp roles: warps 0-3 epilogue, warp 5 MMA issuer + TMEM owner, warp 4 activation-tile producer, warps 6 / 7
+// weight-tile producers (even / odd tile slot).
 #include <cuda.h>
 #include <stdio.h>
 
@@ -23,8 +31,9 @@
 
 namespace {
 
-constexpr int NUM_THREADS = 192;
-constexpr int PRODUCER_WARP = 4, MMA_WARP = 5;
+constexpr int NUM_THREADS = 256;
+constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, WPROD_WARP0 = 6;
+constexpr int NUM_PRODUCERS = 3;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
@@ -34,6 +43,7 @@ struct D4Params {
   int BW, BH, BN, lg_tw, lg_th;  // 128-position tile box in small-map coordinates
   int total_tiles;
   int a_bytes, b_bytes, stage_bytes, stages, nacc;   // nacc = 2 (double-buffered accumulator sets) or 1
+  int cps;                                           // channel chunks per pipeline stage (1 or 2)
   int act;
   const float* bias;
   bf16* out;
@@ -44,6 +54,23 @@ struct D4Params {
 __device__ __forceinline__ int shift_d(int u) { return 1 - u; }
 __device__ __forceinline__ int shift_ntaps(int u) { return u == 0 ? 1 : 2; }
 __device__ __forceinline__ int shift_tap(int u, int i) { return u == 0 ? 0 : 2 * u - 1 + i; }
+
+// Accumulator order in TMEM: phases 1, 3, 2, 0 (column = d4_pos(ph) * NT).  That makes the phase set of every shift
+// contiguous - {1,3,2,0} for the four 4-tap shifts (N = 4 NT), {1,3} / {3,2} for the 2-tap shifts (N = 2 NT), {3} for
+// shift (+1,+1) - so the taps of a shift are one MMA.  The 4-tap shift (0,0) goes first: it writes all four phases,
+// so one accumulate flag serves every MMA of the tile.
+__device__ __forceinline__ int d4_pos(int ph) { return (0x1203 >> (4 * ph)) & 0xF; }
+__device__ __forceinline__ int d4_phase(int ky, int kx) { return ((ky + 1) & 1) * 2 + ((kx + 1) & 1); }
+__device__ __forceinline__ int d4_shift(int o) { return o == 0 ? 4 : (o <= 4 ? o - 1 : o); }   // 4,0,1,2,3,5,6,7,8
+__device__ __forceinline__ int d4_min_pos(int uy, int ux) {       // first accumulator position of the shift
+  int m = 4;
+  for (int iy = 0; iy < shift_ntaps(uy); ++iy)
+    for (int ix = 0; ix < shift_ntaps(ux); ++ix) {
+      const int q = d4_pos(d4_phase(shift_tap(uy, iy), shift_tap(ux, ix)));
+      m = q < m ? q : m;
+    }
+  return m;
+}
 
 template <bool NB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -67,7 +94,7 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == PRODUCER_WARP && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
-    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], NUM_PRODUCERS); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 4); }
     tc::fence_barrier_init();
   }
@@ -84,7 +111,13 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t stage_bytes_u = (uint32_t)p.stage_bytes, a_bytes_u = (uint32_t)p.a_bytes, b_bytes_u = (uint32_t)p.b_bytes;
   const int nstages = p.stages, KCc = p.KC, nacc = p.nacc;
 
-  if (warp == PRODUCER_WARP) {
+  const int cps = p.cps, groups = kc_per_tap / p.cps;          // chunk groups per shift
+  const uint32_t chunk_w_bytes = 4u * b_bytes_u;                 // weight-tile area of one chunk: 4 slots
+  if (warp == PRODUCER_WARP || warp >= WPROD_WARP0) {
+    // role 0: the activation tiles of every stage; role 1 / 2: the weight tiles in even / odd slot (slot = accumulator
+    // position relative to the shift's first).  Every producer waits for the stage, announces its own byte count on
+    // the full barrier (count 3) and issues its boxes.
+    const int role = warp == PRODUCER_WARP ? 0 : 1 + (warp - WPROD_WARP0);
     if (tc::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -92,41 +125,57 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int th = (t >> p.lg_tw) & ((1 << p.lg_th) - 1);
         const int n0 = (t >> (p.lg_tw + p.lg_th)) * p.BN;
         const int i0 = th * p.BH, j0 = tw * p.BW;
-        for (int uy = 0; uy < 3; ++uy) {
-          for (int ux = 0; ux < 3; ++ux) {
-            const int nyt = shift_ntaps(uy), nxt = shift_ntaps(ux);
-            for (int kc = 0; kc < kc_per_tap; ++kc) {
-              const uint32_t fb = full_u32 + (uint32_t)stage * 8u;
-              const uint32_t sa = smem_u32 + (uint32_t)stage * stage_bytes_u;
-              tc::mbar_wait_addr(empty_u32 + (uint32_t)stage * 8u, phase ^ 1);
-              tc::mbar_expect_tx_addr(fb, a_bytes_u + (uint32_t)(nyt * nxt) * b_bytes_u);
-              tc::tma_load_4d_addr(sa, &tmA, fb, kc * KCc, j0 + shift_d(ux), i0 + shift_d(uy), n0);
-              uint32_t sb = sa + a_bytes_u;
+        for (int o = 0; o < 9; ++o) {
+          const int sh = d4_shift(o), uy = sh / 3, ux = sh - 3 * uy;
+          const int nyt = shift_ntaps(uy), nxt = shift_ntaps(ux);
+          const int pos0 = d4_min_pos(uy, ux);
+          int mine = 0;                                           // this producer's weight tiles per chunk
 #pragma unroll
-              for (int iy = 0; iy < 2; ++iy) {
+          for (int iy = 0; iy < 2; ++iy)
 #pragma unroll
-                for (int ix = 0; ix < 2; ++ix) {
-                  if (iy < nyt && ix < nxt) {
-                    const int tap = shift_tap(uy, iy) * 5 + shift_tap(ux, ix);
-                    tc::tma_load_3d_addr(sb, &tmB, fb, kc * KCc, 0, tap);
-                    sb += b_bytes_u;
-                  }
-                }
+            for (int ix = 0; ix < 2; ++ix)
+              if (iy < nyt && ix < nxt)
+                mine += (((d4_pos(d4_phase(shift_tap(uy, iy), shift_tap(ux, ix))) - pos0) & 1) == role - 1);
+          for (int g = 0; g < groups; ++g) {
+            const uint32_t fb = full_u32 + (uint32_t)stage * 8u;
+            const uint32_t sa = smem_u32 + (uint32_t)stage * stage_bytes_u;
+            const uint32_t sw = sa + (uint32_t)cps * a_bytes_u;
+            tc::mbar_wait_addr(empty_u32 + (uint32_t)stage * 8u, phase ^ 1);
+            if (role == 0) {
+              tc::mbar_expect_tx_addr(fb, (uint32_t)cps * a_bytes_u);
+              for (int cc = 0; cc < cps; ++cc)
+                tc::tma_load_4d_addr(sa + (uint32_t)cc * a_bytes_u, &tmA, fb, (g * cps + cc) * KCc, j0 + shift_d(ux),
+                                     i0 + shift_d(uy), n0);
+            } else {
+              tc::mbar_expect_tx_addr(fb, (uint32_t)(cps * mine) * b_bytes_u);
+              for (int cc = 0; cc < cps; ++cc) {
+#pragma unroll
+                for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+                  for (int ix = 0; ix < 2; ++ix)
+                    if (iy < nyt && ix < nxt) {
+                      const int ky = shift_tap(uy, iy), kx = shift_tap(ux, ix);
+                      const int slot = d4_pos(d4_phase(ky, kx)) - pos0;
+                      if ((slot & 1) == role - 1)
+                        tc::tma_load_3d_addr(sw + (uint32_t)cc * chunk_w_bytes + (uint32_t)slot * b_bytes_u, &tmB, fb,
+                                             (g * cps + cc) * KCc, 0, ky * 5 + kx);
+                    }
               }
-              if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == MMA_WARP) {
     if (tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc(128, p.NT, 0, 0);
+      const uint32_t idesc1 = tc::make_idesc(128, p.NT, 0, 0), idesc2 = tc::make_idesc(128, 2 * p.NT, 0, 0),
+                     idesc4 = tc::make_idesc(128, 4 * p.NT, 0, 0);
       const uint32_t layout = (KCc == 64) ? 2u : 4u;
       const uint32_t sbo = 8u * (uint32_t)KCc * 2u;
       const uint32_t desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
       const uint32_t desc_lo0 = ((smem_u32 & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t stage_units = stage_bytes_u >> 4, a_units = a_bytes_u >> 4, b_units = b_bytes_u >> 4;
+      const uint32_t stage_units = stage_bytes_u >> 4, a_units = a_bytes_u >> 4, cw_units = chunk_w_bytes >> 4;
       const int ksteps = KCc / 16;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -134,36 +183,26 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc::mbar_wait_addr(tc::smem_u32(&tempty[acc]), acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t d_set = tmem_base + (uint32_t)(acc * set_cols);
-        uint32_t started = 0;                                       // bit ph: accumulator ph already written
-        for (int uy = 0; uy < 3; ++uy) {
-          for (int ux = 0; ux < 3; ++ux) {
-            const int nyt = shift_ntaps(uy), nxt = shift_ntaps(ux);
-            for (int kc = 0; kc < kc_per_tap; ++kc) {
-              tc::mbar_wait_addr(full_u32 + (uint32_t)stage * 8u, phase);
-              tc::fence_after_sync();
-              const uint32_t a_lo = desc_lo0 + (uint32_t)stage * stage_units;
-              uint32_t b_lo = a_lo + a_units;
-#pragma unroll
-              for (int iy = 0; iy < 2; ++iy) {
-#pragma unroll
-                for (int ix = 0; ix < 2; ++ix) {
-                  if (iy < nyt && ix < nxt) {
-                    const int ky = shift_tap(uy, iy), kx = shift_tap(ux, ix);
-                    const int ph = ((ky + 1) & 1) * 2 + ((kx + 1) & 1);          // output phase of this tap
-                    const uint32_t d_tmem = d_set + (uint32_t)(ph * p.NT);
-                    uint32_t accum = (started >> ph) & 1u;
-                    for (int k = 0; k < ksteps; ++k) {
-                      tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum);
-                      accum = 1;
-                    }
-                    started |= 1u << ph;
-                    b_lo += b_units;
-                  }
-                }
+        uint32_t accum = 0;                                         // the first shift writes all four phases
+        for (int o = 0; o < 9; ++o) {
+          const int sh = d4_shift(o), uy = sh / 3, ux = sh - 3 * uy;
+          const int ntiles = shift_ntaps(uy) * shift_ntaps(ux);
+          const uint32_t idesc = ntiles == 4 ? idesc4 : ntiles == 2 ? idesc2 : idesc1;
+          const uint32_t d_tmem = d_set + (uint32_t)(d4_min_pos(uy, ux) * p.NT);
+          for (int g = 0; g < groups; ++g) {
+            tc::mbar_wait_addr(full_u32 + (uint32_t)stage * 8u, phase);
+            tc::fence_after_sync();
+            const uint32_t a_lo0 = desc_lo0 + (uint32_t)stage * stage_units;
+            const uint32_t b_lo0 = a_lo0 + (uint32_t)cps * a_units;
+            for (int cc = 0; cc < cps; ++cc) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)cc * a_units, b_lo = b_lo0 + (uint32_t)cc * cw_units;
+              for (int k = 0; k < ksteps; ++k) {
+                tc::mma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, accum);
+                accum = 1;
               }
-              tc::mma_commit_addr(empty_u32 + (uint32_t)stage * 8u);
-              if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
+            tc::mma_commit_addr(empty_u32 + (uint32_t)stage * 8u);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
         tc::mma_commit(&tfull[acc]);
@@ -223,7 +262,7 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int cb = 16 * c;
             if (cb < p.NT) {
               float v[16];
-              tc::tmem_ld16(taddr + ph * p.NT + cb, v);
+              tc::tmem_ld16(taddr + d4_pos(ph) * p.NT + cb, v);
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] += sbias[cb + e];
               uint32_t pk[8];
@@ -242,7 +281,7 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bf16* orow = obase + ((int64_t)(ph >> 1) * p.Wb + (ph & 1)) * p.Nch;
         for (int cb = 0; cb < p.NT; cb += 16) {
           float v[16];
-          tc::tmem_ld16(taddr + ph * p.NT + cb, v);
+          tc::tmem_ld16(taddr + d4_pos(ph) * p.NT + cb, v);
           if (cb >= p.Nch) continue;
           if (cb + 16 <= p.Nch && vec_ok) {
             uint32_t pk[8];
@@ -261,11 +300,14 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
           } else {
-            for (int e = 0; e < 16 && cb + e < p.Nch; ++e) {
-              float a = v[e] + sbias[cb + e];
-              s1 += a; s2 += a * a;
-              if (p.act == LG_ACT_TANH) a = tanhf(a);
-              if (valid) orow[cb + e] = __float2bfloat16_rn(a);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {                   // constant indices: no local-memory copy of v[]
+              if (cb + e < p.Nch) {
+                float a = v[e] + sbias[cb + e];
+                s1 += a; s2 += a * a;
+                if (p.act == LG_ACT_TANH) a = tanhf(a);
+                if (valid) orow[cb + e] = __float2bfloat16_rn(a);
+              }
             }
           }
         }
@@ -317,7 +359,10 @@ bool plan_d4(int Nimg, int Hb, int Wb, int A, int B, D4Params* p) {
   p->total_tiles = tilesW * tilesH * tilesN;
   p->a_bytes = 128 * p->KC * 2;
   p->b_bytes = p->NT * p->KC * 2;
-  p->stage_bytes = p->a_bytes + 4 * p->b_bytes;
+  const int kc_per_tap = B / p->KC;
+  p->cps = (kc_per_tap % 2 == 0) ? 2 : 1;
+  p->stage_bytes = p->cps * (p->a_bytes + 4 * p->b_bytes);
+  if (SMEM_BUDGET / p->stage_bytes < 2) { p->cps = 1; p->stage_bytes = p->a_bytes + 4 * p->b_bytes; }
   int st = SMEM_BUDGET / p->stage_bytes;
   p->stages = st > MAX_STAGES ? MAX_STAGES : st;
   if (p->stages < 2) return false;
