@@ -246,6 +246,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;                       // row of the tile == TMEM lane
     const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
     const bool vec_ok = (p.Nch & 7) == 0;
+    const uint32_t sbias_u32 = tc::smem_u32(sbias);
     // column range of this warp: half of the tile when that is a whole number of 16-column chunks
     const int half = warp >> 2;
     const bool split = (p.NT & 31) == 0;
@@ -300,8 +301,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (cb < col0 + ncol) {
               float v[16];
               tc::tmem_ld16(taddr + cb, v);
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] += sbias[ch0 + cb + e];
+              tc::add_bias16(v, sbias_u32, ch0 + cb);
               uint32_t pk[8];
               nb_chunk(v, zc.v[2 * c], zc.v[2 * c + 1], coef, nb.alpha, s1, s2, pk);
               if (valid) {
@@ -319,12 +319,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::tmem_ld16(taddr + cb, v);
         const int chb = ch0 + cb;
         if (chb >= p.Nch) continue;                       // channel padding (uniform over the CTA)
+        tc::add_bias16(v, sbias_u32, chb);
         if (chb + 16 <= p.Nch && vec_ok) {
           uint32_t pk[8];
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
-            float a = v[e] + sbias[chb + e];
-            float b = v[e + 1] + sbias[chb + e + 1];
+            float a = v[e];
+            float b = v[e + 1];
             s1 += a + b; s2 += a * a + b * b;
             if (p.act == LG_ACT_TANH) { a = tanhf(a); b = tanhf(b); }
             __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -341,7 +342,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             if (chb + e < p.Nch) {
-              float a = v[e] + sbias[chb + e];
+              float a = v[e];
               s1 += a; s2 += a * a;
               if (p.act == LG_ACT_TANH) a = tanhf(a);
               if (valid) orow[chb + e] = __float2bfloat16_rn(a);

@@ -215,6 +215,7 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
     const bool vec_ok = (p.Nch & 7) == 0;
+    const uint32_t sbias_u32 = tc::smem_u32(sbias);
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int tw = t & ((1 << p.lg_tw) - 1);
@@ -263,8 +264,7 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (cb < p.NT) {
               float v[16];
               tc::tmem_ld16(taddr + d4_pos(ph) * p.NT + cb, v);
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] += sbias[cb + e];
+              tc::add_bias16(v, sbias_u32, cb);
               uint32_t pk[8];
               nb_chunk(v, zc.v[2 * c], zc.v[2 * c + 1], coef, nb.alpha, s1, s2, pk);
               if (valid) {
@@ -283,12 +283,13 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[16];
           tc::tmem_ld16(taddr + d4_pos(ph) * p.NT + cb, v);
           if (cb >= p.Nch) continue;
+          tc::add_bias16(v, sbias_u32, cb);
           if (cb + 16 <= p.Nch && vec_ok) {
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 16; e += 2) {
-              float a = v[e] + sbias[cb + e];
-              float b = v[e + 1] + sbias[cb + e + 1];
+              float a = v[e];
+              float b = v[e + 1];
               s1 += a + b; s2 += a * a + b * b;
               if (p.act == LG_ACT_TANH) { a = tanhf(a); b = tanhf(b); }
               __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -303,7 +304,7 @@ tc_dgrad4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int e = 0; e < 16; ++e) {                   // constant indices: no local-memory copy of v[]
               if (cb + e < p.Nch) {
-                float a = v[e] + sbias[cb + e];
+                float a = v[e];
                 s1 += a; s2 += a * a;
                 if (p.act == LG_ACT_TANH) a = tanhf(a);
                 if (valid) orow[cb + e] = __float2bfloat16_rn(a);

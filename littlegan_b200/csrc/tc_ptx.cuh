@@ -176,6 +176,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// v[16] += bias[cb .. cb+15]: the bias table lives in shared memory behind a generic pointer, which made every read a
+// generic LD.E (15% of the epilogue's stall samples); read it through the shared window, 16 bytes at a time
+__device__ __forceinline__ void add_bias16(float (&v)[16], uint32_t sbias_u32, int cb) {
+#pragma unroll
+  for (int e = 0; e < 16; e += 4) {
+    const float4 b = lds_v4(sbias_u32 + 4u * (uint32_t)(cb + e));
+    v[e] += b.x; v[e + 1] += b.y; v[e + 2] += b.z; v[e + 3] += b.w;
+  }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
