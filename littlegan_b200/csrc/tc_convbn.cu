@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const uint32_t sscale_u32 = tc::smem_u32(sscale), sshift_u32 = tc::smem_u32(sshift);
     int acc = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = p.n_tiles == 1 ? t : cb_div(t, p.nt_mul, p.nt_shr), nt = t - mt * p.n_tiles;
@@ -249,13 +250,18 @@ __global__ void __launch_bounds__(THREADS, 1) convbn_kernel(const CBParams p) {
         float v[16];
         tc::tmem_ld16(taddr + cb, v);                          // warp-collective: every lane, also past the M tail
         uint32_t pk[8];
+        // folded-BN scale / shift from shared memory through the shared window, 16 bytes at a time (behind the generic
+        // pointers these were 32 scalar LD.E per chunk and thread)
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          float a = fmaf(v[e], sscale[c0 + cb + e], sshift[c0 + cb + e]);
-          float b = fmaf(v[e + 1], sscale[c0 + cb + e + 1], sshift[c0 + cb + e + 1]);
-          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-          pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        for (int e = 0; e < 16; e += 4) {
+          const float4 sc = tc::lds_v4(sscale_u32 + 4u * (uint32_t)(c0 + cb + e));
+          const float4 sh = tc::lds_v4(sshift_u32 + 4u * (uint32_t)(c0 + cb + e));
+          float a0 = fmaf(v[e], sc.x, sh.x), a1 = fmaf(v[e + 1], sc.y, sh.y);
+          float a2 = fmaf(v[e + 2], sc.z, sh.z), a3 = fmaf(v[e + 3], sc.w, sh.w);
+          if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(a0, a1), h1 = __floats2bfloat162_rn(a2, a3);
+          pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[(e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
         }
         if (gm < p.M) {
           uint4* dst = reinterpret_cast<uint4*>(orow + cb);
