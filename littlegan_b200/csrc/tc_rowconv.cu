@@ -277,6 +277,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     // ------------------------------------------------------------ epilogue: one thread per pixel of a stage;
     // warp group 0 takes the even stages of the CTA's stage sequence, group 1 the odd ones
     const int q = warp & 3, grp = warp >> 2;
+    const uint32_t sbias_u32 = tc::smem_u32(sbias);
     // pixel of the stage held by this thread's TMEM lane: M = 64 rows 16q..16q+15 of output row `sub`
     const int m = (MM == 64) ? (lane >> 4) * 64 + q * 16 + (lane & 15) : q * 32 + lane;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
@@ -310,7 +311,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
               float a[16];
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
-                const float4 sb = *reinterpret_cast<const float4*>(sbias + cb + 16 * h + e);
+                const float4 sb = tc::lds_v4(sbias_u32 + 4u * (uint32_t)(cb + 16 * h + e));   // shared window
                 a[e] = v[16 * h + e] + sb.x; a[e + 1] = v[16 * h + e + 1] + sb.y;
                 a[e + 2] = v[16 * h + e + 2] + sb.z; a[e + 3] = v[16 * h + e + 3] + sb.w;
               }

@@ -204,6 +204,7 @@ tc_rowdgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const RgParams p) {
   } else {
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3, grp = warp >> 2;
+    const uint32_t sbias_u32 = tc::smem_u32(sbias);
     const int sub = lane >> 4, j = q * 16 + (lane & 15);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const int nstage = p.R / 2;
@@ -230,7 +231,7 @@ tc_rowdgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const RgParams p) {
             uint32_t pk[16];
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
-              const float4 sb4 = *reinterpret_cast<const float4*>(sbias + e);
+              const float4 sb4 = tc::lds_v4(sbias_u32 + 4u * (uint32_t)e);     // shared window, not a generic LD.E
               const float a0 = v[e] + sb4.x, a1 = v[e + 1] + sb4.y, a2 = v[e + 2] + sb4.z, a3 = v[e + 3] + sb4.w;
               s1 += (a0 + a1) + (a2 + a3);
               s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
