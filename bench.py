@@ -188,12 +188,12 @@ def dominant_kernel_roofline(peaks):
     return {"bound": "tensor", "kernel": "tc_conv_kernel<dgrad> dec2 (16x16x256 -> 32x32x128), batch %d" % N,
             "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
             "peak_source": peaks["src"] + " bf16 burst", "ms_per_launch": ms,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-            # (profiles/r1_ncu_tc_dgrad_dec2.txt): 18.69 MB + 0.12 MB; algorithmic input bytes 18.4 MB, the
-            # 33.6 MB output stays in the 126 MB L2 for the kernel's lifetime
-            "traffic": 18.8e6, "traffic_unit": "bytes/launch",
-            "traffic_source": "profiles/r1_ncu_tc_dgrad_dec2.txt (ncu --set full of this launch; not re-measured "
-                              "by this run)"}
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture of
+            # the round's final build (profiles/r2_ncu_tc_dgrad_dec2.txt): 18.48 MB + 0.05 MB (tensor pipe 57.6% active);
+            # algorithmic input bytes 18.4 MB, the 33.6 MB output stays in the 126 MB L2 for the kernel's lifetime
+            "traffic": 18.53e6, "traffic_unit": "bytes/launch",
+            "traffic_source": "profiles/r2_ncu_tc_dgrad_dec2.txt (ncu --set full of this launch, final build of the "
+                              "round; not re-measured by this run)"}
 
 
 def _time_launch(fn, flush, reps=10, warm=3):
