@@ -37,10 +37,11 @@ E_MAC, DC_MAC = 596.4e6, 825.8e6
 STEP_FLOP_PER_IMG = 2 * (7 * DC_MAC + 12 * E_MAC)      # 25.88 GFLOP executed, adjuster on
 # DRAM bytes of one captured step at batch 64: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 152
 # launches of one graph replay (an offline measurement - ncu serialises and cold-starts every launch, so this is an
-# upper bound of the replayed step's traffic; scripts/ncu_step_dram.py over profiles/r2_launches_bench.csv)
-STEP_DRAM_BYTES = {"bytes": 6.333e9, "read": 5.557e9, "write": 0.777e9, "hbm_floor_ms": 6.333e9 / 6484.6e9 * 1e3,
-                   "source": "profiles/r2_step_dram_start.txt (ncu launch list of `bench.py --steps 1 --warmup 3`; "
-                             "not re-measured by this run)"}
+# upper bound of the replayed step's traffic; scripts/ncu_step_dram.py over profiles/r2_launches_bench_final.csv)
+STEP_DRAM_BYTES = {"bytes": 6.348e9, "read": 5.582e9, "write": 0.766e9, "hbm_floor_ms": 6.348e9 / 6484.6e9 * 1e3,
+                   "cold_serialised_kernel_ms": 3.947,
+                   "source": "profiles/r2_step_dram_final.txt (ncu launch list of `bench.py --steps 1 --warmup 3`, "
+                             "final build of the round; not re-measured by this run)"}
 
 
 def _peaks():
