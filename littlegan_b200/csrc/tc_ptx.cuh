@@ -222,8 +222,13 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (.release at CTA scope, the CUTLASS form):
+// the explicit `.release.cluster` form compiled to MEMBAR.ALL.GPU + ERRBAR, i.e. every epilogue warp waited for all its
+// global stores to drain before it could hand the accumulator back (20% of the pair kernels' epilogue stall samples,
+// profiles/r2_ncu_tc_dgrad_dec2.txt).  What the consumer (the MMA issuer) needs ordered are this warp's TMEM reads,
+// and those are complete (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync) before the arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
                                                 int c1, int c2) {
