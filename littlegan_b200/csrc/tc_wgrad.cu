@@ -19,6 +19,7 @@
 // issue rate (6 instructions = ~350 ns per stage against ~190 ns of MMAs).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -214,6 +215,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmBig, const __grid_constant
   }
 }
 
+// Fixed cost of a CTA lifetime (prologue, pipeline fill, reduction epilogue) in k-block times, for the split-K choice.
+// 12 was measured before the producer warps tripled the main loop's rate; a k-block is now so much shorter that
+// the same fixed cost is worth 20-30 of them (enc4 at batch 128: 3 waves of 32 k-blocks 51.6 us, 2 waves of 64
+// k-blocks 45.9 us; 20 .. 45 choose the same splits on every layer of the model).
+inline int wg_overhead() {
+  static const int v = getenv("LG_WG_OVERHEAD") ? atoi(getenv("LG_WG_OVERHEAD")) : 24;
+  return v;
+}
+
 // A = channels of `big` as stored (16, 32, 64 or a multiple of 128); A_real <= A rows of dW per tap.
 bool plan_wgrad(int Nimg, int Hb, int Wb, int A, int A_real, int B, int s, WgParams* p) {
   if (s != 1 && s != 2) return false;
@@ -246,7 +256,7 @@ bool plan_wgrad(int Nimg, int Hb, int Wb, int A, int A_real, int B, int s, WgPar
   // Split K so that the CTAs (one per SM: a CTA holds ~200 KB of shared memory) come in WHOLE waves: with
   // tiles x slices just above a multiple of the SM count the last wave runs a handful of CTAs on an otherwise
   // idle GPU (300 CTAs on 148 SMs took three CTA lifetimes instead of two).  Cost of a candidate =
-  // waves x (k-blocks per CTA + a fixed prologue / pipeline fill / reduction epilogue of ~12 k-block times).
+  // waves x (k-blocks per CTA + a fixed prologue / pipeline fill / reduction epilogue of wg_overhead() k-block times).
   const int tiles = p->groups * p->a_tiles * p->n_tiles;
   const int sms = lg_num_sms();
   const int max_slices = (p->total_kb + 3) / 4;           // at least ~4 k-blocks per CTA
@@ -258,7 +268,7 @@ bool plan_wgrad(int Nimg, int Hb, int Wb, int A, int A_real, int B, int s, WgPar
     if (sl > max_slices) sl = max_slices;
     const int kbs = (p->total_kb + sl - 1) / sl;
     const int ctas = tiles * ((p->total_kb + kbs - 1) / kbs);
-    const long cost = (long)((ctas + sms - 1) / sms) * (kbs + 12);
+    const long cost = (long)((ctas + sms - 1) / sms) * (kbs + wg_overhead());
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_kbs = kbs; }
   }
   p->kb_per_slice = best_kbs;
