@@ -399,7 +399,11 @@ bool plan_rc(int Nimg, int Hb, int Wb, int A, int Cpad, int B, int s, bool with_
     if (p.Hs % R) continue;
     const int tiles = Nimg * (p.Hs / R);
     const int waves = (tiles + ctas - 1) / ctas;
-    const double eff = (double)tiles / ((double)waves * ctas) * (1.0 - 0.25 * 4.0 / (s * R + 4.0));
+    // the stride-2 RGB layer (15 MMAs per output row) pays the 5-row fill of every strip four times as dearly as
+    // the others (measured, batch 128: R = 4 / 8 / 16 / 32 -> 56.1 / 51.6 / 48.9 / 48.7 us; the 32-channel and the
+    // stride-1 layers are fastest at R = 8)
+    const double fill = (pl->CH == 1 && s == 2) ? 1.0 : 0.25;
+    const double eff = (double)tiles / ((double)waves * ctas) * (1.0 - fill * 4.0 / (s * R + 4.0));
     if (eff > best) { best = eff; bestR = R; }
   }
   if (const char* e = getenv("LG_RC_R")) { const int R = atoi(e); if (R >= 4 && p.Hs % R == 0 && R % 2 == 0) bestR = R; }   // tuning knob
