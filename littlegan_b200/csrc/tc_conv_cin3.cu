@@ -73,17 +73,20 @@ __device__ __forceinline__ void store_image_rows(const C3Params& p, uint8_t* sim
 template <int S>
 __device__ __forceinline__ void build_patches(const C3Params& p, const uint8_t* simg, uint8_t* sA, int m) {
   const int oi = m / p.BW, oj = m - oi * p.BW;
+  const uint32_t simg_u32 = tc::smem_u32(simg);
   uint32_t pk[KPAD / 2];
 #pragma unroll
   for (int i = 0; i < KPAD / 2; ++i) pk[i] = 0u;
 #pragma unroll
   for (int ky = 0; ky < 5; ++ky) {
-    const uint16_t* src = reinterpret_cast<const uint16_t*>(simg + (S * oi + ky) * p.pitch +
-                                                            (S * oj - p.pad + MARGIN) * 6);
+    // 15 bf16 of one kernel row, read through the shared window (behind the generic pointer these were 75 LD.E.U16
+    // per position and tile)
+    const uint32_t src = simg_u32 + (uint32_t)((S * oi + ky) * p.pitch + (S * oj - p.pad + MARGIN) * 6);
 #pragma unroll
     for (int t = 0; t < 15; ++t) {
       const int k = ky * 15 + t;
-      const uint32_t v = src[t];
+      uint32_t v;
+      asm volatile("{\n\t.reg .u16 h;\n\tld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"(src + 2u * (uint32_t)t));
       pk[k >> 1] |= (k & 1) ? (v << 16) : v;
     }
   }
