@@ -1,3 +1,4 @@
+# 8-GPU bench (with extras), per-step timeline and the same-box 1-GPU number: gpurun --gpus 8 -- bash scripts/r2_n8.sh
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518"
 (time timeout 300 $TR bench.py --gpus 8 --steps 20 --warmup 5) > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err
