@@ -181,6 +181,11 @@ __device__ __forceinline__ float4 lds_v4(uint32_t a) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint4 lds_v4u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
 // v[16] += bias[cb .. cb+15]: the bias table lives in shared memory behind a generic pointer, which made every read a
 // generic LD.E (15% of the epilogue's stall samples); read it through the shared window, 16 bytes at a time
 __device__ __forceinline__ void add_bias16(float (&v)[16], uint32_t sbias_u32, int cb) {

@@ -300,7 +300,7 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         if constexpr (NB) tc::mbar_wait(&zfull[zs], zphase);
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + tlane + (uint32_t)(acc * p.B);
-        const uint8_t* zr = sZ + (size_t)zs * p.z_slot_bytes + m * zrow_bytes;
+        const uint32_t zr_u32 = tc::smem_u32(sZ) + (uint32_t)(zs * p.z_slot_bytes + m * zrow_bytes);
         for (int cb = 0; cb < p.B; cb += 32) {
           float v[32];
           tc::tmem_ld32(taddr + cb, v);
@@ -317,8 +317,8 @@ tc_rowconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
               }
               if constexpr (NB) {
                 const int c0 = (cb >> 3) + 2 * h;                 // logical 16-byte chunk of the z row
-                const uint4 z0 = *reinterpret_cast<const uint4*>(zr + ((c0 ^ swz) << 4));
-                const uint4 z1 = *reinterpret_cast<const uint4*>(zr + (((c0 + 1) ^ swz) << 4));
+                const uint4 z0 = tc::lds_v4u(zr_u32 + (uint32_t)((c0 ^ swz) << 4));          // shared window (was LD.E.128)
+                const uint4 z1 = tc::lds_v4u(zr_u32 + (uint32_t)(((c0 + 1) ^ swz) << 4));
                 nb_chunk(a, z0, z1, coef, nb.alpha, s1, s2, pk);
               } else {
 #pragma unroll
